@@ -1,0 +1,76 @@
+// apa_kernels.h — internal (non-ABI) interface between the C-ABI dispatcher and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/apa.h"
+
+namespace apa {
+
+enum { MODE_PLAIN = 0, MODE_RELU = 1, MODE_SOFTMAX = 2 };
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = 32 * kConsumerWarps;
+constexpr int kFusedThreads = kConsumerThreads + 32;  // + 1 bulk-copy producer warp
+constexpr int kRowsPerStage = 4;
+constexpr int kVideoTile = 32;  // videos per phase-2 tile
+constexpr int kColTile = 16;    // classes per phase-2 pass
+
+// Parameters of the fused single-map (M == 1) kernel.  See apa_pool_fused.cu.
+struct FusedParams {
+  const float* X;        // [B, HW, C]
+  const float* attn_in;  // optional precomputed a_0 [B*HW] (attention source is not X); else nullptr
+  const float* attn_w[APA_MAX_RANK];  // r==0: [C] (unused if attn_in); r>=1: scalar
+  const float* attn_b[APA_MAX_RANK];  // scalars
+  const float* td_w[APA_MAX_RANK];    // [C, K]
+  const float* td_b[APA_MAX_RANK];    // [K]
+  float* logits;                      // [B/F, K]
+  float* attn_raw;                    // optional [B*HW]: a_0 before chain/relu/softmax
+  float* g;                           // workspace [B, R, C]: attention-weighted feature sums
+  float* sn;                          // workspace [B, R]: sum of attention weights (1 if softmax)
+  float* smx;                         // workspace [B, 2]: softmax (max, sum) per image
+  unsigned int* barrier;              // workspace control block (2 words)
+  int B, HW, C, K, R, F;
+  int do_phase1, do_phase2;           // fused: 1,1   split: (1,0) then (0,1)
+  float inv_scale;                    // 1 / (HW * F)
+};
+
+struct FusedPlan {
+  int Q;        // C / 1024
+  int rmax;     // 1 or APA_MAX_RANK (template instance)
+  int mode;     // MODE_*
+  int cluster;  // CTAs per image
+  int nclusters;
+  int fused;    // 1: single kernel + grid barrier
+  int cooperative;
+  size_t smem;
+};
+
+// Pick cluster size / grid for (B, HW, C, K) on the current device. Returns cudaSuccess or error.
+cudaError_t fused_make_plan(int B, int HW, int C, int K, int R, int mode, const ApaTuning* tuning,
+                            FusedPlan* plan);
+// Same decision without touching the device (assumes a 148-SM B200); for plan introspection on CPU.
+void fused_make_plan_nodevice(int B, int HW, int C, int K, int R, int mode, const ApaTuning* tuning,
+                              FusedPlan* plan);
+cudaError_t fused_launch(const FusedParams& p, const FusedPlan& plan, cudaStream_t stream);
+bool fused_supported(int C, int R);
+
+// ---- dense path (apa_dense.cu)
+// Y[m, col_off + n*col_stride] (row stride ldy) = act(sum_k X[m*ldx + k*xs] W[k,n] + bias[n])
+cudaError_t dense_gemm(const float* X, int ldx, int xs, const float* W, int ldw, const float* bias,
+                       float* Y, int ldy, int col_stride, int col_off, int M, int N, int Kd, int relu,
+                       cudaStream_t stream);
+// attention finalisation for M == 1 given raw a_0 (chain, relu, softmax) -> attn_out [B,HW,(R)]
+cudaError_t attn_finalize_m1(const float* a0, const float* const* attn_w, const float* const* attn_b,
+                             const float* smx, float* attn_out, int B, int HW, int R, int mode,
+                             cudaStream_t stream);
+// in-place spatial softmax / relu on A [B, HW, M]
+cudaError_t dense_softmax_hw(float* A, int B, int HW, int M, cudaStream_t stream);
+cudaError_t dense_relu(float* A, size_t n, cudaStream_t stream);
+// logits[v,k] = 1/(HW F) sum_f sum_hw sum_r A[b,hw,m(k),r] T[b,hw,k,r]
+cudaError_t dense_pool(const float* A, const float* T, float* logits, int B, int HW, int K, int M,
+                       int R, int F, cudaStream_t stream);
+cudaError_t gram_launch(int B, int HW, int C, const float* X, float* G, cudaStream_t stream);
+
+}  // namespace apa

@@ -1,0 +1,676 @@
+// apa_pool_fused.cu — the headline kernel: single-map (M == 1) attentional pooling, rank 1..4,
+// optional relu / spatial softmax, frame mean, for X[B,HW,C] fp32 -> logits[B/F,K].
+//
+// Replaces (reference, TF-1.1 graph): nets_factory.py:259-274 attention conv(s), :276-286 softmax /
+// relu, :299-309 top-down conv(s), :322-328 pool + rank sum, :350-352 squeeze, :354-374 frame mean.
+//
+// Math (exact re-association of the reference graph for M == 1):
+//   a_0[hw] = X[hw,:].w_0 + c_0 ;  a_r = w_r a_{r-1} + c_r  (the reference CHAINS the maps, Q1)
+//   A_r = relu / softmax_hw / identity (a_r)
+//   g_r[c] = sum_hw A_r[hw] X[hw,c] ,  s_r = sum_hw A_r[hw]
+//   logits[k] = 1/(HW F) sum_f sum_r ( g_r . B_r[:,k] + d_r[k] s_r )
+// i.e. the [HW,K] top-down map is never formed and X is read from HBM exactly once.
+//
+// Structure (one launch):
+//   phase 1  one thread-block CLUSTER of p CTAs per image; CTA q owns rows [q HW/p, (q+1) HW/p).
+//            warp 8 lane 0 streams 4-row x C tiles HBM -> smem with cp.async.bulk (TMA engine, UBLKCP)
+//            through a 5/6-stage mbarrier ring; 8 consumer warps each own C/8 channels: per tile they
+//            form partial dots, one named barrier combines them into a[row], then they accumulate
+//            g (8 channels per thread per rank, in registers).  At the end of an image the p partial
+//            g vectors are combined through distributed shared memory (each CTA reduces C/p channels)
+//            with the softmax max/sum merge, and written once to a [B,R,C] workspace.
+//   barrier  self-resetting grid barrier (all CTAs co-resident; cooperative launch when available)
+//   phase 2  logits = g . B  as a register-tiled fp32 SIMT GEMM: cluster -> class slice, CTA in
+//            cluster -> channel slice, partial sums combined through DSMEM (deterministic, no atomics).
+#include "apa_common.cuh"
+#include "apa_kernels.h"
+
+#include <atomic>
+#include <mutex>
+
+namespace apa {
+
+namespace {
+
+template <int Q, int RMAX>
+struct Smem {
+  static constexpr int C = Q * 1024;
+  static constexpr int kStages = (RMAX == 1) ? 6 : 5;
+  static constexpr size_t kStageBytes = size_t(kRowsPerStage) * C * 4;
+  static constexpr size_t kRing = kStages * kStageBytes;
+  static constexpr size_t kOffRed = kRing;                       // float red[RMAX][C]
+  static constexpr size_t kOffPart = kOffRed + size_t(RMAX) * C * 4;  // float part[2][rows][8]
+  static constexpr size_t kOffStats = kOffPart + 2 * kRowsPerStage * 8 * 4;  // float stats[8]
+  static constexpr size_t kOffScl = kOffStats + 32;              // float scl[16]
+  static constexpr size_t kOffBars = kOffScl + 64;               // u64 full[8] empty[8] ready free
+  static constexpr size_t kTotal = kOffBars + 8 * 18;
+  // phase-2 carve inside the ring
+  static constexpr int kChunk = (Q == 1) ? 256 : 512;            // channels per smem chunk
+  static constexpr int kChunkPad = kChunk + 4;
+  static constexpr size_t kOffG = 0;                             // float gS[32][kChunkPad]
+  static constexpr size_t kOffW = kOffG + size_t(kVideoTile) * kChunkPad * 4;  // float Ws[kChunk][16]
+  static constexpr size_t kOffAcc = kOffW + size_t(kChunk) * kColTile * 4;     // float accS[8][32][16]
+  static constexpr size_t kOffOut = kOffAcc + size_t(kConsumerWarps) * kVideoTile * kColTile * 4;
+  static constexpr size_t kPhase2End = kOffOut + size_t(kVideoTile) * kColTile * 4;
+  static_assert(kPhase2End <= kRing, "phase-2 scratch must fit in the stage ring");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ void axpy4(float* f, float a, const float4& x) {
+  f[0] = fmaf(a, x.x, f[0]);
+  f[1] = fmaf(a, x.y, f[1]);
+  f[2] = fmaf(a, x.z, f[2]);
+  f[3] = fmaf(a, x.w, f[3]);
+}
+
+template <int Q, int RMAX, int MODE>
+__global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const FusedParams p) {
+  using L = Smem<Q, RMAX>;
+  constexpr int C = L::C;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* red = reinterpret_cast<float*>(smem + L::kOffRed);
+  float* partS = reinterpret_cast<float*>(smem + L::kOffPart);
+  float* stats = reinterpret_cast<float*>(smem + L::kOffStats);
+  float* scl = reinterpret_cast<float*>(smem + L::kOffScl);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 8;
+  uint64_t* parts_ready = bars + 16;
+  uint64_t* parts_free = bars + 17;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t csize = cluster_nctarank();
+  const uint32_t crank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / csize;
+  const int nclusters = gridDim.x / csize;
+  const int R = p.R;
+
+  if (tid == 0) {
+    for (int i = 0; i < L::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kConsumerWarps);
+    }
+    mbar_init(parts_ready, csize);
+    mbar_init(parts_free, csize);
+    fence_mbar_init();
+  }
+  cluster_sync_all();  // barrier inits visible cluster-wide before any remote arrive
+
+  // Warm L2 with this CTA's phase-2 weight slice while phase 1 streams X.
+  if (p.do_phase1 && p.do_phase2 && tid < kConsumerThreads) {
+    const int k_lo = int((long long)p.K * cluster_id / nclusters);
+    const int k_hi = int((long long)p.K * (cluster_id + 1) / nclusters);
+    const int Cp = C / int(csize);
+    if (k_hi > k_lo) {
+      for (int j = 0; j < R; ++j)
+        for (int c = tid; c < Cp; c += kConsumerThreads) {
+          const float* row = p.td_w[j] + size_t(crank * Cp + c) * p.K;
+          prefetch_l2(row + k_lo);
+          prefetch_l2(row + k_hi - 1);
+        }
+    }
+  }
+
+  // =========================================================================== phase 1
+  if (p.do_phase1) {
+    const int row_lo = int((long long)p.HW * crank / csize);
+    const int row_hi = int((long long)p.HW * (crank + 1) / csize);
+    if (warp == kConsumerWarps) {
+      // ------------------------------------------------ producer: one lane drives the copy engine
+      if (lane == 0) {
+        const uint64_t pol = l2_policy_evict_first();
+        uint32_t stage = 0, phase = 0;
+        for (int b = cluster_id; b < p.B; b += nclusters) {
+          const float* xb = p.X + (size_t(b) * p.HW) * C;
+          for (int t0 = row_lo; t0 < row_hi; t0 += kRowsPerStage) {
+            const int rows = min(kRowsPerStage, row_hi - t0);
+            const uint32_t bytes = uint32_t(rows) * C * 4u;
+            mbar_wait(&empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            bulk_g2s(smem + stage * L::kStageBytes, xb + size_t(t0) * C, bytes, &full[stage], pol);
+            if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else {
+      // ------------------------------------------------ consumers: warp w owns channels [w C/8, (w+1) C/8)
+      const int col0 = warp * (C / kConsumerWarps) + lane * 4;  // + q*128
+      float4 wv[Q];
+      float c0 = 0.f;
+      if (p.attn_in == nullptr) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) wv[q] = __ldg(reinterpret_cast<const float4*>(p.attn_w[0] + col0 + q * 128));
+        c0 = __ldg(p.attn_b[0]);
+      }
+      float cw[RMAX], cb[RMAX];  // chain coefficients a_r = cw[r] a_{r-1} + cb[r], r >= 1
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) {
+        cw[j] = (j >= 1 && j < R) ? __ldg(p.attn_w[j]) : 0.f;
+        cb[j] = (j >= 1 && j < R) ? __ldg(p.attn_b[j]) : 0.f;
+      }
+      uint32_t stage = 0, phase = 0, tile_ctr = 0, img_iter = 0;
+      for (int b = cluster_id; b < p.B; b += nclusters, ++img_iter) {
+        float f[RMAX][Q * 4];
+        float s[RMAX];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) {
+          s[j] = 0.f;
+#pragma unroll
+          for (int i = 0; i < Q * 4; ++i) f[j][i] = 0.f;
+        }
+        for (int t0 = row_lo; t0 < row_hi; t0 += kRowsPerStage, ++tile_ctr) {
+          const int rows = min(kRowsPerStage, row_hi - t0);
+          const float* st = reinterpret_cast<const float*>(smem + stage * L::kStageBytes);
+          mbar_wait(&full[stage], phase);
+          float4 x[kRowsPerStage][Q];
+#pragma unroll
+          for (int r = 0; r < kRowsPerStage; ++r)
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+              x[r][q] = (r < rows) ? *reinterpret_cast<const float4*>(st + r * C + col0 + q * 128)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          float a[kRowsPerStage];
+          if (p.attn_in == nullptr) {
+            float pd[kRowsPerStage];
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r) {
+              pd[r] = 0.f;
+#pragma unroll
+              for (int q = 0; q < Q; ++q) pd[r] += dot4(x[r][q], wv[q]);
+            }
+            // x is in registers now: hand the stage back to the copy engine
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r) pd[r] = warp_sum(pd[r]);
+            float* part = partS + (tile_ctr & 1u) * (kRowsPerStage * 8);
+            if (lane == 0) {
+#pragma unroll
+              for (int r = 0; r < kRowsPerStage; ++r) part[r * 8 + warp] = pd[r];
+            }
+            named_bar_sync(1, kConsumerThreads);
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r) {
+              const float4 p0 = *reinterpret_cast<const float4*>(part + r * 8);
+              const float4 p1 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
+              a[r] = c0 + (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w)));
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r)
+              a[r] = (r < rows) ? __ldg(p.attn_in + size_t(b) * p.HW + t0 + r) : 0.f;
+          }
+          if (p.attn_raw != nullptr && tid == 0) {
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r)
+              if (r < rows) p.attn_raw[size_t(b) * p.HW + t0 + r] = a[r];
+          }
+          if (MODE == MODE_SOFTMAX) {
+            float tmax = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r)
+              if (r < rows) tmax = fmaxf(tmax, a[r]);
+            const float mnew = fmaxf(mx, tmax);
+            const float sc = expf(mx - mnew);  // exp(-inf) == 0 on the first tile
+            mx = mnew;
+            s[0] *= sc;
+#pragma unroll
+            for (int i = 0; i < Q * 4; ++i) f[0][i] *= sc;
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r) {
+              if (r < rows) {
+                const float e = expf(a[r] - mx);
+                s[0] += e;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) axpy4(&f[0][q * 4], e, x[r][q]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r) {
+              if (r < rows) {
+                float ar = a[r];
+#pragma unroll
+                for (int j = 0; j < RMAX; ++j) {
+                  if (j < R) {
+                    if (j >= 1) ar = fmaf(cw[j], ar, cb[j]);
+                    const float A = (MODE == MODE_RELU) ? fmaxf(ar, 0.f) : ar;
+                    s[j] += A;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) axpy4(&f[j][q * 4], A, x[r][q]);
+                  }
+                }
+              }
+            }
+          }
+          if (p.attn_in != nullptr) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+          }
+          if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+        }
+
+        // ---------------------------------------------- combine the p row-slices of image b (DSMEM)
+        if (img_iter > 0) mbar_wait_cluster(parts_free, (img_iter - 1) & 1u);  // my red buffer is free
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j)
+          if (j < R)
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+              *reinterpret_cast<float4*>(red + j * C + col0 + q * 128) =
+                  make_float4(f[j][q * 4 + 0], f[j][q * 4 + 1], f[j][q * 4 + 2], f[j][q * 4 + 3]);
+        if (tid == 0) {
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) stats[j] = s[j];
+          stats[4] = mx;
+        }
+        named_bar_sync(1, kConsumerThreads);
+        if (tid < int(csize)) mbar_arrive_cluster(parts_ready, tid);
+        mbar_wait_cluster(parts_ready, img_iter & 1u);  // every CTA's partial is visible
+
+        if (tid < 16) {
+          float v = 1.f;
+          if (MODE == MODE_SOFTMAX) {
+            v = 0.f;
+            if (tid < int(csize)) {
+              float M = -INFINITY;
+              for (uint32_t q = 0; q < csize; ++q) M = fmaxf(M, ld_dsmem_f(dsmem_addr(&stats[4], q)));
+              float S = 0.f;
+              for (uint32_t q = 0; q < csize; ++q)
+                S += expf(ld_dsmem_f(dsmem_addr(&stats[4], q)) - M) * ld_dsmem_f(dsmem_addr(&stats[0], q));
+              v = expf(ld_dsmem_f(dsmem_addr(&stats[4], tid)) - M) / S;
+              if (tid == 0 && crank == 0) {
+                p.smx[2 * b + 0] = M;
+                p.smx[2 * b + 1] = S;
+              }
+            }
+          }
+          scl[tid] = v;
+        }
+        named_bar_sync(1, kConsumerThreads);
+        {
+          const int Cp = C / int(csize);
+          const int n4 = Cp / 4;
+          for (int idx = tid; idx < R * n4; idx += kConsumerThreads) {
+            const int j = idx / n4;
+            const int c = int(crank) * Cp + (idx - j * n4) * 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t q = 0; q < csize; ++q) {
+              const float4 v = ld_dsmem_f4(dsmem_addr(red + j * C + c, q));
+              const float sc = scl[q];
+              acc.x = fmaf(sc, v.x, acc.x);
+              acc.y = fmaf(sc, v.y, acc.y);
+              acc.z = fmaf(sc, v.z, acc.z);
+              acc.w = fmaf(sc, v.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(p.g + (size_t(b) * R + j) * C + c) = acc;
+          }
+          if (crank == 0 && tid < R) {
+            float S = 1.f;
+            if (MODE != MODE_SOFTMAX) {
+              S = 0.f;
+              for (uint32_t q = 0; q < csize; ++q) S += ld_dsmem_f(dsmem_addr(&stats[tid], q));
+            }
+            p.sn[size_t(b) * R + tid] = S;
+          }
+        }
+        named_bar_sync(1, kConsumerThreads);
+        if (tid < int(csize)) mbar_arrive_cluster(parts_free, tid);  // done reading everyone's smem
+      }
+      // nobody may still be reading my shared memory when I move on / exit
+      if (img_iter > 0) mbar_wait_cluster(parts_free, (img_iter - 1) & 1u);
+    }
+  }
+
+  if (p.do_phase1 && p.do_phase2) grid_barrier(p.barrier, gridDim.x);
+  if (!p.do_phase2) return;
+
+  // =========================================================================== phase 2
+  {
+    float* gS = reinterpret_cast<float*>(smem + L::kOffG);
+    float* Ws = reinterpret_cast<float*>(smem + L::kOffW);
+    float* accS = reinterpret_cast<float*>(smem + L::kOffAcc);
+    float* outP = reinterpret_cast<float*>(smem + L::kOffOut);
+    constexpr int CHP = L::kChunkPad;
+    const int Cp = C / int(csize);
+    const int c_base = int(crank) * Cp;
+    const int CHc = min(L::kChunk, Cp);
+    const int Bv = p.B / p.F;
+    const int k_lo = int((long long)p.K * cluster_id / nclusters);
+    const int k_hi = int((long long)p.K * (cluster_id + 1) / nclusters);
+    const int ig = lane >> 2, cg = lane & 3;
+
+    for (int v0 = 0; v0 < Bv; v0 += kVideoTile) {
+      for (int kp = k_lo; kp < k_hi; kp += kColTile) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) acc[i][t] = 0.f;
+
+        for (int j = 0; j < R; ++j) {
+          for (int cc = 0; cc < Cp; cc += CHc) {
+            __syncthreads();
+            const int c4n = CHc >> 2;
+            for (int idx = tid; idx < kVideoTile * c4n; idx += kFusedThreads) {
+              const int row = idx / c4n, c4 = idx - row * c4n;
+              const int v = v0 + row;
+              float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (v < Bv) {
+                for (int fr = 0; fr < p.F; ++fr) {
+                  const float4 t = ldg_cg_f4(p.g + (size_t(v * p.F + fr) * R + j) * C + c_base + cc + c4 * 4);
+                  sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+                }
+              }
+              *reinterpret_cast<float4*>(gS + row * CHP + c4 * 4) = sum;
+            }
+            const float* Wj = p.td_w[j];
+            for (int idx = tid; idx < CHc * kColTile; idx += kFusedThreads) {
+              const int c = idx >> 4, kk = idx & 15;
+              const int k = kp + kk;
+              Ws[idx] = (k < k_hi) ? __ldg(Wj + size_t(c_base + cc + c) * p.K + k) : 0.f;
+            }
+            __syncthreads();
+            if (tid < kConsumerThreads) {
+              const int cw = CHc / kConsumerWarps;
+              const int c_begin = warp * cw;
+              for (int c = c_begin; c < c_begin + cw; c += 4) {
+                float4 gv[4], wv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gv[i] = *reinterpret_cast<const float4*>(gS + (ig + 8 * i) * CHP + c);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) wv[t] = *reinterpret_cast<const float4*>(Ws + (c + t) * kColTile + cg * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  acc[i][0] = fmaf(gv[i].x, wv[0].x, acc[i][0]);
+                  acc[i][1] = fmaf(gv[i].x, wv[0].y, acc[i][1]);
+                  acc[i][2] = fmaf(gv[i].x, wv[0].z, acc[i][2]);
+                  acc[i][3] = fmaf(gv[i].x, wv[0].w, acc[i][3]);
+                  acc[i][0] = fmaf(gv[i].y, wv[1].x, acc[i][0]);
+                  acc[i][1] = fmaf(gv[i].y, wv[1].y, acc[i][1]);
+                  acc[i][2] = fmaf(gv[i].y, wv[1].z, acc[i][2]);
+                  acc[i][3] = fmaf(gv[i].y, wv[1].w, acc[i][3]);
+                  acc[i][0] = fmaf(gv[i].z, wv[2].x, acc[i][0]);
+                  acc[i][1] = fmaf(gv[i].z, wv[2].y, acc[i][1]);
+                  acc[i][2] = fmaf(gv[i].z, wv[2].z, acc[i][2]);
+                  acc[i][3] = fmaf(gv[i].z, wv[2].w, acc[i][3]);
+                  acc[i][0] = fmaf(gv[i].w, wv[3].x, acc[i][0]);
+                  acc[i][1] = fmaf(gv[i].w, wv[3].y, acc[i][1]);
+                  acc[i][2] = fmaf(gv[i].w, wv[3].z, acc[i][2]);
+                  acc[i][3] = fmaf(gv[i].w, wv[3].w, acc[i][3]);
+                }
+              }
+            }
+          }
+        }
+        // combine the 8 channel-split warps, then the p channel-split CTAs
+        if (tid < kConsumerThreads) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(accS + (warp * kVideoTile + ig + 8 * i) * kColTile + cg * 4) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+        for (int o = tid; o < kVideoTile * kColTile; o += kFusedThreads) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < kConsumerWarps; ++w) sum += accS[w * kVideoTile * kColTile + o];
+          outP[o] = sum;
+        }
+        cluster_sync_all();
+        for (int o = int(crank) + int(csize) * tid; o < kVideoTile * kColTile; o += int(csize) * kFusedThreads) {
+          const int v = v0 + (o >> 4);
+          const int k = kp + (o & 15);
+          if (v < Bv && k < k_hi) {
+            float sum = 0.f;
+            for (uint32_t q = 0; q < csize; ++q) sum += ld_dsmem_f(dsmem_addr(outP + o, q));
+            for (int j = 0; j < R; ++j) {
+              float S = 0.f;
+              for (int fr = 0; fr < p.F; ++fr) S += ldg_cg_f(p.sn + size_t(v * p.F + fr) * R + j);
+              sum = fmaf(__ldg(p.td_b[j] + k), S, sum);
+            }
+            p.logits[size_t(v) * p.K + k] = sum * p.inv_scale;
+          }
+        }
+        cluster_sync_all();  // outP / accS are reused by the next pass; also guards exit
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- host side
+using KernelFn = void (*)(const FusedParams);
+
+template <int Q, int RMAX, int MODE>
+KernelFn kfn() {
+  return &apa_pool_fused_kernel<Q, RMAX, MODE>;
+}
+
+KernelFn select_kernel(int Q, int rmax, int mode) {
+  if (Q == 2) {
+    if (rmax == 1) {
+      if (mode == MODE_PLAIN) return kfn<2, 1, MODE_PLAIN>();
+      if (mode == MODE_RELU) return kfn<2, 1, MODE_RELU>();
+      return kfn<2, 1, MODE_SOFTMAX>();
+    }
+    if (mode == MODE_PLAIN) return kfn<2, APA_MAX_RANK, MODE_PLAIN>();
+    if (mode == MODE_RELU) return kfn<2, APA_MAX_RANK, MODE_RELU>();
+    return nullptr;
+  }
+  if (Q == 1) {
+    if (rmax == 1) {
+      if (mode == MODE_PLAIN) return kfn<1, 1, MODE_PLAIN>();
+      if (mode == MODE_RELU) return kfn<1, 1, MODE_RELU>();
+      return kfn<1, 1, MODE_SOFTMAX>();
+    }
+    if (mode == MODE_PLAIN) return kfn<1, APA_MAX_RANK, MODE_PLAIN>();
+    if (mode == MODE_RELU) return kfn<1, APA_MAX_RANK, MODE_RELU>();
+    return nullptr;
+  }
+  return nullptr;
+}
+
+size_t smem_bytes(int Q, int rmax) {
+  if (Q == 2) return rmax == 1 ? Smem<2, 1>::kTotal : Smem<2, APA_MAX_RANK>::kTotal;
+  return rmax == 1 ? Smem<1, 1>::kTotal : Smem<1, APA_MAX_RANK>::kTotal;
+}
+
+// max co-resident clusters per (device, kernel, cluster size); filled lazily, immutable afterwards.
+struct OccCache {
+  std::mutex mu;
+  struct Entry { int dev; KernelFn fn; int cluster; int nmax; };
+  Entry e[64];
+  int n = 0;
+};
+OccCache g_occ;
+
+cudaError_t max_clusters(KernelFn fn, size_t smem, int cluster, int* out) {
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  {
+    std::lock_guard<std::mutex> lk(g_occ.mu);
+    for (int i = 0; i < g_occ.n; ++i)
+      if (g_occ.e[i].dev == dev && g_occ.e[i].fn == fn && g_occ.e[i].cluster == cluster) {
+        *out = g_occ.e[i].nmax;
+        return cudaSuccess;
+      }
+  }
+  err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (err != cudaSuccess) return err;
+  if (cluster > 8) {
+    err = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (err != cudaSuccess) return err;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster, 1, 1);
+  cfg.blockDim = dim3(kFusedThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  err = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    n = 0;  // this cluster size is not launchable here
+  }
+  std::lock_guard<std::mutex> lk(g_occ.mu);
+  if (g_occ.n < 64) g_occ.e[g_occ.n++] = {dev, fn, cluster, n};
+  *out = n;
+  return cudaSuccess;
+}
+
+// nominal B200 capacity (148 SMs in 8 GPCs of 16/18/20) for device-less planning
+int nominal_max_clusters(int cluster) {
+  switch (cluster) {
+    case 1: return 148;
+    case 2: return 74;
+    case 4: return 33;
+    case 8: return 16;
+    default: return 8;
+  }
+}
+
+void choose(int B, int HW, int C, const ApaTuning* tuning, const int nmax[5], FusedPlan* plan) {
+  static const int cand[5] = {1, 2, 4, 8, 16};
+  int best = -1;
+  long long best_cost = 0;
+  const int forced = tuning ? tuning->cluster_size : 0;
+  for (int i = 0; i < 5; ++i) {
+    const int cs = cand[i];
+    if (forced > 0 && cs != forced) continue;
+    if (nmax[i] <= 0) continue;
+    if ((C / cs) % 32 != 0 || C % cs != 0) continue;
+    int ncl = nmax[i];
+    if (tuning && tuning->max_ctas > 0) ncl = ncl < tuning->max_ctas / cs ? ncl : tuning->max_ctas / cs;
+    if (ncl <= 0) continue;
+    const long long waves = (B + ncl - 1) / ncl;
+    const long long rows = (HW + cs - 1) / cs;
+    // time ~ waves * (rows + fixed per-image cost in row units); ties -> smaller cluster
+    const long long cost = waves * (rows + 3);
+    if (best < 0 || cost < best_cost) {
+      best = i;
+      best_cost = cost;
+    }
+  }
+  if (best < 0) {
+    plan->cluster = 0;
+    plan->nclusters = 0;
+    return;
+  }
+  int ncl = nmax[best];
+  if (tuning && tuning->max_ctas > 0 && ncl > tuning->max_ctas / cand[best]) ncl = tuning->max_ctas / cand[best];
+  if (ncl > B) ncl = B;
+  plan->cluster = cand[best];
+  plan->nclusters = ncl;
+}
+
+void fill_common(int C, int R, int mode, const ApaTuning* tuning, FusedPlan* plan) {
+  plan->Q = C / 1024;
+  plan->rmax = (R == 1) ? 1 : APA_MAX_RANK;
+  plan->mode = mode;
+  plan->smem = smem_bytes(plan->Q, plan->rmax);
+  plan->fused = (tuning && tuning->fused == 0) ? 0 : 1;
+  plan->cooperative = 0;
+}
+
+}  // namespace
+
+bool fused_supported(int C, int R) {
+  return (C == 1024 || C == 2048) && R >= 1 && R <= APA_MAX_RANK;
+}
+
+void fused_make_plan_nodevice(int B, int HW, int C, int K, int R, int mode, const ApaTuning* tuning,
+                              FusedPlan* plan) {
+  (void)K;
+  fill_common(C, R, mode, tuning, plan);
+  int nmax[5];
+  static const int cand[5] = {1, 2, 4, 8, 16};
+  for (int i = 0; i < 5; ++i) nmax[i] = nominal_max_clusters(cand[i]);
+  choose(B, HW, C, tuning, nmax, plan);
+}
+
+cudaError_t fused_make_plan(int B, int HW, int C, int K, int R, int mode, const ApaTuning* tuning,
+                            FusedPlan* plan) {
+  (void)K;
+  fill_common(C, R, mode, tuning, plan);
+  KernelFn fn = select_kernel(plan->Q, plan->rmax, mode);
+  if (fn == nullptr) return cudaErrorInvalidValue;
+  int nmax[5];
+  static const int cand[5] = {1, 2, 4, 8, 16};
+  for (int i = 0; i < 5; ++i) {
+    cudaError_t err = max_clusters(fn, plan->smem, cand[i], &nmax[i]);
+    if (err != cudaSuccess) return err;
+  }
+  choose(B, HW, C, tuning, nmax, plan);
+  if (plan->cluster == 0) return cudaErrorInvalidConfiguration;
+  int dev = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  plan->cooperative = (coop && !(tuning && tuning->no_cooperative)) ? 1 : 0;
+  return cudaSuccess;
+}
+
+namespace {
+std::atomic<int> g_coop_refused{0};  // set once if the driver refuses cooperative + cluster launches
+
+cudaError_t launch_one(KernelFn fn, const FusedParams& p, const FusedPlan& plan, bool coop,
+                       cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.cluster * plan.nclusters, 1, 1);
+  cfg.blockDim = dim3(kFusedThreads, 1, 1);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = plan.cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  int na = 1;
+  if (coop) {
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    na = 2;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, fn, p);
+}
+}  // namespace
+
+cudaError_t fused_launch(const FusedParams& p, const FusedPlan& plan, cudaStream_t stream) {
+  KernelFn fn = select_kernel(plan.Q, plan.rmax, plan.mode);
+  if (fn == nullptr) return cudaErrorInvalidValue;
+  if (plan.fused) {
+    FusedParams q = p;
+    q.do_phase1 = 1;
+    q.do_phase2 = 1;
+    if (plan.cooperative && !g_coop_refused.load(std::memory_order_relaxed)) {
+      cudaError_t err = launch_one(fn, q, plan, true, stream);
+      if (err == cudaSuccess) return err;
+      (void)cudaGetLastError();  // cooperative+cluster refused: the grid is still sized to be co-resident
+      g_coop_refused.store(1, std::memory_order_relaxed);
+    }
+    return launch_one(fn, q, plan, false, stream);
+  }
+  FusedParams q = p;
+  q.do_phase1 = 1;
+  q.do_phase2 = 0;
+  cudaError_t err = launch_one(fn, q, plan, false, stream);
+  if (err != cudaSuccess) return err;
+  q.do_phase1 = 0;
+  q.do_phase2 = 1;
+  return launch_one(fn, q, plan, false, stream);
+}
+
+}  // namespace apa

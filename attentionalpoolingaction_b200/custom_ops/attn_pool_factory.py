@@ -1,0 +1,393 @@
+"""Loader + thin Python wrappers for the B200 attentional-pooling library.
+
+Mirrors the reference's op packaging (src/custom_ops/custom_ops_factory.py:7-28): the shared
+library sits next to this file, is loaded by absolute path at import time, and each entry
+point is wrapped by a same-named Python function.  The reference loads with
+`tf.load_op_library`; here the boundary is a plain C ABI (include/apa.h) loaded with ctypes.
+PyTorch tensors are only containers for device memory and the CUDA stream.
+
+There is NO CPU fallback: importing without the built library raises, and calling without
+an sm_100 device returns the library's error.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from collections import OrderedDict
+
+cur_path = os.path.realpath(__file__)
+ROOT_PATH = os.path.dirname(cur_path)
+LIB_NAME = "libapa_attn_pool.so"
+LIB_PATH = os.path.join(ROOT_PATH, LIB_NAME)
+
+APA_ABI_VERSION = 1
+APA_MAX_RANK = 4
+APA_FLAG_SINGLE_LAYER_ATT = 1 << 0
+APA_FLAG_SOFTMAX_ATT = 1 << 1
+APA_FLAG_RELU_ATT = 1 << 2
+APA_FLAG_PER_CLASS = 1 << 3
+
+APA_OK = 0
+APA_ERR_NULL = -1
+APA_ERR_SHAPE = -2
+APA_ERR_RANK = -3
+APA_ERR_SOFTMAX_RANK = -4
+APA_ERR_WORKSPACE = -5
+APA_ERR_UNSUPPORTED = -6
+APA_ERR_ALIGN = -7
+APA_ERR_DEVICE = -8
+
+# every symbol include/apa.h declares (tests/test_abi.py checks the header against this list)
+ABI_SYMBOLS = (
+    "apa_abi_version",
+    "apa_strerror",
+    "apa_attn_pool_check",
+    "apa_attn_pool_workspace",
+    "apa_attn_pool_workspace_init",
+    "apa_attn_pool_fwd",
+    "apa_attn_pool_fwd_host",
+    "apa_gram_fwd",
+    "apa_attn_pool_plan",
+)
+
+
+class ApaDesc(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_int32),
+        ("batch", ctypes.c_int32),
+        ("hw", ctypes.c_int32),
+        ("channels", ctypes.c_int32),
+        ("num_classes", ctypes.c_int32),
+        ("frames", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
+        ("pose_channels", ctypes.c_int32),
+        ("num_pose_keypoints", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 6),
+    ]
+
+
+_FP = ctypes.c_void_p  # const float* (device)
+
+
+class ApaWeights(ctypes.Structure):
+    _fields_ = [
+        ("attn_w", _FP * APA_MAX_RANK),
+        ("attn_b", _FP * APA_MAX_RANK),
+        ("topdown_w", _FP * APA_MAX_RANK),
+        ("topdown_b", _FP * APA_MAX_RANK),
+        ("pose_w", _FP),
+        ("pose_b", _FP),
+        ("pose_logits_w", _FP),
+        ("pose_logits_b", _FP),
+    ]
+
+
+class ApaTuning(ctypes.Structure):
+    _fields_ = [
+        ("cluster_size", ctypes.c_int32),
+        ("fused", ctypes.c_int32),
+        ("max_ctas", ctypes.c_int32),
+        ("no_cooperative", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 4),
+    ]
+
+
+class ApaError(RuntimeError):
+    def __init__(self, status, where=""):
+        self.status = int(status)
+        msg = _lib.apa_strerror(self.status).decode() if _lib is not None else "apa error"
+        super().__init__("%s%s (status %d)" % (where + ": " if where else "", msg, self.status))
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found next to %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C attentionalpoolingaction_b200/csrc`). There is no CPU fallback." % (LIB_NAME, cur_path))
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    lib.apa_abi_version.restype = c.c_int
+    lib.apa_abi_version.argtypes = []
+    lib.apa_strerror.restype = c.c_char_p
+    lib.apa_strerror.argtypes = [c.c_int]
+    lib.apa_attn_pool_check.restype = c.c_int
+    lib.apa_attn_pool_check.argtypes = [c.POINTER(ApaDesc)]
+    lib.apa_attn_pool_workspace.restype = c.c_size_t
+    lib.apa_attn_pool_workspace.argtypes = [c.POINTER(ApaDesc), c.c_int, c.c_int, c.c_int]
+    lib.apa_attn_pool_workspace_init.restype = c.c_int
+    lib.apa_attn_pool_workspace_init.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.apa_attn_pool_fwd.restype = c.c_int
+    lib.apa_attn_pool_fwd.argtypes = [c.POINTER(ApaDesc), c.c_void_p, c.POINTER(ApaWeights), c.c_void_p,
+                                      c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t,
+                                      c.POINTER(ApaTuning), c.c_void_p]
+    lib.apa_attn_pool_fwd_host.restype = c.c_int
+    lib.apa_attn_pool_fwd_host.argtypes = [c.POINTER(ApaDesc), c.c_void_p, c.POINTER(ApaWeights), c.c_void_p,
+                                           c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t,
+                                           c.POINTER(ApaTuning), c.c_void_p]
+    lib.apa_gram_fwd.restype = c.c_int
+    lib.apa_gram_fwd.argtypes = [c.c_int32, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.apa_attn_pool_plan.restype = c.c_int
+    lib.apa_attn_pool_plan.argtypes = [c.POINTER(ApaDesc), c.POINTER(ApaTuning), c.c_int, c.c_int, c.c_int,
+                                       c.POINTER(c.c_int32 * 8)]
+    if lib.apa_abi_version() != APA_ABI_VERSION:
+        raise ImportError("ABI mismatch: library %d, wrapper %d" % (lib.apa_abi_version(), APA_ABI_VERSION))
+    return lib
+
+
+_lib = None
+_lib = _load()
+attn_pool_lib = _lib  # like `pose_to_heatmap_fn = tf.load_op_library(...)` in the reference
+
+# TF variable names of the head (nets_factory.py:147-160, :243-303)
+POSE_W = "PoseLogits/ExtraConv2d_1x1/weights"
+POSE_B = "PoseLogits/ExtraConv2d_1x1/biases"
+POSE_LOGITS_W = "PoseLogits/Conv2d_1c_1x1/weights"
+POSE_LOGITS_B = "PoseLogits/Conv2d_1c_1x1/biases"
+
+
+def attn_scope(rank_id):
+    return "PosePrelogitsBasedAttention/Conv2d_PrePose_Attn" + (str(rank_id) if rank_id >= 1 else "")
+
+
+def topdown_scope(rank_id):
+    return "PosePrelogitsBasedAttention/Conv" + ("_%d" % rank_id if rank_id >= 1 else "")
+
+
+def flags_from_cfg_net(net):
+    """cfg.NET.* (src/config.py:182-209) -> (APA flag bits, rank).  `net` is attribute- or dict-like."""
+    def get(key, default):
+        full = "USE_POSE_PRELOGITS_BASED_ATTENTION_" + key
+        if isinstance(net, dict):
+            return net.get(full, net.get(key, default))
+        return getattr(net, full, getattr(net, key, default))
+    flags = 0
+    if get("SINGLE_LAYER_ATT", False):
+        flags |= APA_FLAG_SINGLE_LAYER_ATT
+    if get("SOFTMAX_ATT", False):
+        flags |= APA_FLAG_SOFTMAX_ATT
+    if get("RELU_ATT", False):
+        flags |= APA_FLAG_RELU_ATT
+    if get("PER_CLASS", False):
+        flags |= APA_FLAG_PER_CLASS
+    return flags, int(get("RANK", 1))
+
+
+def make_desc(batch, hw, channels, num_classes, frames=1, rank=1, flags=APA_FLAG_SINGLE_LAYER_ATT,
+              pose_channels=768, num_pose_keypoints=16):
+    d = ApaDesc()
+    d.abi_version = APA_ABI_VERSION
+    d.batch, d.hw, d.channels, d.num_classes = int(batch), int(hw), int(channels), int(num_classes)
+    d.frames, d.rank, d.flags = int(frames), int(rank), int(flags)
+    d.pose_channels, d.num_pose_keypoints = int(pose_channels), int(num_pose_keypoints)
+    return d
+
+
+def make_tuning(cluster_size=0, fused=-1, max_ctas=0, no_cooperative=0):
+    t = ApaTuning()
+    t.cluster_size, t.fused, t.max_ctas = int(cluster_size), int(fused), int(max_ctas)
+    t.no_cooperative = int(no_cooperative)
+    return t
+
+
+def attn_pool_check(desc):
+    return int(_lib.apa_attn_pool_check(ctypes.byref(desc)))
+
+
+def attn_pool_workspace(desc, want_attn=False, want_topdown=False, want_pose=False):
+    return int(_lib.apa_attn_pool_workspace(ctypes.byref(desc), int(want_attn), int(want_topdown),
+                                            int(want_pose)))
+
+
+def attn_pool_plan(desc, tuning=None, want_attn=False, want_topdown=False, want_pose=False):
+    out = (ctypes.c_int32 * 8)()
+    st = _lib.apa_attn_pool_plan(ctypes.byref(desc), ctypes.byref(tuning) if tuning is not None else None,
+                                 int(want_attn), int(want_topdown), int(want_pose), ctypes.byref(out))
+    if st != APA_OK:
+        raise ApaError(st, "apa_attn_pool_plan")
+    keys = ("path", "cluster_size", "grid", "fused", "launches", "smem_bytes")
+    return OrderedDict(zip(keys, list(out)[:6]))
+
+
+def strerror(status):
+    return _lib.apa_strerror(int(status)).decode()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class AttnPoolOp(object):
+    """One configured head: descriptor + device-resident variables + workspace.
+
+    `params` maps the reference's TF variable names to float32 CUDA tensors shaped
+    [Cin, Cout] / [Cout] (HWIO with the leading 1,1 dropped; 4-D HWIO tensors are accepted
+    and viewed).  The op keeps references so the pointers stay valid.
+    """
+
+    def __init__(self, params, num_classes, hw, channels=2048, batch=1, frames=1, rank=1,
+                 flags=APA_FLAG_SINGLE_LAYER_ATT, num_pose_keypoints=16, tuning=None, device=None):
+        import torch
+        self._torch = torch
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.num_classes, self.hw, self.channels = int(num_classes), int(hw), int(channels)
+        self.frames, self.rank, self.flags = int(frames), int(rank), int(flags)
+        self.num_pose_keypoints = int(num_pose_keypoints)
+        self.tuning = tuning
+        self._keep = []
+        self.weights = ApaWeights()
+        single = bool(flags & APA_FLAG_SINGLE_LAYER_ATT)
+
+        def dev(name, required=True):
+            if name not in params:
+                if required:
+                    raise KeyError("missing variable %r" % name)
+                return None
+            t = params[name]
+            if not torch.is_tensor(t):
+                t = torch.as_tensor(t)
+            t = t.to(device=self.device, dtype=torch.float32)
+            if t.dim() == 4:  # HWIO [1,1,Cin,Cout]
+                t = t.reshape(t.shape[2], t.shape[3])
+            t = t.contiguous()
+            self._keep.append(t)
+            return t
+
+        self.pose_channels = 768
+        pw = dev(POSE_W, required=not single)
+        if pw is not None:
+            self.pose_channels = int(pw.shape[1])
+            self.weights.pose_w = _ptr(pw)
+            self.weights.pose_b = _ptr(dev(POSE_B))
+            plw = dev(POSE_LOGITS_W, required=False)
+            if plw is not None:
+                self.num_pose_keypoints = int(plw.shape[1])
+                self.weights.pose_logits_w = _ptr(plw)
+                self.weights.pose_logits_b = _ptr(dev(POSE_LOGITS_B))
+        for r in range(self.rank):
+            self.weights.attn_w[r] = _ptr(dev(attn_scope(r) + "/weights")).value
+            self.weights.attn_b[r] = _ptr(dev(attn_scope(r) + "/biases")).value
+            self.weights.topdown_w[r] = _ptr(dev(topdown_scope(r) + "/weights")).value
+            self.weights.topdown_b[r] = _ptr(dev(topdown_scope(r) + "/biases")).value
+        self._has_pose_logits = bool(self.weights.pose_logits_w)
+        self._ws = {}  # (batch, want flags) -> (desc, workspace tensor)
+
+    def desc(self, batch):
+        return make_desc(batch, self.hw, self.channels, self.num_classes, self.frames, self.rank, self.flags,
+                         self.pose_channels, self.num_pose_keypoints)
+
+    def _workspace(self, batch, want):
+        key = (int(batch),) + tuple(bool(w) for w in want)
+        hit = self._ws.get(key)
+        if hit is not None:
+            return hit
+        torch = self._torch
+        d = self.desc(batch)
+        st = attn_pool_check(d)
+        if st != APA_OK:
+            raise ApaError(st, "apa_attn_pool_check")
+        nbytes = attn_pool_workspace(d, *want)
+        ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+        off = (-ws.data_ptr()) % 256
+        ws_al = ws[off:off + nbytes]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        st = _lib.apa_attn_pool_workspace_init(_ptr(ws_al), nbytes, ctypes.c_void_p(stream))
+        if st != APA_OK:
+            raise ApaError(st, "apa_attn_pool_workspace_init")
+        self._ws[key] = (d, ws_al, ws)
+        return self._ws[key]
+
+    def __call__(self, X, want_attn=False, want_topdown=False, want_pose=False, logits=None):
+        """X: float32 CUDA tensor [B*F, HW, C] (or [B*F, H, W, C]).  Returns (logits, end_points)."""
+        torch = self._torch
+        if not X.is_cuda or X.dtype != torch.float32:
+            raise TypeError("X must be a float32 CUDA tensor (PyTorch is only the container here)")
+        if X.dim() == 4:
+            X = X.reshape(X.shape[0], X.shape[1] * X.shape[2], X.shape[3])
+        X = X.contiguous()
+        batch, hw, ch = X.shape
+        if hw != self.hw or ch != self.channels:
+            raise ValueError("X is [%d,%d,%d], op was built for hw=%d channels=%d" %
+                             (batch, hw, ch, self.hw, self.channels))
+        want = (want_attn, want_topdown, want_pose and self._has_pose_logits)
+        d, ws, _ = self._workspace(batch, want)
+        K, R = self.num_classes, self.rank
+        M = K if (self.flags & APA_FLAG_PER_CLASS) else 1
+        if logits is None:
+            logits = torch.empty((batch // self.frames, K), dtype=torch.float32, device=X.device)
+        tail = (R,) if R > 1 else ()
+        attn = torch.empty((batch, hw, M) + tail, dtype=torch.float32, device=X.device) if want[0] else None
+        topdown = torch.empty((batch, hw, K) + tail, dtype=torch.float32, device=X.device) if want[1] else None
+        pose = (torch.empty((batch, hw, self.num_pose_keypoints), dtype=torch.float32, device=X.device)
+                if want[2] else None)
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        st = _lib.apa_attn_pool_fwd(ctypes.byref(d), _ptr(X), ctypes.byref(self.weights), _ptr(logits),
+                                    _ptr(attn), _ptr(topdown), _ptr(pose), _ptr(ws), ws.numel(),
+                                    ctypes.byref(self.tuning) if self.tuning is not None else None,
+                                    ctypes.c_void_p(stream))
+        if st != APA_OK:
+            raise ApaError(st, "apa_attn_pool_fwd")
+        end_points = OrderedDict()
+        if pose is not None:
+            end_points["PoseLogits"] = pose
+        if attn is not None:
+            end_points["PosePrelogitsBasedAttention"] = attn
+        if topdown is not None:
+            end_points["TopDownAttention"] = topdown
+        end_points["Logits"] = logits
+        return logits, end_points
+
+    def forward_host(self, X_host, logits_host=None):
+        """Plugin-style call with HOST buffers (pinned for speed): H2D copy, head, D2H copy, sync."""
+        torch = self._torch
+        if X_host.is_cuda or X_host.dtype != torch.float32:
+            raise TypeError("X_host must be a float32 CPU tensor")
+        if X_host.dim() == 4:
+            X_host = X_host.reshape(X_host.shape[0], X_host.shape[1] * X_host.shape[2], X_host.shape[3])
+        X_host = X_host.contiguous()
+        batch = X_host.shape[0]
+        d, ws, _ = self._workspace(batch, (False, False, False))
+        key = ("staging", batch)
+        st_bufs = self._ws.get(key)
+        if st_bufs is None:
+            st_bufs = (torch.empty(X_host.shape, dtype=torch.float32, device=self.device),
+                       torch.empty((batch // self.frames, self.num_classes), dtype=torch.float32,
+                                   device=self.device))
+            self._ws[key] = st_bufs
+        if logits_host is None:
+            logits_host = torch.empty((batch // self.frames, self.num_classes), dtype=torch.float32,
+                                      pin_memory=True)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        st = _lib.apa_attn_pool_fwd_host(ctypes.byref(d), _ptr(X_host), ctypes.byref(self.weights),
+                                         _ptr(logits_host), _ptr(st_bufs[0]), _ptr(st_bufs[1]), _ptr(ws),
+                                         ws.numel(),
+                                         ctypes.byref(self.tuning) if self.tuning is not None else None,
+                                         ctypes.c_void_p(stream))
+        if st != APA_OK:
+            raise ApaError(st, "apa_attn_pool_fwd_host")
+        return logits_host
+
+
+def attn_pool(X, params, num_classes, flags=APA_FLAG_SINGLE_LAYER_ATT, rank=1, frames=1, **kwargs):
+    """Functional form, like the reference's `pose_to_heatmap(*args, **kwargs)` wrappers: builds the op
+    for this call's shapes and runs it.  Prefer AttnPoolOp for repeated calls."""
+    want = {k: kwargs.pop(k, False) for k in ("want_attn", "want_topdown", "want_pose")}
+    hw = X.shape[1] if X.dim() == 3 else X.shape[1] * X.shape[2]
+    op = AttnPoolOp(params, num_classes, hw, channels=X.shape[-1], frames=frames, rank=rank, flags=flags,
+                    device=X.device, **kwargs)
+    return op(X, **want)
+
+
+def gram(X):
+    """Full second-order pooling G[b] = X[b]^T X[b] (paper; not in the reference code)."""
+    import torch
+    if X.dim() == 4:
+        X = X.reshape(X.shape[0], X.shape[1] * X.shape[2], X.shape[3])
+    X = X.contiguous()
+    B, HW, C = X.shape
+    G = torch.empty((B, C, C), dtype=torch.float32, device=X.device)
+    st = _lib.apa_gram_fwd(B, HW, C, _ptr(X), _ptr(G),
+                           ctypes.c_void_p(torch.cuda.current_stream(X.device).cuda_stream))
+    if st != APA_OK:
+        raise ApaError(st, "apa_gram_fwd")
+    return G

@@ -1,0 +1,73 @@
+"""Multi-GPU plumbing for the head: images are independent (no cross-image term anywhere in
+nets_factory.py:242-352, and no batch-norm in the head: normalizer_fn=None :268,:303), so the
+batch is scattered contiguously over ranks — keeping each video's F frames/crops on one rank
+so the frame mean (nets_factory.py:354-374) stays local — and the only collective is ONE
+all-gather of the [B/G, K] logits.  The reference's analogue is in-graph towers
+(models/slim/deployment/model_deploy.py:145 create_clones); it has no collective library.
+
+One process per GPU, `torch.distributed` (NCCL over NVLink on the GPU box, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+
+def shard_bounds(num_videos, rank, world):
+    """Contiguous, balanced [lo, hi) of videos for `rank` (first `num_videos % world` ranks get one more)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world %d" % (rank, world))
+    base, extra = divmod(int(num_videos), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_features(X, frames, rank, world):
+    """X: [B*F, ...] -> this rank's rows (whole videos only)."""
+    if X.shape[0] % frames:
+        raise ValueError("batch %d is not a multiple of frames %d" % (X.shape[0], frames))
+    lo, hi = shard_bounds(X.shape[0] // frames, rank, world)
+    return X[lo * frames:hi * frames]
+
+
+def all_gather_logits(local, out=None, group=None):
+    """One all-gather of equally sized [b, K] blocks into [world*b, K] (rank-major == batch order)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+def all_gather_logits_uneven(local, num_videos, group=None):
+    """All-gather when num_videos % world != 0: pad every block to the largest shard, gather once, trim."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_bounds(num_videos, r, world) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    lo, hi = sizes[rank]
+    if local.shape[0] != hi - lo:
+        raise ValueError("rank %d holds %d videos, expected %d" % (rank, local.shape[0], hi - lo))
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:hi - lo] = local
+    full = all_gather_logits(pad, group=group).reshape((world, mx) + tuple(local.shape[1:]))
+    return torch.cat([full[r, :sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
+
+
+class ShardedHead(object):
+    """network_fn-like callable for a batch that is sharded over the ranks of `group`.
+
+    `head(X_local) -> logits_local` is any per-rank head (the CUDA AttnPoolOp on the GPU box).
+    """
+
+    def __init__(self, head, num_videos, group=None):
+        self.head, self.num_videos, self.group = head, int(num_videos), group
+
+    def __call__(self, X_local):
+        import torch.distributed as dist
+        local = self.head(X_local)
+        world = dist.get_world_size(self.group)
+        if self.num_videos % world == 0:
+            return all_gather_logits(local, group=self.group)
+        return all_gather_logits_uneven(local, self.num_videos, group=self.group)

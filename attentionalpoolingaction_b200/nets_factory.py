@@ -1,0 +1,78 @@
+"""`get_network_fn` shim with the reference's signature and return contract
+(models/slim/nets/nets_factory.py:94-118, :375-380), for callers that hand over conv5 features.
+
+    network_fn = get_network_fn('resnet_v1_101', num_classes, num_pose_keypoints, cfg, params=variables)
+    logits, end_points = network_fn(last_conv)      # eval.py:181 / train.py:399 call shape
+
+`images` here is the backbone's last conv map (end_points['resnet_v1_101/block4'],
+nets_factory.py:63-67,137): [B,H,W,C] or, for videos, [B,F,H,W,C] which is folded to
+[B*F,H,W,C] and whose logits are averaged over F (nets_factory.py:119-125, :354-374).
+The backbone itself is out of scope.  `params` maps the reference's TF
+variable names to arrays (what the checkpoint restore would have put in the variable store).
+"""
+from __future__ import annotations
+
+import functools
+
+from .custom_ops import attn_pool_factory as ops
+
+# nets_factory.py:63-67
+last_conv_map = {
+    "inception_v3": "Mixed_7c",
+    "inception_v2_tsn": "InceptionV2_TSN/inception_5c",
+    "resnet_v1_101": "resnet_v1_101/block4",
+    "vgg_16": "vgg_16/conv5",
+}
+last_conv_channels = {"resnet_v1_101": 2048, "inception_v2_tsn": 1024, "inception_v3": 2048, "vgg_16": 512}
+
+
+def get_network_fn(name, num_classes, num_pose_keypoints, cfg, weight_decay=0.0, is_training=False,
+                   params=None, tuning=None):
+    """Returns `network_fn(images) -> (logits, end_points)` for the attentional-pooling head.
+
+    Raises ValueError for unknown `name` (nets_factory.py:113-114), and for head variants that
+    are out of scope (anything but USE_POSE_PRELOGITS_BASED_ATTENTION).
+    """
+    if name not in last_conv_map:
+        raise ValueError("Name of network unknown %s" % name)
+    net = cfg.NET
+    if not net.USE_POSE_PRELOGITS_BASED_ATTENTION:
+        raise ValueError("only the USE_POSE_PRELOGITS_BASED_ATTENTION head is built here (DESIGN.md §7)")
+    if getattr(net, "USE_POSE_PRELOGITS_BASED_ATTENTION_WITH_POSE_FEAT", False):
+        raise NotImplementedError("WITH_POSE_FEAT changes C to 2064 (nets_factory.py:289-295): out of scope")
+    if getattr(net, "USE_TEMPORAL_ATT", False):
+        raise NotImplementedError("USE_TEMPORAL_ATT (nets_factory.py:361-372) is out of scope")
+    if is_training:
+        raise NotImplementedError("forward/eval only: the training graph (dropout, backward) is a 'next' row")
+    if params is None:
+        raise ValueError("params (TF variable name -> array) is required: the head has trained variables")
+    flags, rank = ops.flags_from_cfg_net(net)
+    state = {}
+
+    def network_fn(images, end_point_names=()):
+        frames_per_video = 1
+        if images.dim() == 5:                       # nets_factory.py:121-125
+            frames_per_video = images.shape[1]
+            images = images.reshape((-1,) + tuple(images.shape[2:]))
+        B, H, W, C = images.shape
+        key = (H * W, C, frames_per_video)
+        op = state.get(key)
+        if op is None:
+            op = ops.AttnPoolOp(params, num_classes, H * W, channels=C, frames=frames_per_video, rank=rank,
+                                flags=flags, num_pose_keypoints=num_pose_keypoints, tuning=tuning,
+                                device=images.device)
+            state[key] = op
+        want = set(end_point_names)
+        logits, eps = op(images.reshape(B, H * W, C),
+                         want_attn="PosePrelogitsBasedAttention" in want,
+                         want_topdown="TopDownAttention" in want,
+                         want_pose="PoseLogits" in want)
+        # restore the spatial axes the reference's end-points carry
+        for k in ("PosePrelogitsBasedAttention", "TopDownAttention", "PoseLogits"):
+            if k in eps:
+                t = eps[k]
+                eps[k] = t.reshape((B, H, W) + tuple(t.shape[2:]))
+        return logits, eps
+
+    network_fn.default_image_size = 224
+    return network_fn

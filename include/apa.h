@@ -1,0 +1,166 @@
+/*
+ * apa.h — C ABI of the B200-native attentional-pooling head.
+ *
+ * This is the drop-in boundary for ONE path of rohitgirdhar/AttentionalPoolingAction:
+ * the head that turns conv5 features X[B,H,W,C] into action logits[B,K]
+ * (reference: models/slim/nets/nets_factory.py:119-125 frame fold, :143-160 pose
+ * branch, :242-328 PosePrelogitsBasedAttention, :350-352 squeeze, :354-374 frame mean).
+ *
+ * The reference has no C ABI for this path (it is a TF-1.1 Python graph; its native
+ * ops use the TF C++ OpKernel interface, src/custom_ops/pose_to_heatmap.cc:26-104).
+ * The conventions below restate those OpKernel conventions as plain C:
+ *   - inputs are borrowed (context->input(i), pose_to_heatmap.cc:37-44)       -> const pointers
+ *   - outputs are framework-allocated (allocate_output, :55-69)               -> caller-owned buffers
+ *   - errors propagate as a status (OP_REQUIRES_OK, :27-32)                    -> int return, 0 == OK
+ *   - attrs are fixed at construction (:26-33)                                 -> ApaDesc
+ *   - Compute() is called concurrently from TF's inter-op pool                 -> re-entrant, no global
+ *     (thread-safety note pose_utils.hpp:7-14)                                    mutable state; all work
+ *                                                                                 is enqueued on `stream`.
+ *
+ * No torch types appear here. All device pointers are plain `float*` in the
+ * address space of the current CUDA device; `stream` is a cudaStream_t passed
+ * as void*.  The library never allocates or frees device memory on the
+ * device-pointer entry points; it never synchronises the stream there either.
+ *
+ * Layouts (all fp32, row-major, "NHWC with H*W flattened"):
+ *   X            [batch, hw, channels]                    (nets_factory.py:137 last_conv)
+ *   conv weights [Cin, Cout]  == TF HWIO [1,1,Cin,Cout] with the two leading 1s dropped
+ *   logits       [batch/frames, num_classes]              (nets_factory.py:350-352, :373)
+ *   attn_out     [batch, hw, M]      if rank==1 else [batch, hw, M, rank]   (:271-274, :287)
+ *   topdown_out  [batch, hw, K]      if rank==1 else [batch, hw, K, rank]   (:305-309)
+ *   pose_out     [batch, hw, num_pose_keypoints]          (:158-160)
+ *   with M = num_classes if APA_FLAG_PER_CLASS else 1     (:258)
+ */
+#ifndef APA_H_
+#define APA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APA_ABI_VERSION 1
+#define APA_MAX_RANK 4
+
+/* cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION_* flags (src/config.py:182-209). */
+enum {
+  APA_FLAG_SINGLE_LAYER_ATT = 1 << 0, /* attention reads X, not the 768-ch pose pre-logits (:247-250) */
+  APA_FLAG_SOFTMAX_ATT      = 1 << 1, /* spatial softmax over H*W per map (:276-284)                  */
+  APA_FLAG_RELU_ATT         = 1 << 2, /* relu on the (stacked) attention (:285-286)                   */
+  APA_FLAG_PER_CLASS        = 1 << 3  /* one attention map per class, M = K (:258)                    */
+};
+
+/* Status codes. 0 == OK; negatives are library errors; positives are cudaError_t passthrough. */
+enum {
+  APA_OK                   = 0,
+  APA_ERR_NULL             = -1, /* required pointer is NULL                                         */
+  APA_ERR_SHAPE            = -2, /* bad batch/hw/channels/classes/frames                             */
+  APA_ERR_RANK             = -3, /* rank outside [1, APA_MAX_RANK]                                    */
+  APA_ERR_SOFTMAX_RANK     = -4, /* SOFTMAX_ATT with RANK>1: graph-build error in the reference       */
+                                 /* (nets_factory.py:278 applies a 4-perm transpose to a rank-5       */
+                                 /*  tensor) -- rejected, not given invented semantics                */
+  APA_ERR_WORKSPACE        = -5, /* workspace too small or misaligned                                 */
+  APA_ERR_UNSUPPORTED      = -6, /* valid in the reference but not built here         */
+  APA_ERR_ALIGN            = -7, /* X / outputs not 16-byte aligned                                   */
+  APA_ERR_DEVICE           = -8  /* not an sm_100 device                                              */
+};
+
+/* Construction-time attributes of the head (what the reference fixes at graph build). */
+typedef struct ApaDesc {
+  int32_t abi_version;        /* = APA_ABI_VERSION                                                   */
+  int32_t batch;              /* number of feature maps B*F (frames already folded, :121-125)        */
+  int32_t hw;                 /* H*W spatial locations (196 synthetic, 225 in the 450-px pipeline)    */
+  int32_t channels;           /* C of last_conv (2048 for resnet_v1_101/block4)                       */
+  int32_t num_classes;        /* K (393 MPII, 600 HICO)                                               */
+  int32_t frames;             /* F frames/crops per video; logits are averaged over F (:354-374)      */
+  int32_t rank;               /* USE_POSE_PRELOGITS_BASED_ATTENTION_RANK (chained, see quirk Q1)      */
+  int32_t flags;              /* APA_FLAG_*                                                           */
+  int32_t pose_channels;      /* width of ExtraConv2d_1x1 (768, :151-157); used iff !SINGLE_LAYER_ATT  */
+  int32_t num_pose_keypoints; /* width of Conv2d_1c_1x1 (16, :158-159); used iff pose_out requested   */
+  int32_t reserved[6];        /* must be 0                                                            */
+} ApaDesc;
+
+/* Borrowed device pointers to the head's variables, addressed as the reference names them
+ * (variable scopes nets_factory.py:147,243,260-269,300-303).                               */
+typedef struct ApaWeights {
+  /* PosePrelogitsBasedAttention/Conv2d_PrePose_Attn{,1,2,..}/{weights,biases}
+   *   r == 0: [Cs, M], [M]  with Cs = channels (SINGLE_LAYER_ATT) or pose_channels
+   *   r >= 1: [M, M],  [M]  (the conv is applied to the previous map: quirk Q1, :263-270)  */
+  const float* attn_w[APA_MAX_RANK];
+  const float* attn_b[APA_MAX_RANK];
+  /* PosePrelogitsBasedAttention/Conv{,_1,_2,..}/{weights,biases}: [channels, K], [K] (:300-303) */
+  const float* topdown_w[APA_MAX_RANK];
+  const float* topdown_b[APA_MAX_RANK];
+  /* PoseLogits/ExtraConv2d_1x1/{weights,biases}: [channels, pose_channels], [pose_channels] */
+  const float* pose_w;
+  const float* pose_b;
+  /* PoseLogits/Conv2d_1c_1x1/{weights,biases}: [pose_channels, num_pose_keypoints], [..]    */
+  const float* pose_logits_w;
+  const float* pose_logits_b;
+} ApaWeights;
+
+/* Launch/tuning knobs; pass NULL for defaults. Does not change results beyond fp32 rounding. */
+typedef struct ApaTuning {
+  int32_t cluster_size; /* CTAs per image in the streaming kernel: 0 = auto, else 1,2,4,8,16         */
+  int32_t fused;        /* 1 = one kernel with a grid barrier, 0 = two kernels, -1 = auto             */
+  int32_t max_ctas;     /* 0 = all SMs                                                                */
+  int32_t no_cooperative; /* 1 = never use the cooperative-launch attribute for the fused kernel      */
+  int32_t reserved[4];
+} ApaTuning;
+
+/* Library/ABI version (APA_ABI_VERSION of the build). */
+int apa_abi_version(void);
+
+/* Human-readable text for a status returned by any function below. Never NULL. */
+const char* apa_strerror(int status);
+
+/* Validate a descriptor exactly as apa_attn_pool_fwd would (no device access). */
+int apa_attn_pool_check(const ApaDesc* desc);
+
+/* Bytes of device workspace apa_attn_pool_fwd needs for `desc` (and whether the optional
+ * outputs are requested). 0 on invalid desc. The workspace must be 256-byte aligned and its
+ * first 256 bytes must have been zeroed once (apa_attn_pool_workspace_init) before first use;
+ * one workspace must not be used by two in-flight calls at the same time.                   */
+size_t apa_attn_pool_workspace(const ApaDesc* desc, int want_attn, int want_topdown, int want_pose);
+
+/* Enqueue zeroing of the workspace control block on `stream`. */
+int apa_attn_pool_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+/* The head, forward, device buffers.  Replaces the graph built by
+ * nets_factory.py:143-160 + :242-328 + :350-352 + :354-374 for a given last_conv X.
+ *   logits       required, [batch/frames, K]
+ *   attn_out     optional (NULL to skip): end_points['PosePrelogitsBasedAttention'] (:287)
+ *   topdown_out  optional: end_points['TopDownAttention'] (:309) -- forces the dense path
+ *   pose_out     optional: end_points['PoseLogits'] (:160); needs pose weights
+ * Everything is enqueued on `stream`; no host synchronisation.                              */
+int apa_attn_pool_fwd(const ApaDesc* desc, const float* X, const ApaWeights* weights,
+                      float* logits, float* attn_out, float* topdown_out, float* pose_out,
+                      void* workspace, size_t workspace_bytes, const ApaTuning* tuning,
+                      void* stream);
+
+/* Same call with HOST buffers for X and logits (weights stay device-resident, as TF variables
+ * do): copies X host->device into `x_staging` (device, batch*hw*channels floats), runs the
+ * head, copies logits device->host, and waits for the result on `stream`.  This is the
+ * plugin-style entry a sess.run()-like caller uses (eval.py:258-264 feeds host arrays).     */
+int apa_attn_pool_fwd_host(const ApaDesc* desc, const float* X_host, const ApaWeights* weights,
+                           float* logits_host, float* x_staging, float* logits_staging,
+                           void* workspace, size_t workspace_bytes, const ApaTuning* tuning,
+                           void* stream);
+
+/* Full second-order pooling G[b] = X[b]^T X[b]  ([batch, C, C], symmetric).  Not present in the
+ * reference code; defined from the paper's second-order pooling equation (BASELINE config 5). */
+int apa_gram_fwd(int32_t batch, int32_t hw, int32_t channels, const float* X, float* G,
+                 void* stream);
+
+/* Introspection for tests/bench: how the last-validated desc would be executed.
+ * Fills plan[0]=path (0 fused-rank1-map, 1 dense), [1]=cluster_size, [2]=grid CTAs,
+ * [3]=fused(0/1), [4]=kernel launches per call, [5]=smem bytes, [6..7] reserved.            */
+int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_attn,
+                       int want_topdown, int want_pose, int32_t plan[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APA_H_ */

@@ -1,0 +1,229 @@
+"""Parity of the CUDA head (through the C ABI) against the CPU oracle.  All tests need a B200.
+
+Tolerance (north_star: <= 1e-4 rel on logits): max|d| / max|ref| <= 1e-4 AND
+allclose(rtol=1e-4, atol=1e-4*max|ref|), against the fp64 oracle.  The fp32 SIMT/FMA kernels here
+land around 1e-6; the 1e-4 bar is the contract.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _setup(B, HW, C, K, flags, seed=0, F=1, pose_channels=768, kp=16):
+    import torch
+    from oracle import attn_pool_oracle as orc
+    fl = dict(orc.DEFAULT_FLAGS, **flags)
+    params = orc.make_params(K, C, pose_channels, kp, flags=fl, seed=seed)
+    X = orc.make_features(B, HW, C, seed=seed)
+    return fl, params, X
+
+
+def _run(B, HW, C, K, flags, seed=0, F=1, want=(False, False, False), tuning=None, pose_channels=768, kp=16):
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    fl, params, X = _setup(B, HW, C, K, flags, seed, F, pose_channels, kp)
+    ref, ref_ep = orc.attn_pool_head(X, params, fl, K, frames_per_video=F, want_pose=want[2])
+    bits, rank = ops.flags_from_cfg_net(fl)
+    op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, frames=F,
+                        rank=rank, flags=bits, num_pose_keypoints=kp, tuning=tuning, device="cuda:0")
+    logits, ep = op(torch.from_numpy(X).cuda(), want_attn=want[0], want_topdown=want[1], want_pose=want[2])
+    torch.cuda.synchronize()
+    return logits.cpu().numpy(), {k: v.cpu().numpy() for k, v in ep.items()}, ref, ref_ep
+
+
+SINGLE = dict(SINGLE_LAYER_ATT=True)
+
+FUSED_CASES = [
+    # (id, B, HW, C, K, flags, F)
+    ("cfg002_b4", 4, 196, 2048, 393, SINGLE, 1),
+    ("cfg2_full_b32", 32, 196, 2048, 393, SINGLE, 1),
+    ("hw225_b3", 3, 225, 2048, 393, SINGLE, 1),
+    ("relu", 5, 196, 2048, 393, dict(SINGLE, RELU_ATT=True), 1),
+    ("softmax", 5, 196, 2048, 393, dict(SINGLE, SOFTMAX_ATT=True), 1),
+    ("softmax_relu", 2, 49, 2048, 101, dict(SINGLE, SOFTMAX_ATT=True, RELU_ATT=True), 1),
+    ("rank2", 4, 196, 2048, 393, dict(SINGLE, RANK=2), 1),
+    ("rank3_relu", 3, 196, 2048, 393, dict(SINGLE, RANK=3, RELU_ATT=True), 1),
+    ("rank4", 2, 100, 2048, 51, dict(SINGLE, RANK=4), 1),
+    ("hico_k600_10crop", 20, 196, 2048, 600, SINGLE, 10),
+    ("frames3_rank2", 6, 49, 2048, 21, dict(SINGLE, RANK=2), 3),
+    ("c1024", 4, 196, 1024, 393, SINGLE, 1),
+    ("b1", 1, 196, 2048, 393, SINGLE, 1),
+    ("k1", 3, 196, 2048, 1, SINGLE, 1),
+    ("hw1", 3, 1, 2048, 17, SINGLE, 1),
+    ("hw7_softmax", 3, 7, 2048, 17, dict(SINGLE, SOFTMAX_ATT=True), 1),
+    ("multiwave_b200", 200, 49, 2048, 40, SINGLE, 1),
+    ("multiwave_b77_softmax", 77, 64, 2048, 33, dict(SINGLE, SOFTMAX_ATT=True), 1),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_fused_path_parity(case):
+    from oracle import attn_pool_oracle as orc
+    _, B, HW, C, K, flags, F = case
+    got, _, ref, _ = _run(B, HW, C, K, flags, F=F)
+    orc.assert_parity(got, ref, TOL)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("fused", [1, 0])
+def test_cluster_sizes_and_split_launch(cluster, fused):
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    for flags in (SINGLE, dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=2, RELU_ATT=True)):
+        got, _, ref, _ = _run(9, 196, 2048, 393, flags, seed=3, tuning=ops.make_tuning(cluster, fused))
+        orc.assert_parity(got, ref, TOL)
+
+
+def test_config003_pose_attention_rank2():
+    """BASELINE config 3: attention from relu(X Wp + bp) (768 ch), RANK=2 chain (quirk Q1)."""
+    from oracle import attn_pool_oracle as orc
+    got, ep, ref, ref_ep = _run(3, 196, 2048, 393, dict(RANK=2), want=(True, False, True))
+    orc.assert_parity(got, ref, TOL)
+    orc.assert_parity(ep["PoseLogits"], ref_ep["PoseLogits"], TOL, "PoseLogits")
+    orc.assert_parity(ep["PosePrelogitsBasedAttention"], ref_ep["PosePrelogitsBasedAttention"], TOL, "attention")
+
+
+DENSE_CASES = [
+    ("per_class", 2, 196, 2048, 393, dict(SINGLE, PER_CLASS=True), 1),
+    ("per_class_softmax", 2, 49, 2048, 57, dict(SINGLE, PER_CLASS=True, SOFTMAX_ATT=True), 1),
+    ("per_class_relu_rank2", 2, 49, 2048, 37, dict(SINGLE, PER_CLASS=True, RELU_ATT=True, RANK=2), 2),
+    ("per_class_pose_src", 2, 49, 2048, 37, dict(PER_CLASS=True), 1),
+    ("c512_falls_to_dense", 3, 49, 512, 37, SINGLE, 1),
+]
+
+
+@pytest.mark.parametrize("case", DENSE_CASES, ids=[c[0] for c in DENSE_CASES])
+def test_dense_path_parity(case):
+    from oracle import attn_pool_oracle as orc
+    _, B, HW, C, K, flags, F = case
+    got, _, ref, _ = _run(B, HW, C, K, flags, F=F)
+    orc.assert_parity(got, ref, TOL)
+
+
+@pytest.mark.parametrize("flags", [SINGLE, dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=3, RELU_ATT=True),
+                                   dict(SINGLE, PER_CLASS=True, RANK=2)],
+                         ids=["plain", "softmax", "rank3relu", "perclass_rank2"])
+def test_end_points(flags):
+    """The three observable end-points (nets_factory.py:160, :287, :309) with the reference's shapes."""
+    from oracle import attn_pool_oracle as orc
+    K = 29 if flags.get("PER_CLASS") else 393
+    got, ep, ref, ref_ep = _run(3, 49, 2048, K, flags, want=(True, True, True))
+    orc.assert_parity(got, ref, TOL)
+    for name in ("PosePrelogitsBasedAttention", "TopDownAttention", "PoseLogits"):
+        assert ep[name].shape == ref_ep[name].shape, name
+        orc.assert_parity(ep[name], ref_ep[name], TOL, name)
+    if flags.get("SOFTMAX_ATT"):
+        np.testing.assert_allclose(ep["PosePrelogitsBasedAttention"].sum(axis=1), 1.0, rtol=1e-5)
+
+
+def test_bitwise_deterministic():
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    fl, params, X = _setup(32, 196, 2048, 393, SINGLE, seed=5)
+    bits, rank = ops.flags_from_cfg_net(fl)
+    op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 393, 196, rank=rank, flags=bits,
+                        device="cuda:0")
+    Xd = torch.from_numpy(X).cuda()
+    a = op(Xd)[0].clone()
+    for _ in range(5):
+        b = op(Xd)[0]
+        assert torch.equal(a, b)
+
+
+def test_properties_at_full_size():
+    """Size-independent properties at BASELINE config-4 per-GPU size (320 crop maps, K=600, 10-crop):
+    batch-permutation equivariance, crop-mean linearity, linearity in the top-down weights."""
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    B, HW, C, K, F = 320, 196, 2048, 600, 10
+    fl = dict(orc.DEFAULT_FLAGS, SINGLE_LAYER_ATT=True)
+    params = orc.make_params(K, C, flags=fl, seed=11)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    X = torch.relu(torch.randn((B, HW, C), device="cuda", generator=g))
+    P = {k: torch.from_numpy(v) for k, v in params.items()}
+    bits, rank = ops.flags_from_cfg_net(fl)
+    op1 = ops.AttnPoolOp(P, K, HW, frames=1, rank=rank, flags=bits, device="cuda:0")
+    opF = ops.AttnPoolOp(P, K, HW, frames=F, rank=rank, flags=bits, device="cuda:0")
+    per_crop = op1(X)[0]
+    pooled = opF(X)[0]
+    scale = per_crop.abs().max().item()
+    # crop mean == mean of per-crop logits
+    assert (pooled - per_crop.reshape(B // F, F, K).mean(1)).abs().max().item() <= 1e-5 * scale
+    # permuting the batch permutes the logits (bitwise: per-image work is independent of position)
+    perm = torch.randperm(B, device="cuda", generator=g)
+    assert torch.equal(op1(X[perm].contiguous())[0], per_crop[perm])
+    # linear in the top-down weights and biases
+    P2 = dict(P)
+    tw, tb = "PosePrelogitsBasedAttention/Conv/weights", "PosePrelogitsBasedAttention/Conv/biases"
+    P2[tw] = P[tw] * 2.0
+    P2[tb] = P[tb] * 2.0
+    op2 = ops.AttnPoolOp(P2, K, HW, frames=1, rank=rank, flags=bits, device="cuda:0")
+    assert (op2(X)[0] - 2.0 * per_crop).abs().max().item() <= 1e-5 * scale
+    # and the oracle agrees on a slice of it
+    ref, _ = orc.attn_pool_head(X[:20].cpu().numpy(), params, fl, K, frames_per_video=F, want_pose=False)
+    orc.assert_parity(pooled[:2].cpu().numpy(), ref, TOL)
+
+
+def test_host_buffer_entry_point():
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    fl, params, X = _setup(8, 196, 2048, 393, SINGLE, seed=9)
+    ref, _ = orc.attn_pool_head(X, params, fl, 393, want_pose=False)
+    bits, rank = ops.flags_from_cfg_net(fl)
+    op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 393, 196, rank=rank, flags=bits,
+                        device="cuda:0")
+    out = op.forward_host(torch.from_numpy(X).pin_memory())
+    orc.assert_parity(out.numpy(), ref, TOL)
+
+
+def test_network_fn_shim():
+    """get_network_fn(...) -> network_fn(images) -> (logits, end_points), 5-D input folds frames."""
+    import torch
+    from attentionalpoolingaction_b200 import config, nets_factory
+    from oracle import attn_pool_oracle as orc
+    cfg = config.cfg_from_dict({"NET": {"USE_POSE_PRELOGITS_BASED_ATTENTION": True,
+                                        "USE_POSE_PRELOGITS_BASED_ATTENTION_SINGLE_LAYER_ATT": True}})
+    fl = dict(orc.DEFAULT_FLAGS, SINGLE_LAYER_ATT=True)
+    params = orc.make_params(393, 2048, flags=fl, seed=2)
+    X = orc.make_features(6, 225, 2048, seed=2)
+    fn = nets_factory.get_network_fn("resnet_v1_101", 393, 16, cfg,
+                                     params={k: torch.from_numpy(v) for k, v in params.items()})
+    images = torch.from_numpy(X).cuda().reshape(2, 3, 15, 15, 2048)
+    logits, ep = fn(images, end_point_names=("PosePrelogitsBasedAttention",))
+    ref, ref_ep = orc.attn_pool_head(X, params, fl, 393, frames_per_video=3, want_pose=False)
+    orc.assert_parity(logits.cpu().numpy(), ref, TOL)
+    assert tuple(ep["PosePrelogitsBasedAttention"].shape) == (6, 15, 15, 1)
+    orc.assert_parity(ep["PosePrelogitsBasedAttention"].reshape(6, 225, 1).cpu().numpy(),
+                      ref_ep["PosePrelogitsBasedAttention"], TOL)
+
+
+def test_gram_matches_oracle():
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    X = orc.make_features(2, 49, 256, seed=4)
+    G = ops.gram(torch.from_numpy(X).cuda()).cpu().numpy()
+    orc.assert_parity(G, orc.gram(X), TOL, "gram")
+
+
+def test_errors_are_loud():
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    fl = dict(orc.DEFAULT_FLAGS, SINGLE_LAYER_ATT=True, SOFTMAX_ATT=True, RANK=2)
+    params = orc.make_params(10, 2048, flags=fl)
+    bits, rank = ops.flags_from_cfg_net(fl)
+    op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 10, 49, rank=rank, flags=bits,
+                        device="cuda:0")
+    with pytest.raises(ops.ApaError) as e:
+        op(torch.zeros((2, 49, 2048), device="cuda"))
+    assert e.value.status == ops.APA_ERR_SOFTMAX_RANK
+    with pytest.raises(orc.ReferenceGraphError):
+        orc.attn_pool_head(np.zeros((2, 49, 2048), np.float32), params, fl, 10)

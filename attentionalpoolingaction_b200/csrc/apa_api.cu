@@ -19,8 +19,11 @@ inline int mode_of(int flags) {
   return MODE_PLAIN;
 }
 
+constexpr size_t kCtrlBytes = 2048;         // 256 x u64 arrival counters, indexed by gridDim.x
+constexpr size_t kTsBytes = 160 * 64 * 8;  // debug timeline: up to 160 CTAs x 64 stamps
+
 struct Carve {
-  size_t ctrl, g, sn, smx, attn_raw, pose_pre, a0, A, T, total;
+  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, total;
   int path;  // 0 fused single-map, 1 dense
 };
 
@@ -35,7 +38,7 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
   const size_t M = (d->flags & APA_FLAG_PER_CLASS) ? K : 1;
   const bool single = (d->flags & APA_FLAG_SINGLE_LAYER_ATT) != 0;
   c.path = use_fused_path(d, want_topdown) ? 0 : 1;
-  size_t off = 256;  // control block
+  size_t off = kCtrlBytes;  // control block: one grid-barrier counter per grid size
   c.ctrl = 0;
   auto take = [&](size_t floats) {
     size_t o = off;
@@ -43,6 +46,7 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
     return o;
   };
   if (c.path == 0) {
+    c.ts = take(kTsBytes / sizeof(float));
     c.g = take(B * R * C);
     c.sn = take(B * R);
     c.smx = take(B * 2);
@@ -133,8 +137,8 @@ size_t apa_attn_pool_workspace(const ApaDesc* desc, int want_attn, int want_topd
 
 int apa_attn_pool_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
   if (workspace == nullptr) return APA_ERR_NULL;
-  if (workspace_bytes < 256 || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APA_ERR_WORKSPACE;
-  APA_CUDA(cudaMemsetAsync(workspace, 0, 256, static_cast<cudaStream_t>(stream)));
+  if (workspace_bytes < kCtrlBytes || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APA_ERR_WORKSPACE;
+  APA_CUDA(cudaMemsetAsync(workspace, 0, kCtrlBytes, static_cast<cudaStream_t>(stream)));
   return APA_OK;
 }
 
@@ -245,7 +249,9 @@ int apa_attn_pool_fwd(const ApaDesc* d, const float* X, const ApaWeights* w, flo
     p.g = wsf(c.g);
     p.sn = wsf(c.sn);
     p.smx = wsf(c.smx);
-    p.barrier = reinterpret_cast<unsigned int*>(ws + c.ctrl);
+    p.barrier = reinterpret_cast<unsigned long long*>(ws + c.ctrl) + ((plan.cluster * plan.nclusters) & 255);
+    p.dbg_pieces = tuning ? tuning->copy_pieces : 0;
+    p.ts = (tuning && tuning->debug_timestamps) ? reinterpret_cast<unsigned long long*>(ws + c.ts) : nullptr;
     p.B = B; p.HW = HW; p.C = C; p.K = K; p.R = R; p.F = F;
     p.inv_scale = 1.0f / (float(HW) * float(F));
     APA_CUDA(fused_launch(p, plan, stream));

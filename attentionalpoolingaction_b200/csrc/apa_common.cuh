@@ -107,6 +107,29 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() {
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void st_dsmem_f4(uint32_t raddr, const float4& v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_dsmem_f(uint32_t raddr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+// volatile (keeps its order w.r.t. the barrier asms) but no memory clobber, so a run of these pipelines
+__device__ __forceinline__ float ld_dsmem_f_nv(uint32_t raddr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr));
+  return v;
+}
 // All threads of all CTAs of the cluster.
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -154,32 +177,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Grid-wide barrier for a grid whose CTAs are all co-resident (grid <= resident capacity;
-// the host launches cooperatively when the driver allows it).  ctrl[0] = arrival count,
-// ctrl[1] = generation; both zero before first use and self-resetting afterwards.
-// Must be called by every thread of every CTA.
-__device__ __forceinline__ void grid_barrier(unsigned int* ctrl, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int gen0, prev;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen0) : "l"(ctrl + 1) : "memory");
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ctrl) : "memory");
-    if (prev == nblocks - 1) {
-      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ctrl), "r"(0u) : "memory");
-      asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ctrl + 1) : "memory");
-    } else {
-      const long long t0 = clock64();
-      unsigned int g;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(ctrl + 1) : "memory");
-        if (g != gen0) break;
-        __nanosleep(40);
-        if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
-      } while (true);
-    }
-    __threadfence();
-  }
-  __syncthreads();
+// Grid-wide barrier for a grid whose CTAs are all co-resident (grid <= resident capacity; the host
+// launches cooperatively when the driver allows it).  `ctr` is a 64-bit arrival counter that only ever
+// grows: every launch with the same grid size adds exactly `nblocks`, so the next multiple of `nblocks`
+// above a CTA's own ticket is the release point.  One counter per grid size (the host indexes the
+// workspace control block by gridDim), zeroed once by apa_attn_pool_workspace_init.
+// Split in two so independent work can be done between arrive and wait; call both from ONE thread,
+// with a __syncthreads() before the arrive and after the wait.
+__device__ __forceinline__ unsigned long long grid_arrive(unsigned long long* ctr, unsigned int nblocks) {
+  unsigned long long prev;
+  asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(prev) : "l"(ctr) : "memory");
+  return prev - (prev % nblocks) + nblocks;
+}
+__device__ __forceinline__ void grid_wait(unsigned long long* ctr, unsigned long long target) {
+  const long long t0 = clock64();
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+    if (v >= target) break;
+    if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
+  } while (true);
 }
 
 }  // namespace apa

@@ -30,9 +30,11 @@ struct FusedParams {
   float* g;                           // workspace [B, R, C]: attention-weighted feature sums
   float* sn;                          // workspace [B, R]: sum of attention weights (1 if softmax)
   float* smx;                         // workspace [B, 2]: softmax (max, sum) per image
-  unsigned int* barrier;              // workspace control block (2 words)
+  unsigned long long* barrier;        // grid-barrier arrival counter for this grid size (control block)
+  unsigned long long* ts;             // optional debug timeline, 64 words per CTA (see apa_pool_fused.cu)
   int B, HW, C, K, R, F;
   int do_phase1, do_phase2;           // fused: 1,1   split: (1,0) then (0,1)
+  int dbg_pieces;                     // bulk copies per 4-row tile (0/1 = one 32 KB copy)
   float inv_scale;                    // 1 / (HW * F)
 };
 

@@ -13,13 +13,15 @@
 //
 // Structure (one launch):
 //   phase 1  one thread-block CLUSTER of p CTAs per image; CTA q owns rows [q HW/p, (q+1) HW/p).
-//            warp 8 lane 0 streams 4-row x C tiles HBM -> smem with cp.async.bulk (TMA engine, UBLKCP)
-//            through a 5/6-stage mbarrier ring; 8 consumer warps each own C/8 channels: per tile they
+//            Warp 8 streams 4-row x C tiles HBM -> smem with cp.async.bulk (TMA engine, UBLKCP)
+//            through a 4/6-stage mbarrier ring; 8 consumer warps each own C/8 channels: per tile they
 //            form partial dots, one named barrier combines them into a[row], then they accumulate
-//            g (8 channels per thread per rank, in registers).  At the end of an image the p partial
-//            g vectors are combined through distributed shared memory (each CTA reduces C/p channels)
-//            with the softmax max/sum merge, and written once to a [B,R,C] workspace.
-//   barrier  self-resetting grid barrier (all CTAs co-resident; cooperative launch when available)
+//            g (8 channels per thread per rank, in registers).  At the end of an image every CTA
+//            PUSHES its partial g (st.shared::cluster) into the slot buffers of the CTA that owns
+//            those C/p channels, one cluster-scope mbarrier round publishes them, and the owner
+//            sums the p slots (softmax max/sum merge included) and writes g once to a [B,R,C] workspace.
+//   barrier  grid barrier (monotonic 64-bit arrival counter; all CTAs co-resident, cooperative launch
+//            when available), split into arrive / wait so the first weight tile loads in between
 //   phase 2  logits = g . B  as a register-tiled fp32 SIMT GEMM: cluster -> class slice, CTA in
 //            cluster -> channel slice, partial sums combined through DSMEM (deterministic, no atomics).
 #include "apa_common.cuh"
@@ -35,14 +37,14 @@ namespace {
 template <int Q, int RMAX>
 struct Smem {
   static constexpr int C = Q * 1024;
-  static constexpr int kStages = (RMAX == 1) ? 6 : 5;
+  static constexpr int kStages = (Q == 1) ? 8 : ((RMAX == 1) ? 6 : 4);
   static constexpr size_t kStageBytes = size_t(kRowsPerStage) * C * 4;
   static constexpr size_t kRing = kStages * kStageBytes;
-  static constexpr size_t kOffRed = kRing;                       // float red[RMAX][C]
-  static constexpr size_t kOffPart = kOffRed + size_t(RMAX) * C * 4;  // float part[2][rows][8]
-  static constexpr size_t kOffStats = kOffPart + 2 * kRowsPerStage * 8 * 4;  // float stats[8]
-  static constexpr size_t kOffScl = kOffStats + 32;              // float scl[16]
-  static constexpr size_t kOffBars = kOffScl + 64;               // u64 full[8] empty[8] ready free
+  static constexpr size_t kOffSlots = kRing;                                  // float slots[2][p][R][C/p]
+  static constexpr size_t kOffStat = kOffSlots + 2 * size_t(RMAX) * C * 4;    // float stat[2][16][8]
+  static constexpr size_t kOffPart = kOffStat + 2 * 16 * 8 * 4;               // float part[2][rows][8]
+  static constexpr size_t kOffScl = kOffPart + 2 * kRowsPerStage * 8 * 4;     // float scl[16]
+  static constexpr size_t kOffBars = kOffScl + 64;                            // u64 full[8] empty[8] ready
   static constexpr size_t kTotal = kOffBars + 8 * 18;
   // phase-2 carve inside the ring
   static constexpr int kChunk = (Q == 1) ? 256 : 512;            // channels per smem chunk
@@ -52,7 +54,7 @@ struct Smem {
   static constexpr size_t kOffAcc = kOffW + size_t(kChunk) * kColTile * 4;     // float accS[8][32][16]
   static constexpr size_t kOffOut = kOffAcc + size_t(kConsumerWarps) * kVideoTile * kColTile * 4;
   static constexpr size_t kPhase2End = kOffOut + size_t(kVideoTile) * kColTile * 4;
-  static_assert(kPhase2End <= kRing, "phase-2 scratch must fit in the stage ring");
+  static_assert(kPhase2End <= kOffStat, "phase-2 scratch must fit in the stage ring + slot buffers");
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
@@ -66,20 +68,109 @@ __device__ __forceinline__ void axpy4(float* f, float a, const float4& x) {
   f[3] = fmaf(a, x.w, f[3]);
 }
 
+// Debug timeline (ApaTuning.debug_timestamps): 64 x u64 per CTA in the workspace.
+//  0 start | 1 after cluster sync | 2 phase-1 end | 3 after DSMEM combine | 4 after grid barrier | 5 end
+//  6 grid-barrier arrive | 7 phase-2 operands in smem
+//  8..31 consumer: tile i ready (full barrier passed) | 32..55 producer: copy i issued | 62,63 globaltimer
+__device__ __forceinline__ void ts_mark(unsigned long long* ts, int slot) {
+  if (ts != nullptr) ts[size_t(blockIdx.x) * 64 + slot] = clock64();
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Phase-2 operand loaders (global/L2 -> smem), loads batched in registers so they overlap.
+template <int CHP>
+__device__ __forceinline__ void load_g_tile(float* gS, const float* g, int v0, int Bv, int F, int R, int j,
+                                            int C, int c_off, int CHc, int tid) {
+  const int c4n = CHc >> 2;
+  const int total = kVideoTile * c4n;
+  if (F == 1) {
+    constexpr int U = 8;
+    for (int base = tid; base < total; base += U * kFusedThreads) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * kFusedThreads;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < total) {
+          const int row = idx / c4n, c4 = idx - row * c4n;
+          if (v0 + row < Bv)
+            v[u] = __ldcg(reinterpret_cast<const float4*>(g + (size_t(v0 + row) * R + j) * C + c_off + c4 * 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * kFusedThreads;
+        if (idx < total) {
+          const int row = idx / c4n, c4 = idx - row * c4n;
+          *reinterpret_cast<float4*>(gS + row * CHP + c4 * 4) = v[u];
+        }
+      }
+    }
+  } else {
+    for (int idx = tid; idx < total; idx += kFusedThreads) {
+      const int row = idx / c4n, c4 = idx - row * c4n;
+      const int v = v0 + row;
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < Bv) {
+        const float* src = g + (size_t(v) * F * R + j) * C + c_off + c4 * 4;
+        int fr = 0;
+        for (; fr + 4 <= F; fr += 4) {
+          float4 t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) t[u] = __ldcg(reinterpret_cast<const float4*>(src + size_t(fr + u) * R * C));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { sum.x += t[u].x; sum.y += t[u].y; sum.z += t[u].z; sum.w += t[u].w; }
+        }
+        for (; fr < F; ++fr) {
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(src + size_t(fr) * R * C));
+          sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+        }
+      }
+      *reinterpret_cast<float4*>(gS + row * CHP + c4 * 4) = sum;
+    }
+  }
+}
+
+__device__ __forceinline__ void load_w_tile(float* Ws, const float* Wj, int K, int c_off, int CHc, int kp,
+                                            int k_hi, int tid) {
+  const int total = CHc * kColTile;
+  constexpr int U = 8;
+  for (int base = tid; base < total; base += U * kFusedThreads) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * kFusedThreads;
+      v[u] = 0.f;
+      if (idx < total) {
+        const int c = idx >> 4, k = kp + (idx & 15);
+        if (k < k_hi) v[u] = __ldg(Wj + size_t(c_off + c) * K + k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * kFusedThreads;
+      if (idx < total) Ws[idx] = v[u];
+    }
+  }
+}
+
 template <int Q, int RMAX, int MODE>
 __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const FusedParams p) {
   using L = Smem<Q, RMAX>;
   constexpr int C = L::C;
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* red = reinterpret_cast<float*>(smem + L::kOffRed);
+  float* slots = reinterpret_cast<float*>(smem + L::kOffSlots);
+  float* statS = reinterpret_cast<float*>(smem + L::kOffStat);
   float* partS = reinterpret_cast<float*>(smem + L::kOffPart);
-  float* stats = reinterpret_cast<float*>(smem + L::kOffStats);
   float* scl = reinterpret_cast<float*>(smem + L::kOffScl);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
   uint64_t* full = bars;
   uint64_t* empty = bars + 8;
   uint64_t* parts_ready = bars + 16;
-  uint64_t* parts_free = bars + 17;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -88,23 +179,68 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
   const int cluster_id = blockIdx.x / csize;
   const int nclusters = gridDim.x / csize;
   const int R = p.R;
+  const int Cp = C / int(csize);  // channels owned by one CTA of the cluster (combine + phase 2)
+  const int row_lo = int((long long)p.HW * crank / csize);
+  const int row_hi = int((long long)p.HW * (crank + 1) / csize);
 
   if (tid == 0) {
-    for (int i = 0; i < L::kStages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kConsumerWarps);
-    }
-    mbar_init(parts_ready, csize);
-    mbar_init(parts_free, csize);
-    fence_mbar_init();
+    ts_mark(p.ts, 0);
+    if (p.ts) p.ts[size_t(blockIdx.x) * 64 + 62] = globaltimer_ns();
   }
-  cluster_sync_all();  // barrier inits visible cluster-wide before any remote arrive
+
+  // =========================================================================== phase 1
+  if (warp == kConsumerWarps) {
+    // -------------------------------------------------- producer warp: owns the stage barriers
+    if (lane == 0) {
+      for (int i = 0; i < L::kStages; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], kConsumerWarps);
+      }
+      mbar_init(parts_ready, csize);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    cluster_arrive();  // publishes the barrier inits; this warp's matching wait comes after its copy loop
+    if (p.do_phase1) {
+      // Start streaming before the rest of the CTA has even synchronised: the first ring fill only
+      // needs the barriers this warp just initialised.
+      const uint64_t pol = l2_policy_evict_first();
+      const int pieces = p.dbg_pieces > 0 ? p.dbg_pieces : 1;  // copies per tile, one per lane
+      uint32_t stage = 0, phase = 0;
+      int issued = 0;
+      for (int b = cluster_id; b < p.B; b += nclusters) {
+        const float* xb = p.X + (size_t(b) * p.HW) * C;
+        for (int t0 = row_lo; t0 < row_hi; t0 += kRowsPerStage) {
+          const int rows = min(kRowsPerStage, row_hi - t0);
+          const uint32_t bytes = uint32_t(rows) * C * 4u;
+          if (lane == 0) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full[stage], bytes);
+          }
+          __syncwarp();
+          const uint32_t piece = uint32_t(kRowsPerStage) * C * 4u / uint32_t(pieces);
+          const uint32_t off = uint32_t(lane) * piece;
+          if (lane < pieces && off < bytes)
+            bulk_g2s(smem + stage * L::kStageBytes + off,
+                     reinterpret_cast<const uint8_t*>(xb + size_t(t0) * C) + off, min(piece, bytes - off),
+                     &full[stage], pol);
+          if (lane == 0 && issued < 24) ts_mark(p.ts, 32 + issued);
+          ++issued;
+          if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    cluster_wait();
+  } else {
+    cluster_arrive();
+    cluster_wait();  // barrier inits of every CTA of the cluster are visible (remote arrives come later)
+  }
+  if (tid == 0) ts_mark(p.ts, 1);
 
   // Warm L2 with this CTA's phase-2 weight slice while phase 1 streams X.
   if (p.do_phase1 && p.do_phase2 && tid < kConsumerThreads) {
     const int k_lo = int((long long)p.K * cluster_id / nclusters);
     const int k_hi = int((long long)p.K * (cluster_id + 1) / nclusters);
-    const int Cp = C / int(csize);
     if (k_hi > k_lo) {
       for (int j = 0; j < R; ++j)
         for (int c = tid; c < Cp; c += kConsumerThreads) {
@@ -115,219 +251,209 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
     }
   }
 
-  // =========================================================================== phase 1
-  if (p.do_phase1) {
-    const int row_lo = int((long long)p.HW * crank / csize);
-    const int row_hi = int((long long)p.HW * (crank + 1) / csize);
-    if (warp == kConsumerWarps) {
-      // ------------------------------------------------ producer: one lane drives the copy engine
-      if (lane == 0) {
-        const uint64_t pol = l2_policy_evict_first();
-        uint32_t stage = 0, phase = 0;
-        for (int b = cluster_id; b < p.B; b += nclusters) {
-          const float* xb = p.X + (size_t(b) * p.HW) * C;
-          for (int t0 = row_lo; t0 < row_hi; t0 += kRowsPerStage) {
-            const int rows = min(kRowsPerStage, row_hi - t0);
-            const uint32_t bytes = uint32_t(rows) * C * 4u;
-            mbar_wait(&empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full[stage], bytes);
-            bulk_g2s(smem + stage * L::kStageBytes, xb + size_t(t0) * C, bytes, &full[stage], pol);
-            if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    } else {
-      // ------------------------------------------------ consumers: warp w owns channels [w C/8, (w+1) C/8)
-      const int col0 = warp * (C / kConsumerWarps) + lane * 4;  // + q*128
-      float4 wv[Q];
-      float c0 = 0.f;
-      if (p.attn_in == nullptr) {
+  if (p.do_phase1 && warp < kConsumerWarps) {
+    // -------------------------------------------------- consumers: warp w owns channels [w C/8, (w+1) C/8)
+    const int col0 = warp * (C / kConsumerWarps) + lane * 4;  // + q*128
+    float4 wv[Q];
+    float c0 = 0.f;
+    if (p.attn_in == nullptr) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) wv[q] = __ldg(reinterpret_cast<const float4*>(p.attn_w[0] + col0 + q * 128));
-        c0 = __ldg(p.attn_b[0]);
-      }
-      float cw[RMAX], cb[RMAX];  // chain coefficients a_r = cw[r] a_{r-1} + cb[r], r >= 1
+      for (int q = 0; q < Q; ++q) wv[q] = __ldg(reinterpret_cast<const float4*>(p.attn_w[0] + col0 + q * 128));
+      c0 = __ldg(p.attn_b[0]);
+    }
+    float cw[RMAX], cb[RMAX];  // chain coefficients a_r = cw[r] a_{r-1} + cb[r], r >= 1
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      cw[j] = (j >= 1 && j < R) ? __ldg(p.attn_w[j]) : 0.f;
+      cb[j] = (j >= 1 && j < R) ? __ldg(p.attn_b[j]) : 0.f;
+    }
+    uint32_t stage = 0, phase = 0, tile_ctr = 0, img_iter = 0;
+    for (int b = cluster_id; b < p.B; b += nclusters, ++img_iter) {
+      float f[RMAX][Q * 4];
+      float s[RMAX];
+      float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < RMAX; ++j) {
-        cw[j] = (j >= 1 && j < R) ? __ldg(p.attn_w[j]) : 0.f;
-        cb[j] = (j >= 1 && j < R) ? __ldg(p.attn_b[j]) : 0.f;
+        s[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < Q * 4; ++i) f[j][i] = 0.f;
       }
-      uint32_t stage = 0, phase = 0, tile_ctr = 0, img_iter = 0;
-      for (int b = cluster_id; b < p.B; b += nclusters, ++img_iter) {
-        float f[RMAX][Q * 4];
-        float s[RMAX];
-        float mx = -INFINITY;
+      for (int t0 = row_lo; t0 < row_hi; t0 += kRowsPerStage, ++tile_ctr) {
+        const int rows = min(kRowsPerStage, row_hi - t0);
+        const float* st = reinterpret_cast<const float*>(smem + stage * L::kStageBytes);
+        mbar_wait(&full[stage], phase);
+        if (tid == 0 && tile_ctr < 24) ts_mark(p.ts, 8 + int(tile_ctr));
+        float4 x[kRowsPerStage][Q];
 #pragma unroll
-        for (int j = 0; j < RMAX; ++j) {
-          s[j] = 0.f;
+        for (int r = 0; r < kRowsPerStage; ++r)
 #pragma unroll
-          for (int i = 0; i < Q * 4; ++i) f[j][i] = 0.f;
-        }
-        for (int t0 = row_lo; t0 < row_hi; t0 += kRowsPerStage, ++tile_ctr) {
-          const int rows = min(kRowsPerStage, row_hi - t0);
-          const float* st = reinterpret_cast<const float*>(smem + stage * L::kStageBytes);
-          mbar_wait(&full[stage], phase);
-          float4 x[kRowsPerStage][Q];
+          for (int q = 0; q < Q; ++q)
+            x[r][q] = (r < rows) ? *reinterpret_cast<const float4*>(st + r * C + col0 + q * 128)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        float a[kRowsPerStage];
+        if (p.attn_in == nullptr) {
+          float pd[kRowsPerStage];
+#pragma unroll
+          for (int r = 0; r < kRowsPerStage; ++r) {
+            pd[r] = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) pd[r] += dot4(x[r][q], wv[q]);
+          }
+          // x is in registers now: hand the stage back to the copy engine
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+#pragma unroll
+          for (int r = 0; r < kRowsPerStage; ++r) pd[r] = warp_sum(pd[r]);
+          float* part = partS + (tile_ctr & 1u) * (kRowsPerStage * 8);
+          if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < kRowsPerStage; ++r) part[r * 8 + warp] = pd[r];
+          }
+          named_bar_sync(1, kConsumerThreads);
+#pragma unroll
+          for (int r = 0; r < kRowsPerStage; ++r) {
+            const float4 p0 = *reinterpret_cast<const float4*>(part + r * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
+            a[r] = c0 + (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w)));
+          }
+        } else {
 #pragma unroll
           for (int r = 0; r < kRowsPerStage; ++r)
+            a[r] = (r < rows) ? __ldg(p.attn_in + size_t(b) * p.HW + t0 + r) : 0.f;
+        }
+        if (p.attn_raw != nullptr && tid == 0) {
 #pragma unroll
-            for (int q = 0; q < Q; ++q)
-              x[r][q] = (r < rows) ? *reinterpret_cast<const float4*>(st + r * C + col0 + q * 128)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-          float a[kRowsPerStage];
-          if (p.attn_in == nullptr) {
-            float pd[kRowsPerStage];
+          for (int r = 0; r < kRowsPerStage; ++r)
+            if (r < rows) p.attn_raw[size_t(b) * p.HW + t0 + r] = a[r];
+        }
+        if (MODE == MODE_SOFTMAX) {
+          float tmax = -INFINITY;
 #pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r) {
-              pd[r] = 0.f;
+          for (int r = 0; r < kRowsPerStage; ++r)
+            if (r < rows) tmax = fmaxf(tmax, a[r]);
+          const float mnew = fmaxf(mx, tmax);
+          const float sc = expf(mx - mnew);  // exp(-inf) == 0 on the first tile
+          mx = mnew;
+          s[0] *= sc;
 #pragma unroll
-              for (int q = 0; q < Q; ++q) pd[r] += dot4(x[r][q], wv[q]);
+          for (int i = 0; i < Q * 4; ++i) f[0][i] *= sc;
+#pragma unroll
+          for (int r = 0; r < kRowsPerStage; ++r) {
+            if (r < rows) {
+              const float e = expf(a[r] - mx);
+              s[0] += e;
+#pragma unroll
+              for (int q = 0; q < Q; ++q) axpy4(&f[0][q * 4], e, x[r][q]);
             }
-            // x is in registers now: hand the stage back to the copy engine
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-#pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r) pd[r] = warp_sum(pd[r]);
-            float* part = partS + (tile_ctr & 1u) * (kRowsPerStage * 8);
-            if (lane == 0) {
-#pragma unroll
-              for (int r = 0; r < kRowsPerStage; ++r) part[r * 8 + warp] = pd[r];
-            }
-            named_bar_sync(1, kConsumerThreads);
-#pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r) {
-              const float4 p0 = *reinterpret_cast<const float4*>(part + r * 8);
-              const float4 p1 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
-              a[r] = c0 + (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w)));
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r)
-              a[r] = (r < rows) ? __ldg(p.attn_in + size_t(b) * p.HW + t0 + r) : 0.f;
           }
-          if (p.attn_raw != nullptr && tid == 0) {
+        } else {
 #pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r)
-              if (r < rows) p.attn_raw[size_t(b) * p.HW + t0 + r] = a[r];
-          }
-          if (MODE == MODE_SOFTMAX) {
-            float tmax = -INFINITY;
+          for (int r = 0; r < kRowsPerStage; ++r) {
+            if (r < rows) {
+              float ar = a[r];
 #pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r)
-              if (r < rows) tmax = fmaxf(tmax, a[r]);
-            const float mnew = fmaxf(mx, tmax);
-            const float sc = expf(mx - mnew);  // exp(-inf) == 0 on the first tile
-            mx = mnew;
-            s[0] *= sc;
+              for (int j = 0; j < RMAX; ++j) {
+                if (j < R) {
+                  if (j >= 1) ar = fmaf(cw[j], ar, cb[j]);
+                  const float A = (MODE == MODE_RELU) ? fmaxf(ar, 0.f) : ar;
+                  s[j] += A;
 #pragma unroll
-            for (int i = 0; i < Q * 4; ++i) f[0][i] *= sc;
-#pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r) {
-              if (r < rows) {
-                const float e = expf(a[r] - mx);
-                s[0] += e;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) axpy4(&f[0][q * 4], e, x[r][q]);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r) {
-              if (r < rows) {
-                float ar = a[r];
-#pragma unroll
-                for (int j = 0; j < RMAX; ++j) {
-                  if (j < R) {
-                    if (j >= 1) ar = fmaf(cw[j], ar, cb[j]);
-                    const float A = (MODE == MODE_RELU) ? fmaxf(ar, 0.f) : ar;
-                    s[j] += A;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) axpy4(&f[j][q * 4], A, x[r][q]);
-                  }
+                  for (int q = 0; q < Q; ++q) axpy4(&f[j][q * 4], A, x[r][q]);
                 }
               }
             }
           }
-          if (p.attn_in != nullptr) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
+        }
+        if (p.attn_in != nullptr) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+        }
+        if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+      }
+      if (tid == 0 && img_iter == 0) ts_mark(p.ts, 2);
+
+      // ------------------------------------------------ combine the p row-slices of image b (DSMEM push)
+      // slot set (img_iter & 1) of the OWNER of each channel block receives this CTA's partial.  Re-use
+      // of a set two images later is safe: passing parts_ready for image i+1 implies every peer has
+      // finished reading image i (it pushes image i+1 only after that).
+      const uint32_t set = img_iter & 1u;
+      {
+        float* slot_base = slots + size_t(set) * R * C;  // [src][j][Cp] on the owner
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const int c = col0 + q * 128;
+          const uint32_t owner = uint32_t(c / Cp);
+          const int cl = c - int(owner) * Cp;
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) {
+            if (j < R) {
+              const uint32_t ra = dsmem_addr(slot_base + (size_t(crank) * R + j) * Cp + cl, owner);
+              st_dsmem_f4(ra, make_float4(f[j][q * 4 + 0], f[j][q * 4 + 1], f[j][q * 4 + 2], f[j][q * 4 + 3]));
+            }
           }
-          if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
         }
-
-        // ---------------------------------------------- combine the p row-slices of image b (DSMEM)
-        if (img_iter > 0) mbar_wait_cluster(parts_free, (img_iter - 1) & 1u);  // my red buffer is free
+        if (tid < int(csize)) {  // my (s_r, max) to every peer's stat table
+          float* dst = statS + (size_t(set) * 16 + crank) * 8;
+          const uint32_t ra = dsmem_addr(dst, uint32_t(tid));
 #pragma unroll
-        for (int j = 0; j < RMAX; ++j)
-          if (j < R)
-#pragma unroll
-            for (int q = 0; q < Q; ++q)
-              *reinterpret_cast<float4*>(red + j * C + col0 + q * 128) =
-                  make_float4(f[j][q * 4 + 0], f[j][q * 4 + 1], f[j][q * 4 + 2], f[j][q * 4 + 3]);
-        if (tid == 0) {
-#pragma unroll
-          for (int j = 0; j < RMAX; ++j) stats[j] = s[j];
-          stats[4] = mx;
+          for (int j = 0; j < RMAX; ++j) st_dsmem_f(ra + 4u * j, s[j]);
+          st_dsmem_f(ra + 16u, mx);
         }
-        named_bar_sync(1, kConsumerThreads);
-        if (tid < int(csize)) mbar_arrive_cluster(parts_ready, tid);
-        mbar_wait_cluster(parts_ready, img_iter & 1u);  // every CTA's partial is visible
+      }
+      fence_acq_rel_cluster();
+      named_bar_sync(1, kConsumerThreads);
+      if (tid < int(csize)) mbar_arrive_cluster(parts_ready, tid);
+      mbar_wait_cluster(parts_ready, img_iter & 1u);  // every CTA's partial has landed here
 
+      const float* my_stat = statS + size_t(set) * 16 * 8;
+      if (MODE == MODE_SOFTMAX) {
         if (tid < 16) {
-          float v = 1.f;
-          if (MODE == MODE_SOFTMAX) {
-            v = 0.f;
-            if (tid < int(csize)) {
-              float M = -INFINITY;
-              for (uint32_t q = 0; q < csize; ++q) M = fmaxf(M, ld_dsmem_f(dsmem_addr(&stats[4], q)));
-              float S = 0.f;
-              for (uint32_t q = 0; q < csize; ++q)
-                S += expf(ld_dsmem_f(dsmem_addr(&stats[4], q)) - M) * ld_dsmem_f(dsmem_addr(&stats[0], q));
-              v = expf(ld_dsmem_f(dsmem_addr(&stats[4], tid)) - M) / S;
-              if (tid == 0 && crank == 0) {
-                p.smx[2 * b + 0] = M;
-                p.smx[2 * b + 1] = S;
-              }
+          float v = 0.f;
+          if (tid < int(csize)) {
+            float M = -INFINITY;
+            for (uint32_t q = 0; q < csize; ++q) M = fmaxf(M, my_stat[q * 8 + 4]);
+            float S = 0.f;
+            for (uint32_t q = 0; q < csize; ++q) S += expf(my_stat[q * 8 + 4] - M) * my_stat[q * 8 + 0];
+            v = expf(my_stat[tid * 8 + 4] - M) / S;
+            if (tid == 0 && crank == 0) {
+              p.smx[2 * b + 0] = M;
+              p.smx[2 * b + 1] = S;
             }
           }
           scl[tid] = v;
         }
         named_bar_sync(1, kConsumerThreads);
-        {
-          const int Cp = C / int(csize);
-          const int n4 = Cp / 4;
-          for (int idx = tid; idx < R * n4; idx += kConsumerThreads) {
-            const int j = idx / n4;
-            const int c = int(crank) * Cp + (idx - j * n4) * 4;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (uint32_t q = 0; q < csize; ++q) {
-              const float4 v = ld_dsmem_f4(dsmem_addr(red + j * C + c, q));
-              const float sc = scl[q];
-              acc.x = fmaf(sc, v.x, acc.x);
-              acc.y = fmaf(sc, v.y, acc.y);
-              acc.z = fmaf(sc, v.z, acc.z);
-              acc.w = fmaf(sc, v.w, acc.w);
-            }
-            *reinterpret_cast<float4*>(p.g + (size_t(b) * R + j) * C + c) = acc;
-          }
-          if (crank == 0 && tid < R) {
-            float S = 1.f;
-            if (MODE != MODE_SOFTMAX) {
-              S = 0.f;
-              for (uint32_t q = 0; q < csize; ++q) S += ld_dsmem_f(dsmem_addr(&stats[tid], q));
-            }
-            p.sn[size_t(b) * R + tid] = S;
-          }
-        }
-        named_bar_sync(1, kConsumerThreads);
-        if (tid < int(csize)) mbar_arrive_cluster(parts_free, tid);  // done reading everyone's smem
       }
-      // nobody may still be reading my shared memory when I move on / exit
-      if (img_iter > 0) mbar_wait_cluster(parts_free, (img_iter - 1) & 1u);
+      {
+        const float* slot_base = slots + size_t(set) * R * C;
+        const int n4 = Cp / 4;
+        for (int idx = tid; idx < R * n4; idx += kConsumerThreads) {
+          const int j = idx / n4;
+          const int cl = (idx - j * n4) * 4;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (uint32_t q = 0; q < csize; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(slot_base + (size_t(q) * R + j) * Cp + cl);
+            const float sc = (MODE == MODE_SOFTMAX) ? scl[q] : 1.f;
+            acc.x = fmaf(sc, v.x, acc.x);
+            acc.y = fmaf(sc, v.y, acc.y);
+            acc.z = fmaf(sc, v.z, acc.z);
+            acc.w = fmaf(sc, v.w, acc.w);
+          }
+          *reinterpret_cast<float4*>(p.g + (size_t(b) * R + j) * C + int(crank) * Cp + cl) = acc;
+        }
+        if (crank == 0 && tid < R) {
+          float S = 1.f;
+          if (MODE != MODE_SOFTMAX) {
+            S = 0.f;
+            for (uint32_t q = 0; q < csize; ++q) S += my_stat[q * 8 + tid];
+          }
+          p.sn[size_t(b) * R + tid] = S;
+        }
+      }
     }
+    if (tid == 0) ts_mark(p.ts, 3);
   }
 
-  if (p.do_phase1 && p.do_phase2) grid_barrier(p.barrier, gridDim.x);
   if (!p.do_phase2) return;
 
   // =========================================================================== phase 2
@@ -337,13 +463,30 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
     float* accS = reinterpret_cast<float*>(smem + L::kOffAcc);
     float* outP = reinterpret_cast<float*>(smem + L::kOffOut);
     constexpr int CHP = L::kChunkPad;
-    const int Cp = C / int(csize);
     const int c_base = int(crank) * Cp;
     const int CHc = min(L::kChunk, Cp);
     const int Bv = p.B / p.F;
     const int k_lo = int((long long)p.K * cluster_id / nclusters);
     const int k_hi = int((long long)p.K * (cluster_id + 1) / nclusters);
     const int ig = lane >> 2, cg = lane & 3;
+
+    // grid barrier, split: arrive -> (load the first weight tile, which does not depend on phase 1) -> wait
+    unsigned long long target = 0;
+    bool w_preloaded = false;
+    if (p.do_phase1) {
+      __syncthreads();  // this CTA's g stores are done (and the stage ring is free)
+      if (tid == 0) {
+        target = grid_arrive(p.barrier, gridDim.x);
+        ts_mark(p.ts, 6);
+      }
+      if (k_hi > k_lo) {
+        load_w_tile(Ws, p.td_w[0], p.K, c_base, CHc, k_lo, k_hi, tid);
+        w_preloaded = true;
+      }
+      if (tid == 0) grid_wait(p.barrier, target);
+      __syncthreads();
+    }
+    if (tid == 0) ts_mark(p.ts, 4);
 
     for (int v0 = 0; v0 < Bv; v0 += kVideoTile) {
       for (int kp = k_lo; kp < k_hi; kp += kColTile) {
@@ -355,27 +498,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
 
         for (int j = 0; j < R; ++j) {
           for (int cc = 0; cc < Cp; cc += CHc) {
+            const bool first = (v0 == 0 && kp == k_lo && j == 0 && cc == 0);
+            if (!first) __syncthreads();  // previous chunk fully consumed
+            load_g_tile<CHP>(gS, p.g, v0, Bv, p.F, R, j, C, c_base + cc, CHc, tid);
+            if (!(first && w_preloaded)) load_w_tile(Ws, p.td_w[j], p.K, c_base + cc, CHc, kp, k_hi, tid);
             __syncthreads();
-            const int c4n = CHc >> 2;
-            for (int idx = tid; idx < kVideoTile * c4n; idx += kFusedThreads) {
-              const int row = idx / c4n, c4 = idx - row * c4n;
-              const int v = v0 + row;
-              float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (v < Bv) {
-                for (int fr = 0; fr < p.F; ++fr) {
-                  const float4 t = ldg_cg_f4(p.g + (size_t(v * p.F + fr) * R + j) * C + c_base + cc + c4 * 4);
-                  sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
-                }
-              }
-              *reinterpret_cast<float4*>(gS + row * CHP + c4 * 4) = sum;
-            }
-            const float* Wj = p.td_w[j];
-            for (int idx = tid; idx < CHc * kColTile; idx += kFusedThreads) {
-              const int c = idx >> 4, kk = idx & 15;
-              const int k = kp + kk;
-              Ws[idx] = (k < k_hi) ? __ldg(Wj + size_t(c_base + cc + c) * p.K + k) : 0.f;
-            }
-            __syncthreads();
+            if (first && tid == 0) ts_mark(p.ts, 7);
             if (tid < kConsumerThreads) {
               const int cw = CHc / kConsumerWarps;
               const int c_begin = warp * cw;
@@ -427,11 +555,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
           const int v = v0 + (o >> 4);
           const int k = kp + (o & 15);
           if (v < Bv && k < k_hi) {
+            float part[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) part[q] = (q < int(csize)) ? ld_dsmem_f_nv(dsmem_addr(outP + o, q)) : 0.f;
             float sum = 0.f;
-            for (uint32_t q = 0; q < csize; ++q) sum += ld_dsmem_f(dsmem_addr(outP + o, q));
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sum += part[q];
             for (int j = 0; j < R; ++j) {
               float S = 0.f;
-              for (int fr = 0; fr < p.F; ++fr) S += ldg_cg_f(p.sn + size_t(v * p.F + fr) * R + j);
+              for (int fr = 0; fr < p.F; ++fr) S += __ldcg(p.sn + size_t(v * p.F + fr) * R + j);
               sum = fmaf(__ldg(p.td_b[j] + k), S, sum);
             }
             p.logits[size_t(v) * p.K + k] = sum * p.inv_scale;
@@ -440,6 +572,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
         cluster_sync_all();  // outP / accS are reused by the next pass; also guards exit
       }
     }
+  }
+  if (tid == 0) {
+    ts_mark(p.ts, 5);
+    if (p.ts) p.ts[size_t(blockIdx.x) * 64 + 63] = globaltimer_ns();
   }
 }
 

@@ -107,7 +107,9 @@ typedef struct ApaTuning {
   int32_t fused;        /* 1 = one kernel with a grid barrier, 0 = two kernels, -1 = auto             */
   int32_t max_ctas;     /* 0 = all SMs                                                                */
   int32_t no_cooperative; /* 1 = never use the cooperative-launch attribute for the fused kernel      */
-  int32_t reserved[4];
+  int32_t debug_timestamps; /* 1 = fused kernel writes a per-CTA clock64 timeline at workspace+2048    */
+  int32_t copy_pieces;  /* bulk copies per 4-row tile: 0/1 = one 32 KB copy, else 2..32 (power of two)  */
+  int32_t reserved[2];
 } ApaTuning;
 
 /* Library/ABI version (APA_ABI_VERSION of the build). */
@@ -121,7 +123,7 @@ int apa_attn_pool_check(const ApaDesc* desc);
 
 /* Bytes of device workspace apa_attn_pool_fwd needs for `desc` (and whether the optional
  * outputs are requested). 0 on invalid desc. The workspace must be 256-byte aligned and its
- * first 256 bytes must have been zeroed once (apa_attn_pool_workspace_init) before first use;
+ * first 2048 bytes (grid-barrier counters) must have been zeroed once (apa_attn_pool_workspace_init) before first use;
  * one workspace must not be used by two in-flight calls at the same time.                   */
 size_t apa_attn_pool_workspace(const ApaDesc* desc, int want_attn, int want_topdown, int want_pose);
 

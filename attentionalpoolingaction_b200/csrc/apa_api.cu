@@ -20,7 +20,7 @@ inline int mode_of(int flags) {
 }
 
 constexpr size_t kCtrlBytes = 2048;         // 256 x u64 arrival counters, indexed by gridDim.x
-constexpr size_t kTsBytes = 160 * 64 * 8;  // debug timeline: up to 160 CTAs x 64 stamps
+constexpr size_t kTsBytes = 320 * 64 * 8;  // debug timeline: up to 320 CTAs x 64 stamps
 
 struct Carve {
   size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, total;
@@ -250,7 +250,8 @@ int apa_attn_pool_fwd(const ApaDesc* d, const float* X, const ApaWeights* w, flo
     p.sn = wsf(c.sn);
     p.smx = wsf(c.smx);
     p.barrier = reinterpret_cast<unsigned long long*>(ws + c.ctrl) + ((plan.cluster * plan.nclusters) & 255);
-    p.dbg_pieces = tuning ? tuning->copy_pieces : 0;
+    p.dbg = tuning ? tuning->reserved[0] : 0;
+    p.tma_percent = (tuning && tuning->tma_percent != 0) ? (tuning->tma_percent < 0 ? 0 : (tuning->tma_percent > 100 ? 100 : tuning->tma_percent)) : 50;
     p.ts = (tuning && tuning->debug_timestamps) ? reinterpret_cast<unsigned long long*>(ws + c.ts) : nullptr;
     p.B = B; p.HW = HW; p.C = C; p.K = K; p.R = R; p.F = F;
     p.inv_scale = 1.0f / (float(HW) * float(F));

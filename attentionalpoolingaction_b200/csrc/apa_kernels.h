@@ -34,7 +34,8 @@ struct FusedParams {
   unsigned long long* ts;             // optional debug timeline, 64 words per CTA (see apa_pool_fused.cu)
   int B, HW, C, K, R, F;
   int do_phase1, do_phase2;           // fused: 1,1   split: (1,0) then (0,1)
-  int dbg_pieces;                     // bulk copies per 4-row tile (0/1 = one 32 KB copy)
+  int dbg;                            // debug bit mask (timing experiments only; results are wrong when set)
+  int tma_percent;                    // share of each CTA's row tiles loaded through the TMA ring (rest: cp.async)
   float inv_scale;                    // 1 / (HW * F)
 };
 

@@ -34,28 +34,36 @@ namespace apa {
 
 namespace {
 
+constexpr int kTileRows = 2;   // rows per tile: one TMA stage, one cp.async slot
+constexpr int kIterRows = 4;   // rows per consumer iteration = one TMA tile + one cp.async tile
+
 template <int Q, int RMAX>
 struct Smem {
   static constexpr int C = Q * 1024;
-  static constexpr int kStages = (Q == 1) ? 8 : ((RMAX == 1) ? 6 : 4);
-  static constexpr size_t kStageBytes = size_t(kRowsPerStage) * C * 4;
-  static constexpr size_t kRing = kStages * kStageBytes;
+  static constexpr int kTmaStages = (Q == 1) ? 6 : 3;
+  static constexpr int kAsyncSlots = 2;
+  static constexpr size_t kTileBytes = size_t(kTileRows) * C * 4;
+  static constexpr size_t kOffAsync = kTmaStages * kTileBytes;
+  static constexpr size_t kRing = (kTmaStages + kAsyncSlots) * kTileBytes;
   static constexpr size_t kOffSlots = kRing;                                  // float slots[2][p][R][C/p]
-  static constexpr size_t kOffStat = kOffSlots + 2 * size_t(RMAX) * C * 4;    // float stat[2][16][8]
-  static constexpr size_t kOffPart = kOffStat + 2 * 16 * 8 * 4;               // float part[2][rows][8]
-  static constexpr size_t kOffScl = kOffPart + 2 * kRowsPerStage * 8 * 4;     // float scl[16]
-  static constexpr size_t kOffBars = kOffScl + 64;                            // u64 full[8] empty[8] ready
-  static constexpr size_t kTotal = kOffBars + 8 * 18;
-  // phase-2 carve inside the ring
-  static constexpr int kChunk = (Q == 1) ? 256 : 512;            // channels per smem chunk
+  static constexpr size_t kPhase1End = kOffSlots + 2 * size_t(RMAX) * C * 4;
+  // phase-2 carve over the ring + slot buffers (both idle by then)
+  static constexpr int kChunk = 512;                             // channels per smem chunk
   static constexpr int kChunkPad = kChunk + 4;
   static constexpr size_t kOffG = 0;                             // float gS[32][kChunkPad]
+  static constexpr size_t kOffAcc = 0;                           // float accS[8][32][16] (aliases gS after use)
   static constexpr size_t kOffW = kOffG + size_t(kVideoTile) * kChunkPad * 4;  // float Ws[kChunk][16]
-  static constexpr size_t kOffAcc = kOffW + size_t(kChunk) * kColTile * 4;     // float accS[8][32][16]
-  static constexpr size_t kOffOut = kOffAcc + size_t(kConsumerWarps) * kVideoTile * kColTile * 4;
+  static constexpr size_t kOffOut = kOffW + size_t(kChunk) * kColTile * 4;     // float outP[32][16]
   static constexpr size_t kPhase2End = kOffOut + size_t(kVideoTile) * kColTile * 4;
-  static_assert(kPhase2End <= kOffStat, "phase-2 scratch must fit in the stage ring + slot buffers");
+  static_assert(size_t(kConsumerWarps) * kVideoTile * kColTile * 4 <= kOffW, "accS must fit inside gS");
+  static constexpr size_t kOffStat = (kPhase1End > kPhase2End) ? kPhase1End : kPhase2End;  // float stat[2][16][8]
+  static constexpr size_t kOffPart = kOffStat + 2 * 16 * 8 * 4;               // float part[2][4][8]
+  static constexpr size_t kOffScl = kOffPart + 2 * kIterRows * 8 * 4;         // float scl[16]
+  static constexpr size_t kOffBars = kOffScl + 64;                            // u64 full[8] empty[8] ready
+  static constexpr size_t kTotal = kOffBars + 8 * 18;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
+  // two CTAs per SM (two launches in flight overlap each other's latency-bound tail) when R == 1
+  static constexpr int kMinCtasPerSm = (RMAX == 1 && kTotal <= 113 * 1024) ? 2 : 1;
 };
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -67,6 +75,13 @@ __device__ __forceinline__ void axpy4(float* f, float a, const float4& x) {
   f[2] = fmaf(a, x.z, f[2]);
   f[3] = fmaf(a, x.w, f[3]);
 }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
+               "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_but_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // Debug timeline (ApaTuning.debug_timestamps): 64 x u64 per CTA in the workspace.
 //  0 start | 1 after cluster sync | 2 phase-1 end | 3 after DSMEM combine | 4 after grid barrier | 5 end
@@ -159,17 +174,19 @@ __device__ __forceinline__ void load_w_tile(float* Ws, const float* Wj, int K, i
 }
 
 template <int Q, int RMAX, int MODE>
-__global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, Smem<Q, RMAX>::kMinCtasPerSm)
+apa_pool_fused_kernel(const FusedParams p) {
   using L = Smem<Q, RMAX>;
   constexpr int C = L::C;
+  constexpr int TR = kTileRows;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* slots = reinterpret_cast<float*>(smem + L::kOffSlots);
   float* statS = reinterpret_cast<float*>(smem + L::kOffStat);
   float* partS = reinterpret_cast<float*>(smem + L::kOffPart);
   float* scl = reinterpret_cast<float*>(smem + L::kOffScl);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 8;
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + 8;
   uint64_t* parts_ready = bars + 16;
 
   const int tid = threadIdx.x;
@@ -180,8 +197,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
   const int nclusters = gridDim.x / csize;
   const int R = p.R;
   const int Cp = C / int(csize);  // channels owned by one CTA of the cluster (combine + phase 2)
+  // This CTA's rows of every image it touches, split between the two load paths:
+  //   A rows [rowA0, rowA0 + rowsA) arrive through the TMA ring (producer warp, cp.async.bulk)
+  //   B rows [rowB0, rowB0 + rowsB) are fetched by the consumer threads themselves with cp.async
+  // (one SM's TMA engine sustains ~42 GB/s from cold HBM; the two paths together saturate HBM).
   const int row_lo = int((long long)p.HW * crank / csize);
   const int row_hi = int((long long)p.HW * (crank + 1) / csize);
+  const int nrows = row_hi - row_lo;
+  const int tiles_total = (nrows + TR - 1) / TR;
+  const int tilesA = min(tiles_total, (tiles_total * p.tma_percent + 50) / 100);
+  const int rowsA = min(nrows, tilesA * TR);
+  const int rowsB = nrows - rowsA;
+  const int tilesB = (rowsB + TR - 1) / TR;
+  const int rowA0 = row_lo, rowB0 = row_lo + rowsA;
+  const int nIter = max(tilesA, tilesB);
 
   if (tid == 0) {
     ts_mark(p.ts, 0);
@@ -192,44 +221,36 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
   if (warp == kConsumerWarps) {
     // -------------------------------------------------- producer warp: owns the stage barriers
     if (lane == 0) {
-      for (int i = 0; i < L::kStages; ++i) {
-        mbar_init(&full[i], 1);
-        mbar_init(&empty[i], kConsumerWarps);
+      for (int i = 0; i < L::kTmaStages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], kConsumerWarps);
       }
       mbar_init(parts_ready, csize);
       fence_mbar_init();
     }
     __syncwarp();
     cluster_arrive();  // publishes the barrier inits; this warp's matching wait comes after its copy loop
-    if (p.do_phase1) {
+    if (p.do_phase1 && lane == 0) {
       // Start streaming before the rest of the CTA has even synchronised: the first ring fill only
-      // needs the barriers this warp just initialised.
+      // needs the barriers this lane just initialised.
       const uint64_t pol = l2_policy_evict_first();
-      const int pieces = p.dbg_pieces > 0 ? p.dbg_pieces : 1;  // copies per tile, one per lane
       uint32_t stage = 0, phase = 0;
       int issued = 0;
       for (int b = cluster_id; b < p.B; b += nclusters) {
-        const float* xb = p.X + (size_t(b) * p.HW) * C;
-        for (int t0 = row_lo; t0 < row_hi; t0 += kRowsPerStage) {
-          const int rows = min(kRowsPerStage, row_hi - t0);
+        const float* xb = p.X + (size_t(b) * p.HW + rowA0) * C;
+        for (int t = 0; t < tilesA; ++t) {
+          const int rows = min(TR, rowsA - t * TR);
           const uint32_t bytes = uint32_t(rows) * C * 4u;
-          if (lane == 0) {
-            mbar_wait(&empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full[stage], bytes);
-          }
-          __syncwarp();
-          const uint32_t piece = uint32_t(kRowsPerStage) * C * 4u / uint32_t(pieces);
-          const uint32_t off = uint32_t(lane) * piece;
-          if (lane < pieces && off < bytes)
-            bulk_g2s(smem + stage * L::kStageBytes + off,
-                     reinterpret_cast<const uint8_t*>(xb + size_t(t0) * C) + off, min(piece, bytes - off),
-                     &full[stage], pol);
-          if (lane == 0 && issued < 24) ts_mark(p.ts, 32 + issued);
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          bulk_g2s(smem + stage * L::kTileBytes, xb + size_t(t) * TR * C, bytes, &full_bar[stage], pol);
+          if (issued < 24) ts_mark(p.ts, 32 + issued);
           ++issued;
-          if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == L::kTmaStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
+    __syncwarp();
     cluster_wait();
   } else {
     cluster_arrive();
@@ -237,23 +258,42 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
   }
   if (tid == 0) ts_mark(p.ts, 1);
 
-  // Warm L2 with this CTA's phase-2 weight slice while phase 1 streams X.
-  if (p.do_phase1 && p.do_phase2 && tid < kConsumerThreads) {
-    const int k_lo = int((long long)p.K * cluster_id / nclusters);
-    const int k_hi = int((long long)p.K * (cluster_id + 1) / nclusters);
-    if (k_hi > k_lo) {
-      for (int j = 0; j < R; ++j)
-        for (int c = tid; c < Cp; c += kConsumerThreads) {
-          const float* row = p.td_w[j] + size_t(crank * Cp + c) * p.K;
-          prefetch_l2(row + k_lo);
-          prefetch_l2(row + k_hi - 1);
-        }
-    }
-  }
-
   if (p.do_phase1 && warp < kConsumerWarps) {
     // -------------------------------------------------- consumers: warp w owns channels [w C/8, (w+1) C/8)
     const int col0 = warp * (C / kConsumerWarps) + lane * 4;  // + q*128
+    const uint64_t pol = l2_policy_evict_first();
+    float* abuf = reinterpret_cast<float*>(smem + L::kOffAsync);
+    // cp.async of this thread's own 16-byte pieces of B tile `t` of image `img` into slot `slot`
+    auto issueB = [&](int img, int t, uint32_t slot) {
+      if (t < tilesB) {
+        const int rows = min(TR, rowsB - t * TR);
+        const float* src = p.X + (size_t(img) * p.HW + rowB0 + t * TR) * C + col0;
+        float* dst = abuf + size_t(slot) * (TR * C) + col0;
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+          if (r < rows) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) cp_async16(dst + r * C + q * 128, src + size_t(r) * C + q * 128, pol);
+          }
+      }
+      cp_async_commit();  // one group per iteration, possibly empty: keeps wait_group counting uniform
+    };
+    if (cluster_id < p.B) issueB(cluster_id, 0, 0);
+
+    // Warm L2 with this CTA's phase-2 weight slice while phase 1 streams X.
+    if (p.do_phase2) {
+      const int k_lo = int((long long)p.K * cluster_id / nclusters);
+      const int k_hi = int((long long)p.K * (cluster_id + 1) / nclusters);
+      if (k_hi > k_lo) {
+        for (int j = 0; j < R; ++j)
+          for (int c = tid; c < Cp; c += kConsumerThreads) {
+            const float* row = p.td_w[j] + size_t(crank * Cp + c) * p.K;
+            prefetch_l2(row + k_lo);
+            prefetch_l2(row + k_hi - 1);
+          }
+      }
+    }
+
     float4 wv[Q];
     float c0 = 0.f;
     if (p.attn_in == nullptr) {
@@ -267,7 +307,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
       cw[j] = (j >= 1 && j < R) ? __ldg(p.attn_w[j]) : 0.f;
       cb[j] = (j >= 1 && j < R) ? __ldg(p.attn_b[j]) : 0.f;
     }
-    uint32_t stage = 0, phase = 0, tile_ctr = 0, img_iter = 0;
+    uint32_t stage = 0, phase = 0, giter = 0, img_iter = 0;
     for (int b = cluster_id; b < p.B; b += nclusters, ++img_iter) {
       float f[RMAX][Q * 4];
       float s[RMAX];
@@ -278,97 +318,142 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
 #pragma unroll
         for (int i = 0; i < Q * 4; ++i) f[j][i] = 0.f;
       }
-      for (int t0 = row_lo; t0 < row_hi; t0 += kRowsPerStage, ++tile_ctr) {
-        const int rows = min(kRowsPerStage, row_hi - t0);
-        const float* st = reinterpret_cast<const float*>(smem + stage * L::kStageBytes);
-        mbar_wait(&full[stage], phase);
-        if (tid == 0 && tile_ctr < 24) ts_mark(p.ts, 8 + int(tile_ctr));
-        float4 x[kRowsPerStage][Q];
+      for (int it = 0; it < nIter; ++it, ++giter) {
+        if (tid == 0 && giter < 6) ts_mark(p.ts, 8 + 4 * int(giter) + 0);
+        // prefetch the B tile of the NEXT iteration (next image's first tile at an image boundary)
+        if (it + 1 < nIter) issueB(b, it + 1, (giter + 1) & 1u);
+        else if (b + nclusters < p.B) issueB(b + nclusters, 0, (giter + 1) & 1u);
+        else cp_async_commit();
+
+        const int rA = (it < tilesA) ? min(TR, rowsA - it * TR) : 0;
+        const int rB = (it < tilesB) ? min(TR, rowsB - it * TR) : 0;
+        const bool full = (rA == TR) && (rB == TR);  // CTA-uniform: fast path without per-row predicates
+        const float* st = reinterpret_cast<const float*>(smem + stage * L::kTileBytes) + col0;
+        const float* sb = abuf + size_t(giter & 1u) * (TR * C) + col0;
+        float4 x[kIterRows][Q];  // rows 0..1: TMA tile, rows 2..3: cp.async tile
+        if (it < tilesA && !(p.dbg & 4)) mbar_wait(&full_bar[stage], phase);
+        if (tid == 0 && giter < 6) ts_mark(p.ts, 8 + 4 * int(giter) + 1);
+        if (!(p.dbg & 8)) cp_async_wait_all_but_1();  // this thread's own pieces of the current B tile have landed
+        if (tid == 0 && giter < 6) ts_mark(p.ts, 8 + 4 * int(giter) + 2);
+        if (full) {
 #pragma unroll
-        for (int r = 0; r < kRowsPerStage; ++r)
+          for (int r = 0; r < TR; ++r)
 #pragma unroll
-          for (int q = 0; q < Q; ++q)
-            x[r][q] = (r < rows) ? *reinterpret_cast<const float4*>(st + r * C + col0 + q * 128)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        float a[kRowsPerStage];
-        if (p.attn_in == nullptr) {
-          float pd[kRowsPerStage];
-#pragma unroll
-          for (int r = 0; r < kRowsPerStage; ++r) {
-            pd[r] = 0.f;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) pd[r] += dot4(x[r][q], wv[q]);
-          }
-          // x is in registers now: hand the stage back to the copy engine
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[stage]);
-#pragma unroll
-          for (int r = 0; r < kRowsPerStage; ++r) pd[r] = warp_sum(pd[r]);
-          float* part = partS + (tile_ctr & 1u) * (kRowsPerStage * 8);
-          if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < kRowsPerStage; ++r) part[r * 8 + warp] = pd[r];
-          }
-          named_bar_sync(1, kConsumerThreads);
-#pragma unroll
-          for (int r = 0; r < kRowsPerStage; ++r) {
-            const float4 p0 = *reinterpret_cast<const float4*>(part + r * 8);
-            const float4 p1 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
-            a[r] = c0 + (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w)));
-          }
+            for (int q = 0; q < Q; ++q) {
+              x[r][q] = *reinterpret_cast<const float4*>(st + r * C + q * 128);
+              x[TR + r][q] = *reinterpret_cast<const float4*>(sb + r * C + q * 128);
+            }
         } else {
 #pragma unroll
-          for (int r = 0; r < kRowsPerStage; ++r)
-            a[r] = (r < rows) ? __ldg(p.attn_in + size_t(b) * p.HW + t0 + r) : 0.f;
+          for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              x[r][q] = (r < rA) ? *reinterpret_cast<const float4*>(st + r * C + q * 128)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+              x[TR + r][q] = (r < rB) ? *reinterpret_cast<const float4*>(sb + r * C + q * 128)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float a[kIterRows];
+        if (p.attn_in == nullptr) {
+          float pd[kIterRows];
+#pragma unroll
+          for (int r = 0; r < kIterRows; ++r) {
+            pd[r] = dot4(x[r][0], wv[0]);
+#pragma unroll
+            for (int q = 1; q < Q; ++q) pd[r] += dot4(x[r][q], wv[q]);
+          }
+          // the TMA tile is in registers now: hand the stage back to the copy engine
+          if (it < tilesA) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          }
+          // 4 partial dots -> one value per 8-lane group (transposed butterfly: 5 shuffles, not 20)
+          const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+          float k0 = hi16 ? pd[2] : pd[0], s0 = hi16 ? pd[0] : pd[2];
+          float k1 = hi16 ? pd[3] : pd[1], s1 = hi16 ? pd[1] : pd[3];
+          k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          float kk = hi8 ? k1 : k0;
+          const float ss = hi8 ? k0 : k1;
+          kk += __shfl_xor_sync(0xffffffffu, ss, 8);
+          kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+          kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+          kk += __shfl_xor_sync(0xffffffffu, kk, 1);  // lanes 8r..8r+7 hold row r's partial of this warp
+          float* part = partS + (giter & 1u) * (kIterRows * 8);
+          if ((lane & 7) == 0) part[(lane >> 3) * 8 + warp] = kk;
+          if (!(p.dbg & 1)) named_bar_sync(1, kConsumerThreads);
+          if (tid == 0 && giter < 6) ts_mark(p.ts, 8 + 4 * int(giter) + 3);
+          // second level: lane l holds part[l] = (row l/8, warp l%8); sum the 8-lane groups, broadcast
+          float v = part[lane];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+#pragma unroll
+          for (int r = 0; r < kIterRows; ++r) a[r] = c0 + __shfl_sync(0xffffffffu, v, 8 * r);
+        } else {
+#pragma unroll
+          for (int r = 0; r < TR; ++r) {
+            a[r] = (r < rA) ? __ldg(p.attn_in + size_t(b) * p.HW + rowA0 + it * TR + r) : 0.f;
+            a[TR + r] = (r < rB) ? __ldg(p.attn_in + size_t(b) * p.HW + rowB0 + it * TR + r) : 0.f;
+          }
         }
         if (p.attn_raw != nullptr && tid == 0) {
 #pragma unroll
-          for (int r = 0; r < kRowsPerStage; ++r)
-            if (r < rows) p.attn_raw[size_t(b) * p.HW + t0 + r] = a[r];
+          for (int r = 0; r < TR; ++r) {
+            if (r < rA) p.attn_raw[size_t(b) * p.HW + rowA0 + it * TR + r] = a[r];
+            if (r < rB) p.attn_raw[size_t(b) * p.HW + rowB0 + it * TR + r] = a[TR + r];
+          }
         }
-        if (MODE == MODE_SOFTMAX) {
+        // validity as a multiplier keeps the accumulation branch-free (x of an absent row is zero)
+        float valid[kIterRows];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          valid[r] = (full || r < rA) ? 1.f : 0.f;
+          valid[TR + r] = (full || r < rB) ? 1.f : 0.f;
+        }
+        if (p.dbg & 2) {
+          s[0] += a[0] + a[1] + a[2] + a[3] + x[0][0].x + x[1][0].y + x[2][0].z + x[3][0].w;
+        } else if (MODE == MODE_SOFTMAX) {
           float tmax = -INFINITY;
 #pragma unroll
-          for (int r = 0; r < kRowsPerStage; ++r)
-            if (r < rows) tmax = fmaxf(tmax, a[r]);
+          for (int r = 0; r < kIterRows; ++r) tmax = fmaxf(tmax, valid[r] != 0.f ? a[r] : -INFINITY);
           const float mnew = fmaxf(mx, tmax);
-          const float sc = expf(mx - mnew);  // exp(-inf) == 0 on the first tile
+          const float sc = (mnew == -INFINITY) ? 1.f : expf(mx - mnew);  // exp(-inf) == 0 on the first tile
           mx = mnew;
           s[0] *= sc;
 #pragma unroll
           for (int i = 0; i < Q * 4; ++i) f[0][i] *= sc;
 #pragma unroll
-          for (int r = 0; r < kRowsPerStage; ++r) {
-            if (r < rows) {
-              const float e = expf(a[r] - mx);
-              s[0] += e;
+          for (int r = 0; r < kIterRows; ++r) {
+            const float e = valid[r] != 0.f ? expf(a[r] - mx) : 0.f;
+            s[0] += e;
 #pragma unroll
-              for (int q = 0; q < Q; ++q) axpy4(&f[0][q * 4], e, x[r][q]);
-            }
+            for (int q = 0; q < Q; ++q) axpy4(&f[0][q * 4], e, x[r][q]);
           }
         } else {
 #pragma unroll
-          for (int r = 0; r < kRowsPerStage; ++r) {
-            if (r < rows) {
-              float ar = a[r];
+          for (int r = 0; r < kIterRows; ++r) {
+            float ar = a[r];
 #pragma unroll
-              for (int j = 0; j < RMAX; ++j) {
-                if (j < R) {
-                  if (j >= 1) ar = fmaf(cw[j], ar, cb[j]);
-                  const float A = (MODE == MODE_RELU) ? fmaxf(ar, 0.f) : ar;
-                  s[j] += A;
+            for (int j = 0; j < RMAX; ++j) {
+              if (j < R) {
+                if (j >= 1) ar = fmaf(cw[j], ar, cb[j]);
+                const float A = ((MODE == MODE_RELU) ? fmaxf(ar, 0.f) : ar) * valid[r];
+                s[j] += A;
 #pragma unroll
-                  for (int q = 0; q < Q; ++q) axpy4(&f[j][q * 4], A, x[r][q]);
-                }
+                for (int q = 0; q < Q; ++q) axpy4(&f[j][q * 4], A, x[r][q]);
               }
             }
           }
         }
-        if (p.attn_in != nullptr) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[stage]);
+        if (it < tilesA) {
+          if (p.attn_in != nullptr) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          }
+          if (++stage == L::kTmaStages) { stage = 0; phase ^= 1u; }
         }
-        if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
       }
       if (tid == 0 && img_iter == 0) ts_mark(p.ts, 2);
 
@@ -537,6 +622,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) apa_pool_fused_kernel(const 
           }
         }
         // combine the 8 channel-split warps, then the p channel-split CTAs
+        __syncthreads();  // accS aliases gS: every warp is done reading its operands
         if (tid < kConsumerThreads) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)

@@ -90,7 +90,7 @@ class ApaTuning(ctypes.Structure):
         ("max_ctas", ctypes.c_int32),
         ("no_cooperative", ctypes.c_int32),
         ("debug_timestamps", ctypes.c_int32),
-        ("copy_pieces", ctypes.c_int32),
+        ("tma_percent", ctypes.c_int32),
         ("reserved", ctypes.c_int32 * 2),
     ]
 
@@ -185,11 +185,11 @@ def make_desc(batch, hw, channels, num_classes, frames=1, rank=1, flags=APA_FLAG
     return d
 
 
-def make_tuning(cluster_size=0, fused=-1, max_ctas=0, no_cooperative=0, debug_timestamps=0, copy_pieces=0):
+def make_tuning(cluster_size=0, fused=-1, max_ctas=0, no_cooperative=0, debug_timestamps=0, tma_percent=0):
     t = ApaTuning()
     t.cluster_size, t.fused, t.max_ctas = int(cluster_size), int(fused), int(max_ctas)
     t.no_cooperative, t.debug_timestamps = int(no_cooperative), int(debug_timestamps)
-    t.copy_pieces = int(copy_pieces)
+    t.tma_percent = int(tma_percent)
     return t
 
 

@@ -105,15 +105,34 @@ class ClockSampler(object):
         return out
 
 
+def _best_thread_count(fn):
+    """The CPU arm gets its best shot: sweep the intra-op thread count (all cores is often NOT the fastest
+    for this memory-bound graph on a many-core host) and keep the fastest; leaves torch set to it."""
+    import torch
+    ncpu = os.cpu_count() or 1
+    cands = sorted(set(c for c in (8, 16, 32, 64, ncpu) if c <= ncpu))
+    best, best_t = ncpu, float("inf")
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            fn()
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            if dt < best_t:
+                best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_port_rate(seconds, images_per_call=B_PER_GPU):
     """images/s of the op-for-op PyTorch-CPU fp32 direct-form port (oracle (ii)), all host threads."""
     import torch
     from oracle import attn_pool_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     fl = dict(orc.DEFAULT_FLAGS, **FLAGS)
     params = {k: torch.from_numpy(v) for k, v in orc.make_params(K, C, flags=fl, seed=42).items()}
     X = torch.from_numpy(orc.make_features(images_per_call, HW, C, seed=42))
+    cores = _best_thread_count(lambda: orc.attn_pool_head_torch_cpu(X, params, fl, K))
     with torch.no_grad():
         orc.attn_pool_head_torch_cpu(X, params, fl, K)  # warm-up
         n, t0 = 0, time.perf_counter()
@@ -133,12 +152,12 @@ def run_reference(args, rank, world):
         return
     import torch
     from oracle import attn_pool_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     fl = dict(orc.DEFAULT_FLAGS, **FLAGS)
     params = {k: torch.from_numpy(v) for k, v in orc.make_params(K, C, flags=fl, seed=42).items()}
     # bound the whole run to ~2 minutes: shrink the per-step sample if K is large
     probe = torch.from_numpy(orc.make_features(4, HW, C, seed=42))
+    cores = _best_thread_count(lambda: orc.attn_pool_head_torch_cpu(
+        torch.from_numpy(orc.make_features(B_PER_GPU, HW, C, seed=42)), params, fl, K))
     with torch.no_grad():
         orc.attn_pool_head_torch_cpu(probe, params, fl, K)
         t0 = time.perf_counter()
@@ -179,6 +198,8 @@ def main():
     ap.add_argument("--cluster", type=int, default=0, help="force CTAs per image (0 = auto)")
     ap.add_argument("--fused", type=int, default=-1, help="1 fused kernel, 0 two kernels, -1 auto")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="independent batches in flight (1 or 2)")
+    ap.add_argument("--tma-percent", type=int, default=0, help="0 = library default")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=30)
     args = ap.parse_args()
@@ -208,22 +229,28 @@ def main():
     fl = dict(orc.DEFAULT_FLAGS, **FLAGS)
     params = orc.make_params(K, C, flags=fl, seed=42)
     bits, rnk = ops.flags_from_cfg_net(fl)
-    tuning = ops.make_tuning(args.cluster, args.fused)
-    op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, rank=rnk,
-                        flags=bits, tuning=tuning, device=dev)
+    tuning = ops.make_tuning(args.cluster, args.fused, tma_percent=args.tma_percent)
+    nstreams = max(1, min(2, args.streams))
+    # one op (= one workspace) per in-flight batch: consecutive steps are independent batches, so two
+    # of them overlap on the GPU (one streams X from HBM while the other is in its latency-bound tail)
+    opl = [ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, rank=rnk,
+                          flags=bits, tuning=tuning, device=dev) for _ in range(nstreams)]
+    op = opl[0]
     plan = ops.attn_pool_plan(op.desc(B_PER_GPU), tuning)
 
     # ring of inputs > 2x L2 so that every step streams X from HBM
     nbuf = max(2, -(-2 * L2_BYTES // X_BYTES) + 1)
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     ring = [torch.relu(torch.randn((B_PER_GPU, HW, C), device=dev, generator=g)) for _ in range(nbuf)]
-    logits = torch.empty((B_PER_GPU, K), device=dev)
-    gathered = torch.empty((world * B_PER_GPU, K), device=dev) if world > 1 else None
+    logits_l = [torch.empty((B_PER_GPU, K), device=dev) for _ in range(nstreams)]
+    logits = logits_l[0]
+    gathered_l = [torch.empty((world * B_PER_GPU, K), device=dev) if world > 1 else None for _ in range(nstreams)]
 
     def step(i, with_collective=True):
-        op(ring[i % nbuf], logits=logits)
+        j = i % nstreams
+        opl[j](ring[i % nbuf], logits=logits_l[j])
         if world > 1 and with_collective:
-            apa_dist.all_gather_logits(logits, gathered)
+            apa_dist.all_gather_logits(logits_l[j], gathered_l[j])
 
     # parity spot-check of what is being timed (first buffer, rank-local) -- outside timed regions
     step(0)
@@ -233,25 +260,37 @@ def main():
     assert parity <= 1e-4, "bench parity check failed: %.3e" % parity
 
     side = torch.cuda.Stream(device=dev)
+    lanes = [side] + [torch.cuda.Stream(device=dev) for _ in range(nstreams - 1)]
+
+    def enqueue(cnt, with_collective):
+        """`cnt` steps on the current stream, step i on lane i % nstreams (fork/join around the extra lane)."""
+        cur = torch.cuda.current_stream(dev)
+        for ln in lanes[1:]:
+            ln.wait_stream(cur)
+        for i in range(cnt):
+            ln = cur if i % nstreams == 0 else lanes[i % nstreams]
+            with torch.cuda.stream(ln):
+                step(i, with_collective)
+        for ln in lanes[1:]:
+            cur.wait_stream(ln)
 
     def make_runner(nsteps, with_collective):
         """Returns run() that enqueues exactly `nsteps` steps; CUDA graphs of one ring pass when possible."""
         if args.no_graph or nsteps == 0:
-            return (lambda: [step(i, with_collective) for i in range(nsteps)]), "stream"
+            return (lambda: enqueue(nsteps, with_collective)), "stream"
         try:
-            full, rem = divmod(nsteps, nbuf)
+            ring_steps = nbuf * nstreams // (2 if nbuf % 2 == 0 and nstreams == 2 else 1)
+            full, rem = divmod(nsteps, ring_steps)
             graphs = []
             with torch.cuda.stream(side):
-                for cnt in ((nbuf,) if full else ()) + ((rem,) if rem else ()):
-                    for i in range(cnt):  # warm the exact launches before capture
-                        step(i, with_collective)
-                    side.synchronize()
+                for cnt in ((ring_steps,) if full else ()) + ((rem,) if rem else ()):
+                    enqueue(cnt, with_collective)  # warm the exact launches before capture
+                    torch.cuda.synchronize()
                     gr = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gr, stream=side):
-                        for i in range(cnt):
-                            step(i, with_collective)
+                        enqueue(cnt, with_collective)
                     graphs.append(gr)
-            side.synchronize()
+            torch.cuda.synchronize()
             g_full = graphs[0] if full else None
             g_rem = graphs[-1] if rem else None
 
@@ -260,11 +299,11 @@ def main():
                     g_full.replay()
                 if g_rem is not None:
                     g_rem.replay()
-            return run, "cuda-graph(%d steps/replay)" % nbuf
+            return run, "cuda-graph(%d steps/replay, %d batches in flight)" % (ring_steps, nstreams)
         except Exception as e:  # capture refused (e.g. cooperative launch): plain stream launches
             sys.stderr.write("graph capture failed (%s); using stream launches\n" % e)
             torch.cuda.synchronize()
-            return (lambda: [step(i, with_collective) for i in range(nsteps)]), "stream"
+            return (lambda: enqueue(nsteps, with_collective)), "stream"
 
     def timed(run):
         if world > 1:
@@ -343,7 +382,7 @@ def main():
                                else "single GPU",
                 "l2": "inputs rotate over %d buffers x %.1f MB (%.0f MB > 2x 126 MB L2): every step reads HBM"
                       % (nbuf, X_BYTES / 1e6, nbuf * X_BYTES / 1e6),
-                "launch": launch_mode, "plan": dict(plan), "parity_rel_err_vs_fp64_oracle": parity,
+                "launch": launch_mode, "plan": dict(plan), "batches_in_flight": nstreams, "parity_rel_err_vs_fp64_oracle": parity,
                 "clock_sampling": "nvidia-smi every 100 ms across warm-up, the K timed steps, the "
                                   "roofline loop (%d launches) and the e2e loop" % n_roof,
             },
@@ -354,6 +393,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "apa_pool_fused_kernel", "us_per_launch": ms_roof * 1e3,
+                         "duration": "CUDA-event time of the loop / launches (%d independent launches in flight)"
+                                     % nstreams,
                          "algorithmic_bytes_per_launch": ALGO_BYTES, "launches_timed": n_roof},
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "%d calls x %d images in %.1f s, PyTorch-CPU fp32 direct form"

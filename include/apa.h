@@ -108,7 +108,8 @@ typedef struct ApaTuning {
   int32_t max_ctas;     /* 0 = all SMs                                                                */
   int32_t no_cooperative; /* 1 = never use the cooperative-launch attribute for the fused kernel      */
   int32_t debug_timestamps; /* 1 = fused kernel writes a per-CTA clock64 timeline at workspace+2048    */
-  int32_t copy_pieces;  /* bulk copies per 4-row tile: 0/1 = one 32 KB copy, else 2..32 (power of two)  */
+  int32_t tma_percent;  /* share of row tiles streamed by the TMA engine (rest: cp.async); 0 = default 50,
+                           1..100 literal, negative = 0 (cp.async only)                              */
   int32_t reserved[2];
 } ApaTuning;
 

@@ -17,16 +17,20 @@ def main():
     fl = dict(orc.DEFAULT_FLAGS, SINGLE_LAYER_ATT=True)
     params = orc.make_params(K, C, flags=fl, seed=42)
     bits, rank = ops.flags_from_cfg_net(fl)
-    tun = ops.make_tuning(cluster, fused, debug_timestamps=1, copy_pieces=pieces)
+    tun = ops.make_tuning(cluster, fused, debug_timestamps=1, tma_percent=pieces)
+    tun.reserved[0] = int(sys.argv[6]) if len(sys.argv) > 6 else 0
     op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, rank=rank, flags=bits, tuning=tun)
     xs = [torch.relu(torch.randn((B, HW, C), device="cuda")) for _ in range(8)]
     for x in xs:
         op(x)
     torch.cuda.synchronize()
+    warm = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     op(xs[0])   # cold in L2 after 7 other buffers
+    if warm:
+        op(xs[0])  # second pass over the same 51 MB: served from L2
     torch.cuda.synchronize()
     d, ws, _ = op._workspace(B, (False, False, False))
-    ts = ws[2048:2048 + 160 * 64 * 8].view(torch.int64).reshape(160, 64).cpu().numpy()
+    ts = ws[2048:2048 + 320 * 64 * 8].view(torch.int64).reshape(320, 64).cpu().numpy()
     plan = ops.attn_pool_plan(d, tun)
     n = plan["grid"]
     ts = ts[:n]
@@ -41,9 +45,11 @@ def main():
     for i, nm in enumerate(names):
         print("%-14s mean %.2f  min %.2f  max %.2f us" % (nm, ev[:, i].mean(), ev[:, i].min(), ev[:, i].max()))
     tiles = rel(ts[:, 8:32]); issue = rel(ts[:, 32:56])
-    for cta in (0, 1, n // 2, n - 1):
-        nt = int((ts[cta, 8:32] > 0).sum())
-        print("CTA %d tiles ready (us):" % cta, np.round(tiles[cta, :nt], 2).tolist())
+    for cta in (0, n // 2):
+        print("CTA %d per-iteration [top, full-wait done, cp.async-wait done, bar done] (us):" % cta)
+        for i in range(6):
+            print("   it %d:" % i, np.round(tiles[cta, 4 * i:4 * i + 4], 2).tolist())
+        nt = int((ts[cta, 32:56] > 0).sum())
         print("CTA %d copies issued (us):" % cta, np.round(issue[cta, :nt], 2).tolist())
 
 main()

@@ -78,6 +78,43 @@ def test_cluster_sizes_and_split_launch(cluster, fused):
         orc.assert_parity(got, ref, TOL)
 
 
+@pytest.mark.parametrize("tma_percent", [-1, 25, 50, 75, 100])
+def test_load_path_split(tma_percent):
+    """Any split of a CTA's rows between the TMA ring and the cp.async path gives the same answer."""
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    for B, HW, flags in ((9, 196, SINGLE), (5, 225, dict(SINGLE, SOFTMAX_ATT=True)),
+                         (70, 37, dict(SINGLE, RANK=2, RELU_ATT=True))):
+        got, _, ref, _ = _run(B, HW, 2048, 393, flags, seed=6, tuning=ops.make_tuning(tma_percent=tma_percent))
+        orc.assert_parity(got, ref, TOL)
+
+
+def test_two_batches_in_flight():
+    """Two ops (two workspaces) on two streams concurrently: results identical to running them alone."""
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    fl, params, X = _setup(32, 196, 2048, 393, SINGLE, seed=8)
+    bits, rank = ops.flags_from_cfg_net(fl)
+    P = {k: torch.from_numpy(v) for k, v in params.items()}
+    opl = [ops.AttnPoolOp(P, 393, 196, rank=rank, flags=bits, device="cuda:0") for _ in range(2)]
+    Xd = [torch.from_numpy(X).cuda(), torch.from_numpy(X[::-1].copy()).cuda()]
+    alone = [opl[i](Xd[i])[0].clone() for i in range(2)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[], []]
+    for it in range(20):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                outs[i].append(opl[i](Xd[i])[0].clone())
+    torch.cuda.synchronize()
+    for i in range(2):
+        for o in outs[i]:
+            assert torch.equal(o, alone[i])
+    ref, _ = orc.attn_pool_head(X, params, fl, 393, want_pose=False)
+    orc.assert_parity(alone[0].cpu().numpy(), ref, TOL)
+
+
 def test_config003_pose_attention_rank2():
     """BASELINE config 3: attention from relu(X Wp + bp) (768 ch), RANK=2 chain (quirk Q1)."""
     from oracle import attn_pool_oracle as orc

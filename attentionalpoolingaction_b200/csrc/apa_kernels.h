@@ -13,7 +13,6 @@ enum { MODE_PLAIN = 0, MODE_RELU = 1, MODE_SOFTMAX = 2 };
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = 32 * kConsumerWarps;
 constexpr int kFusedThreads = kConsumerThreads + 32;  // + 1 bulk-copy producer warp
-constexpr int kRowsPerStage = 4;
 constexpr int kVideoTile = 32;  // videos per phase-2 tile
 constexpr int kColTile = 16;    // classes per phase-2 pass
 

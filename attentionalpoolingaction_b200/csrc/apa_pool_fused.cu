@@ -34,20 +34,17 @@ namespace apa {
 
 namespace {
 
-constexpr int kTileRows = 2;   // rows per tile: one TMA stage, one cp.async slot
-constexpr int kIterRows = 4;   // rows per consumer iteration = one TMA tile + one cp.async tile
+constexpr int kTileRows = 4;   // rows per TMA stage == rows per consumer iteration (32 KB at C = 2048)
 
 template <int Q, int RMAX>
 struct Smem {
   static constexpr int C = Q * 1024;
-  static constexpr int kTmaStages = (Q == 1) ? 6 : 3;
-  static constexpr int kAsyncSlots = 2;
+  static constexpr int kStages = (Q == 1) ? 6 : 3;                            // 96 KB ring
   static constexpr size_t kTileBytes = size_t(kTileRows) * C * 4;
-  static constexpr size_t kOffAsync = kTmaStages * kTileBytes;
-  static constexpr size_t kRing = (kTmaStages + kAsyncSlots) * kTileBytes;
-  static constexpr size_t kOffSlots = kRing;                                  // float slots[2][p][R][C/p]
-  static constexpr size_t kPhase1End = kOffSlots + 2 * size_t(RMAX) * C * 4;
-  // phase-2 carve over the ring + slot buffers (both idle by then)
+  static constexpr size_t kRing = kStages * kTileBytes;
+  static constexpr size_t kOffSlots = kRing;                                  // float slots[p][R][C/p]
+  static constexpr size_t kPhase1End = kOffSlots + size_t(RMAX) * C * 4;
+  // phase-2 carve over the ring + slot buffer (both idle by then)
   static constexpr int kChunk = 512;                             // channels per smem chunk
   static constexpr int kChunkPad = kChunk + 4;
   static constexpr size_t kOffG = 0;                             // float gS[32][kChunkPad]
@@ -56,10 +53,10 @@ struct Smem {
   static constexpr size_t kOffOut = kOffW + size_t(kChunk) * kColTile * 4;     // float outP[32][16]
   static constexpr size_t kPhase2End = kOffOut + size_t(kVideoTile) * kColTile * 4;
   static_assert(size_t(kConsumerWarps) * kVideoTile * kColTile * 4 <= kOffW, "accS must fit inside gS");
-  static constexpr size_t kOffStat = (kPhase1End > kPhase2End) ? kPhase1End : kPhase2End;  // float stat[2][16][8]
-  static constexpr size_t kOffPart = kOffStat + 2 * 16 * 8 * 4;               // float part[2][4][8]
-  static constexpr size_t kOffScl = kOffPart + 2 * kIterRows * 8 * 4;         // float scl[16]
-  static constexpr size_t kOffBars = kOffScl + 64;                            // u64 full[8] empty[8] ready
+  static constexpr size_t kOffStat = (kPhase1End > kPhase2End) ? kPhase1End : kPhase2End;  // float stat[16][8]
+  static constexpr size_t kOffPart = kOffStat + 16 * 8 * 4;                   // float part[2][4][8]
+  static constexpr size_t kOffScl = kOffPart + 2 * kTileRows * 8 * 4;         // float scl[16]
+  static constexpr size_t kOffBars = kOffScl + 64;                            // u64 full[8] empty[8] ready free
   static constexpr size_t kTotal = kOffBars + 8 * 18;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
   // two CTAs per SM (two launches in flight overlap each other's latency-bound tail) when R == 1
@@ -75,14 +72,6 @@ __device__ __forceinline__ void axpy4(float* f, float a, const float4& x) {
   f[2] = fmaf(a, x.z, f[2]);
   f[3] = fmaf(a, x.w, f[3]);
 }
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
-               "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all_but_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-
 // Debug timeline (ApaTuning.debug_timestamps): 64 x u64 per CTA in the workspace.
 //  0 start | 1 after cluster sync | 2 phase-1 end | 3 after DSMEM combine | 4 after grid barrier | 5 end
 //  6 grid-barrier arrive | 7 phase-2 operands in smem
@@ -100,7 +89,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 template <int CHP>
 __device__ __forceinline__ void load_g_tile(float* gS, const float* g, int v0, int Bv, int F, int R, int j,
                                             int C, int c_off, int CHc, int tid) {
-  const int c4n = CHc >> 2;
+  const int c4n = CHc >> 2;              // a power of two (C / cluster size, capped at kChunk)
+  const int sh = 31 - __clz(c4n);
   const int total = kVideoTile * c4n;
   if (F == 1) {
     constexpr int U = 8;
@@ -111,7 +101,7 @@ __device__ __forceinline__ void load_g_tile(float* gS, const float* g, int v0, i
         const int idx = base + u * kFusedThreads;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (idx < total) {
-          const int row = idx / c4n, c4 = idx - row * c4n;
+          const int row = idx >> sh, c4 = idx & (c4n - 1);
           if (v0 + row < Bv)
             v[u] = __ldcg(reinterpret_cast<const float4*>(g + (size_t(v0 + row) * R + j) * C + c_off + c4 * 4));
         }
@@ -120,14 +110,14 @@ __device__ __forceinline__ void load_g_tile(float* gS, const float* g, int v0, i
       for (int u = 0; u < U; ++u) {
         const int idx = base + u * kFusedThreads;
         if (idx < total) {
-          const int row = idx / c4n, c4 = idx - row * c4n;
+          const int row = idx >> sh, c4 = idx & (c4n - 1);
           *reinterpret_cast<float4*>(gS + row * CHP + c4 * 4) = v[u];
         }
       }
     }
   } else {
     for (int idx = tid; idx < total; idx += kFusedThreads) {
-      const int row = idx / c4n, c4 = idx - row * c4n;
+      const int row = idx >> sh, c4 = idx & (c4n - 1);
       const int v = v0 + row;
       float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
       if (v < Bv) {
@@ -188,6 +178,7 @@ apa_pool_fused_kernel(const FusedParams p) {
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + 8;
   uint64_t* parts_ready = bars + 16;
+  uint64_t* parts_free = bars + 17;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -197,20 +188,10 @@ apa_pool_fused_kernel(const FusedParams p) {
   const int nclusters = gridDim.x / csize;
   const int R = p.R;
   const int Cp = C / int(csize);  // channels owned by one CTA of the cluster (combine + phase 2)
-  // This CTA's rows of every image it touches, split between the two load paths:
-  //   A rows [rowA0, rowA0 + rowsA) arrive through the TMA ring (producer warp, cp.async.bulk)
-  //   B rows [rowB0, rowB0 + rowsB) are fetched by the consumer threads themselves with cp.async
-  // (one SM's TMA engine sustains ~42 GB/s from cold HBM; the two paths together saturate HBM).
   const int row_lo = int((long long)p.HW * crank / csize);
   const int row_hi = int((long long)p.HW * (crank + 1) / csize);
   const int nrows = row_hi - row_lo;
-  const int tiles_total = (nrows + TR - 1) / TR;
-  const int tilesA = min(tiles_total, (tiles_total * p.tma_percent + 50) / 100);
-  const int rowsA = min(nrows, tilesA * TR);
-  const int rowsB = nrows - rowsA;
-  const int tilesB = (rowsB + TR - 1) / TR;
-  const int rowA0 = row_lo, rowB0 = row_lo + rowsA;
-  const int nIter = max(tilesA, tilesB);
+  const int ntiles = (nrows + TR - 1) / TR;
 
   if (tid == 0) {
     ts_mark(p.ts, 0);
@@ -221,32 +202,34 @@ apa_pool_fused_kernel(const FusedParams p) {
   if (warp == kConsumerWarps) {
     // -------------------------------------------------- producer warp: owns the stage barriers
     if (lane == 0) {
-      for (int i = 0; i < L::kTmaStages; ++i) {
+      for (int i = 0; i < L::kStages; ++i) {
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], kConsumerWarps);
       }
       mbar_init(parts_ready, csize);
+      mbar_init(parts_free, csize);
       fence_mbar_init();
     }
     __syncwarp();
     cluster_arrive();  // publishes the barrier inits; this warp's matching wait comes after its copy loop
     if (p.do_phase1 && lane == 0) {
       // Start streaming before the rest of the CTA has even synchronised: the first ring fill only
-      // needs the barriers this lane just initialised.
+      // needs the barriers this lane just initialised.  One 32 KB bulk copy per 4-row tile (issuing a
+      // bulk copy costs ~0.3 us of this thread's time, so big copies: scripts/ubench_copy.cu).
       const uint64_t pol = l2_policy_evict_first();
       uint32_t stage = 0, phase = 0;
       int issued = 0;
       for (int b = cluster_id; b < p.B; b += nclusters) {
-        const float* xb = p.X + (size_t(b) * p.HW + rowA0) * C;
-        for (int t = 0; t < tilesA; ++t) {
-          const int rows = min(TR, rowsA - t * TR);
+        const float* xb = p.X + (size_t(b) * p.HW + row_lo) * C;
+        for (int t = 0; t < ntiles; ++t) {
+          const int rows = min(TR, nrows - t * TR);
           const uint32_t bytes = uint32_t(rows) * C * 4u;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
           bulk_g2s(smem + stage * L::kTileBytes, xb + size_t(t) * TR * C, bytes, &full_bar[stage], pol);
           if (issued < 24) ts_mark(p.ts, 32 + issued);
           ++issued;
-          if (++stage == L::kTmaStages) { stage = 0; phase ^= 1u; }
+          if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -261,24 +244,6 @@ apa_pool_fused_kernel(const FusedParams p) {
   if (p.do_phase1 && warp < kConsumerWarps) {
     // -------------------------------------------------- consumers: warp w owns channels [w C/8, (w+1) C/8)
     const int col0 = warp * (C / kConsumerWarps) + lane * 4;  // + q*128
-    const uint64_t pol = l2_policy_evict_first();
-    float* abuf = reinterpret_cast<float*>(smem + L::kOffAsync);
-    // cp.async of this thread's own 16-byte pieces of B tile `t` of image `img` into slot `slot`
-    auto issueB = [&](int img, int t, uint32_t slot) {
-      if (t < tilesB) {
-        const int rows = min(TR, rowsB - t * TR);
-        const float* src = p.X + (size_t(img) * p.HW + rowB0 + t * TR) * C + col0;
-        float* dst = abuf + size_t(slot) * (TR * C) + col0;
-#pragma unroll
-        for (int r = 0; r < TR; ++r)
-          if (r < rows) {
-#pragma unroll
-            for (int q = 0; q < Q; ++q) cp_async16(dst + r * C + q * 128, src + size_t(r) * C + q * 128, pol);
-          }
-      }
-      cp_async_commit();  // one group per iteration, possibly empty: keeps wait_group counting uniform
-    };
-    if (cluster_id < p.B) issueB(cluster_id, 0, 0);
 
     // Warm L2 with this CTA's phase-2 weight slice while phase 1 streams X.
     if (p.do_phase2) {
@@ -318,56 +283,38 @@ apa_pool_fused_kernel(const FusedParams p) {
 #pragma unroll
         for (int i = 0; i < Q * 4; ++i) f[j][i] = 0.f;
       }
-      for (int it = 0; it < nIter; ++it, ++giter) {
-        if (tid == 0 && giter < 6) ts_mark(p.ts, 8 + 4 * int(giter) + 0);
-        // prefetch the B tile of the NEXT iteration (next image's first tile at an image boundary)
-        if (it + 1 < nIter) issueB(b, it + 1, (giter + 1) & 1u);
-        else if (b + nclusters < p.B) issueB(b + nclusters, 0, (giter + 1) & 1u);
-        else cp_async_commit();
-
-        const int rA = (it < tilesA) ? min(TR, rowsA - it * TR) : 0;
-        const int rB = (it < tilesB) ? min(TR, rowsB - it * TR) : 0;
-        const bool full = (rA == TR) && (rB == TR);  // CTA-uniform: fast path without per-row predicates
+      for (int it = 0; it < ntiles; ++it, ++giter) {
+        const int rows = min(TR, nrows - it * TR);
+        const bool full = (rows == TR);  // CTA-uniform: fast path without per-row predicates
         const float* st = reinterpret_cast<const float*>(smem + stage * L::kTileBytes) + col0;
-        const float* sb = abuf + size_t(giter & 1u) * (TR * C) + col0;
-        float4 x[kIterRows][Q];  // rows 0..1: TMA tile, rows 2..3: cp.async tile
-        if (it < tilesA && !(p.dbg & 4)) mbar_wait(&full_bar[stage], phase);
-        if (tid == 0 && giter < 6) ts_mark(p.ts, 8 + 4 * int(giter) + 1);
-        if (!(p.dbg & 8)) cp_async_wait_all_but_1();  // this thread's own pieces of the current B tile have landed
-        if (tid == 0 && giter < 6) ts_mark(p.ts, 8 + 4 * int(giter) + 2);
+        mbar_wait(&full_bar[stage], phase);
+        if (tid == 0 && giter < 24) ts_mark(p.ts, 8 + int(giter));
+        float4 x[TR][Q];
         if (full) {
 #pragma unroll
           for (int r = 0; r < TR; ++r)
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              x[r][q] = *reinterpret_cast<const float4*>(st + r * C + q * 128);
-              x[TR + r][q] = *reinterpret_cast<const float4*>(sb + r * C + q * 128);
-            }
+            for (int q = 0; q < Q; ++q) x[r][q] = *reinterpret_cast<const float4*>(st + r * C + q * 128);
         } else {
 #pragma unroll
           for (int r = 0; r < TR; ++r)
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              x[r][q] = (r < rA) ? *reinterpret_cast<const float4*>(st + r * C + q * 128)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-              x[TR + r][q] = (r < rB) ? *reinterpret_cast<const float4*>(sb + r * C + q * 128)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int q = 0; q < Q; ++q)
+              x[r][q] = (r < rows) ? *reinterpret_cast<const float4*>(st + r * C + q * 128)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float a[kIterRows];
+        float a[TR];
         if (p.attn_in == nullptr) {
-          float pd[kIterRows];
+          float pd[TR];
 #pragma unroll
-          for (int r = 0; r < kIterRows; ++r) {
+          for (int r = 0; r < TR; ++r) {
             pd[r] = dot4(x[r][0], wv[0]);
 #pragma unroll
             for (int q = 1; q < Q; ++q) pd[r] += dot4(x[r][q], wv[q]);
           }
-          // the TMA tile is in registers now: hand the stage back to the copy engine
-          if (it < tilesA) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
-          }
+          // the tile is in registers now: hand the stage back to the copy engine
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
           // 4 partial dots -> one value per 8-lane group (transposed butterfly: 5 shuffles, not 20)
           const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
           float k0 = hi16 ? pd[2] : pd[0], s0 = hi16 ? pd[0] : pd[2];
@@ -380,44 +327,34 @@ apa_pool_fused_kernel(const FusedParams p) {
           kk += __shfl_xor_sync(0xffffffffu, kk, 4);
           kk += __shfl_xor_sync(0xffffffffu, kk, 2);
           kk += __shfl_xor_sync(0xffffffffu, kk, 1);  // lanes 8r..8r+7 hold row r's partial of this warp
-          float* part = partS + (giter & 1u) * (kIterRows * 8);
+          float* part = partS + (giter & 1u) * (TR * 8);
           if ((lane & 7) == 0) part[(lane >> 3) * 8 + warp] = kk;
-          if (!(p.dbg & 1)) named_bar_sync(1, kConsumerThreads);
-          if (tid == 0 && giter < 6) ts_mark(p.ts, 8 + 4 * int(giter) + 3);
+          named_bar_sync(1, kConsumerThreads);
           // second level: lane l holds part[l] = (row l/8, warp l%8); sum the 8-lane groups, broadcast
           float v = part[lane];
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
           v += __shfl_xor_sync(0xffffffffu, v, 1);
 #pragma unroll
-          for (int r = 0; r < kIterRows; ++r) a[r] = c0 + __shfl_sync(0xffffffffu, v, 8 * r);
+          for (int r = 0; r < TR; ++r) a[r] = c0 + __shfl_sync(0xffffffffu, v, 8 * r);
         } else {
 #pragma unroll
-          for (int r = 0; r < TR; ++r) {
-            a[r] = (r < rA) ? __ldg(p.attn_in + size_t(b) * p.HW + rowA0 + it * TR + r) : 0.f;
-            a[TR + r] = (r < rB) ? __ldg(p.attn_in + size_t(b) * p.HW + rowB0 + it * TR + r) : 0.f;
-          }
+          for (int r = 0; r < TR; ++r)
+            a[r] = (r < rows) ? __ldg(p.attn_in + size_t(b) * p.HW + row_lo + it * TR + r) : 0.f;
         }
         if (p.attn_raw != nullptr && tid == 0) {
 #pragma unroll
-          for (int r = 0; r < TR; ++r) {
-            if (r < rA) p.attn_raw[size_t(b) * p.HW + rowA0 + it * TR + r] = a[r];
-            if (r < rB) p.attn_raw[size_t(b) * p.HW + rowB0 + it * TR + r] = a[TR + r];
-          }
+          for (int r = 0; r < TR; ++r)
+            if (r < rows) p.attn_raw[size_t(b) * p.HW + row_lo + it * TR + r] = a[r];
         }
         // validity as a multiplier keeps the accumulation branch-free (x of an absent row is zero)
-        float valid[kIterRows];
+        float valid[TR];
 #pragma unroll
-        for (int r = 0; r < TR; ++r) {
-          valid[r] = (full || r < rA) ? 1.f : 0.f;
-          valid[TR + r] = (full || r < rB) ? 1.f : 0.f;
-        }
-        if (p.dbg & 2) {
-          s[0] += a[0] + a[1] + a[2] + a[3] + x[0][0].x + x[1][0].y + x[2][0].z + x[3][0].w;
-        } else if (MODE == MODE_SOFTMAX) {
+        for (int r = 0; r < TR; ++r) valid[r] = (full || r < rows) ? 1.f : 0.f;
+        if (MODE == MODE_SOFTMAX) {
           float tmax = -INFINITY;
 #pragma unroll
-          for (int r = 0; r < kIterRows; ++r) tmax = fmaxf(tmax, valid[r] != 0.f ? a[r] : -INFINITY);
+          for (int r = 0; r < TR; ++r) tmax = fmaxf(tmax, valid[r] != 0.f ? a[r] : -INFINITY);
           const float mnew = fmaxf(mx, tmax);
           const float sc = (mnew == -INFINITY) ? 1.f : expf(mx - mnew);  // exp(-inf) == 0 on the first tile
           mx = mnew;
@@ -425,7 +362,7 @@ apa_pool_fused_kernel(const FusedParams p) {
 #pragma unroll
           for (int i = 0; i < Q * 4; ++i) f[0][i] *= sc;
 #pragma unroll
-          for (int r = 0; r < kIterRows; ++r) {
+          for (int r = 0; r < TR; ++r) {
             const float e = valid[r] != 0.f ? expf(a[r] - mx) : 0.f;
             s[0] += e;
 #pragma unroll
@@ -433,7 +370,7 @@ apa_pool_fused_kernel(const FusedParams p) {
           }
         } else {
 #pragma unroll
-          for (int r = 0; r < kIterRows; ++r) {
+          for (int r = 0; r < TR; ++r) {
             float ar = a[r];
 #pragma unroll
             for (int j = 0; j < RMAX; ++j) {
@@ -447,23 +384,22 @@ apa_pool_fused_kernel(const FusedParams p) {
             }
           }
         }
-        if (it < tilesA) {
-          if (p.attn_in != nullptr) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
-          }
-          if (++stage == L::kTmaStages) { stage = 0; phase ^= 1u; }
+        if (p.attn_in != nullptr) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
         }
+        if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
       }
       if (tid == 0 && img_iter == 0) ts_mark(p.ts, 2);
 
       // ------------------------------------------------ combine the p row-slices of image b (DSMEM push)
-      // slot set (img_iter & 1) of the OWNER of each channel block receives this CTA's partial.  Re-use
-      // of a set two images later is safe: passing parts_ready for image i+1 implies every peer has
-      // finished reading image i (it pushes image i+1 only after that).
-      const uint32_t set = img_iter & 1u;
+      // Every CTA pushes its partial g into the slot buffer of the CTA that OWNS those C/p channels;
+      // one cluster-scope mbarrier round (parts_ready) publishes them.  The slot buffer is single:
+      // before pushing the next image a CTA waits on parts_free, which every owner arrives on once it
+      // has consumed its slots (only when there IS a next image, so nothing remote touches a CTA that
+      // has moved on).
+      if (img_iter > 0) mbar_wait_cluster(parts_free, (img_iter - 1) & 1u);
       {
-        float* slot_base = slots + size_t(set) * R * C;  // [src][j][Cp] on the owner
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const int c = col0 + q * 128;
@@ -472,14 +408,13 @@ apa_pool_fused_kernel(const FusedParams p) {
 #pragma unroll
           for (int j = 0; j < RMAX; ++j) {
             if (j < R) {
-              const uint32_t ra = dsmem_addr(slot_base + (size_t(crank) * R + j) * Cp + cl, owner);
+              const uint32_t ra = dsmem_addr(slots + (size_t(crank) * R + j) * Cp + cl, owner);
               st_dsmem_f4(ra, make_float4(f[j][q * 4 + 0], f[j][q * 4 + 1], f[j][q * 4 + 2], f[j][q * 4 + 3]));
             }
           }
         }
         if (tid < int(csize)) {  // my (s_r, max) to every peer's stat table
-          float* dst = statS + (size_t(set) * 16 + crank) * 8;
-          const uint32_t ra = dsmem_addr(dst, uint32_t(tid));
+          const uint32_t ra = dsmem_addr(statS + size_t(crank) * 8, uint32_t(tid));
 #pragma unroll
           for (int j = 0; j < RMAX; ++j) st_dsmem_f(ra + 4u * j, s[j]);
           st_dsmem_f(ra + 16u, mx);
@@ -490,16 +425,15 @@ apa_pool_fused_kernel(const FusedParams p) {
       if (tid < int(csize)) mbar_arrive_cluster(parts_ready, tid);
       mbar_wait_cluster(parts_ready, img_iter & 1u);  // every CTA's partial has landed here
 
-      const float* my_stat = statS + size_t(set) * 16 * 8;
       if (MODE == MODE_SOFTMAX) {
         if (tid < 16) {
           float v = 0.f;
           if (tid < int(csize)) {
             float M = -INFINITY;
-            for (uint32_t q = 0; q < csize; ++q) M = fmaxf(M, my_stat[q * 8 + 4]);
+            for (uint32_t q = 0; q < csize; ++q) M = fmaxf(M, statS[q * 8 + 4]);
             float S = 0.f;
-            for (uint32_t q = 0; q < csize; ++q) S += expf(my_stat[q * 8 + 4] - M) * my_stat[q * 8 + 0];
-            v = expf(my_stat[tid * 8 + 4] - M) / S;
+            for (uint32_t q = 0; q < csize; ++q) S += expf(statS[q * 8 + 4] - M) * statS[q * 8 + 0];
+            v = expf(statS[tid * 8 + 4] - M) / S;
             if (tid == 0 && crank == 0) {
               p.smx[2 * b + 0] = M;
               p.smx[2 * b + 1] = S;
@@ -510,14 +444,13 @@ apa_pool_fused_kernel(const FusedParams p) {
         named_bar_sync(1, kConsumerThreads);
       }
       {
-        const float* slot_base = slots + size_t(set) * R * C;
         const int n4 = Cp / 4;
         for (int idx = tid; idx < R * n4; idx += kConsumerThreads) {
           const int j = idx / n4;
           const int cl = (idx - j * n4) * 4;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           for (uint32_t q = 0; q < csize; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(slot_base + (size_t(q) * R + j) * Cp + cl);
+            const float4 v = *reinterpret_cast<const float4*>(slots + (size_t(q) * R + j) * Cp + cl);
             const float sc = (MODE == MODE_SOFTMAX) ? scl[q] : 1.f;
             acc.x = fmaf(sc, v.x, acc.x);
             acc.y = fmaf(sc, v.y, acc.y);
@@ -530,10 +463,14 @@ apa_pool_fused_kernel(const FusedParams p) {
           float S = 1.f;
           if (MODE != MODE_SOFTMAX) {
             S = 0.f;
-            for (uint32_t q = 0; q < csize; ++q) S += my_stat[q * 8 + tid];
+            for (uint32_t q = 0; q < csize; ++q) S += statS[q * 8 + tid];
           }
           p.sn[size_t(b) * R + tid] = S;
         }
+      }
+      if (b + nclusters < p.B) {  // slots / stat table consumed: peers may push the next image
+        named_bar_sync(1, kConsumerThreads);
+        if (tid < int(csize)) mbar_arrive_cluster(parts_free, tid);
       }
     }
     if (tid == 0) ts_mark(p.ts, 3);

@@ -250,8 +250,7 @@ int apa_attn_pool_fwd(const ApaDesc* d, const float* X, const ApaWeights* w, flo
     p.sn = wsf(c.sn);
     p.smx = wsf(c.smx);
     p.barrier = reinterpret_cast<unsigned long long*>(ws + c.ctrl) + ((plan.cluster * plan.nclusters) & 255);
-    p.dbg = tuning ? tuning->reserved[0] : 0;
-    p.tma_percent = (tuning && tuning->tma_percent != 0) ? (tuning->tma_percent < 0 ? 0 : (tuning->tma_percent > 100 ? 100 : tuning->tma_percent)) : 50;
+    p.early_trigger = (tuning && tuning->reserved[0]) ? 1 : 0;
     p.ts = (tuning && tuning->debug_timestamps) ? reinterpret_cast<unsigned long long*>(ws + c.ts) : nullptr;
     p.B = B; p.HW = HW; p.C = C; p.K = K; p.R = R; p.F = F;
     p.inv_scale = 1.0f / (float(HW) * float(F));

@@ -154,6 +154,16 @@ __device__ __forceinline__ float ld_dsmem_f(uint32_t raddr) {
   return v;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel in the stream (if launched with the programmatic-serialization
+// attribute) may start once every CTA of this grid has executed this (or exited).
+// wait: block until the previous grid in the stream has fully completed and its writes are visible
+// (no-op when this grid was not launched as a programmatic dependent).
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

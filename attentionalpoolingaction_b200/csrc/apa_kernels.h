@@ -33,8 +33,7 @@ struct FusedParams {
   unsigned long long* ts;             // optional debug timeline, 64 words per CTA (see apa_pool_fused.cu)
   int B, HW, C, K, R, F;
   int do_phase1, do_phase2;           // fused: 1,1   split: (1,0) then (0,1)
-  int dbg;                            // debug bit mask (timing experiments only; results are wrong when set)
-  int tma_percent;                    // share of each CTA's row tiles loaded through the TMA ring (rest: cp.async)
+  int early_trigger;                  // 1: let the next launch start as soon as this one is resident
   float inv_scale;                    // 1 / (HW * F)
 };
 
@@ -46,6 +45,7 @@ struct FusedPlan {
   int nclusters;
   int fused;    // 1: single kernel + grid barrier
   int cooperative;
+  int pdl;      // launch as a programmatic dependent of the previous kernel in the stream
   size_t smem;
 };
 

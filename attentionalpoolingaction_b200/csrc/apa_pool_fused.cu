@@ -234,9 +234,11 @@ apa_pool_fused_kernel(const FusedParams p) {
       }
     }
     __syncwarp();
+    griddep_launch_dependents();
     cluster_wait();
   } else {
     cluster_arrive();
+    if (p.early_trigger) griddep_launch_dependents();
     cluster_wait();  // barrier inits of every CTA of the cluster are visible (remote arrives come later)
   }
   if (tid == 0) ts_mark(p.ts, 1);
@@ -391,6 +393,11 @@ apa_pool_fused_kernel(const FusedParams p) {
         if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
       }
       if (tid == 0 && img_iter == 0) ts_mark(p.ts, 2);
+      // Programmatic dependent launch: once this CTA has streamed its last tile the NEXT launch may start
+      // streaming (it co-resides, 2 CTAs/SM) while this one finishes its latency-bound tail; before the
+      // first write to the (shared) workspace, make sure the PREVIOUS launch has completely finished.
+      if (b + nclusters >= p.B && !p.early_trigger) griddep_launch_dependents();
+      if (img_iter == 0) griddep_wait();
 
       // ------------------------------------------------ combine the p row-slices of image b (DSMEM push)
       // Every CTA pushes its partial g into the slot buffer of the CTA that OWNS those C/p channels;
@@ -476,6 +483,10 @@ apa_pool_fused_kernel(const FusedParams p) {
     if (tid == 0) ts_mark(p.ts, 3);
   }
 
+  if (!p.do_phase1) {
+    griddep_launch_dependents();
+    griddep_wait();
+  }
   if (!p.do_phase2) return;
 
   // =========================================================================== phase 2
@@ -662,6 +673,8 @@ cudaError_t max_clusters(KernelFn fn, size_t smem, int cluster, int* out) {
   }
   err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (err != cudaSuccess) return err;
+  // max shared-memory carve-out: the SM must be able to hold a CTA of the next launch beside this one
+  (void)cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (cluster > 8) {
     err = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (err != cudaSuccess) return err;
@@ -683,6 +696,8 @@ cudaError_t max_clusters(KernelFn fn, size_t smem, int cluster, int* out) {
     (void)cudaGetLastError();
     n = 0;  // this cluster size is not launchable here
   }
+  // The kernel fits two CTAs per SM so that the NEXT launch (programmatic dependent launch) can stream
+  // beside this launch's tail; one launch therefore only ever takes one CTA slot per SM.
   std::lock_guard<std::mutex> lk(g_occ.mu);
   if (g_occ.n < 64) g_occ.e[g_occ.n++] = {dev, fn, cluster, n};
   *out = n;
@@ -741,6 +756,7 @@ void fill_common(int C, int R, int mode, const ApaTuning* tuning, FusedPlan* pla
   plan->smem = smem_bytes(plan->Q, plan->rmax);
   plan->fused = (tuning && tuning->fused == 0) ? 0 : 1;
   plan->cooperative = 0;
+  plan->pdl = (tuning && tuning->no_pdl) ? 0 : 1;
 }
 
 }  // namespace
@@ -767,14 +783,19 @@ cudaError_t fused_make_plan(int B, int HW, int C, int K, int R, int mode, const 
   if (fn == nullptr) return cudaErrorInvalidValue;
   int nmax[5];
   static const int cand[5] = {1, 2, 4, 8, 16};
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   for (int i = 0; i < 5; ++i) {
     cudaError_t err = max_clusters(fn, plan->smem, cand[i], &nmax[i]);
     if (err != cudaSuccess) return err;
+    // The kernel fits two CTAs per SM so that the NEXT launch (programmatic dependent launch) can stream
+    // beside this launch's tail; one launch therefore only takes one CTA slot per SM (max_ctas < 0 lifts it).
+    if (!(tuning && tuning->max_ctas < 0) && sms > 0 && nmax[i] > sms / cand[i]) nmax[i] = sms / cand[i];
   }
   choose(B, HW, C, tuning, nmax, plan);
   if (plan->cluster == 0) return cudaErrorInvalidConfiguration;
-  int dev = 0, coop = 0;
-  cudaGetDevice(&dev);
+  int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   plan->cooperative = (coop && !(tuning && tuning->no_cooperative)) ? 1 : 0;
   return cudaSuccess;
@@ -782,6 +803,7 @@ cudaError_t fused_make_plan(int B, int HW, int C, int K, int R, int mode, const 
 
 namespace {
 std::atomic<int> g_coop_refused{0};  // set once if the driver refuses cooperative + cluster launches
+std::atomic<int> g_pdl_refused{0};   // set once if the driver refuses programmatic dependent launch here
 
 cudaError_t launch_one(KernelFn fn, const FusedParams& p, const FusedPlan& plan, bool coop,
                        cudaStream_t stream) {
@@ -790,20 +812,32 @@ cudaError_t launch_one(KernelFn fn, const FusedParams& p, const FusedPlan& plan,
   cfg.blockDim = dim3(kFusedThreads, 1, 1);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = stream;
-  cudaLaunchAttribute at[2];
+  cudaLaunchAttribute at[3];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = plan.cluster;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   int na = 1;
   if (coop) {
-    at[1].id = cudaLaunchAttributeCooperative;
-    at[1].val.cooperative = 1;
-    na = 2;
+    at[na].id = cudaLaunchAttributeCooperative;
+    at[na].val.cooperative = 1;
+    ++na;
+  }
+  if (plan.pdl && !g_pdl_refused.load(std::memory_order_relaxed)) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, fn, p);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, fn, p);
+  if (err != cudaSuccess && !coop && plan.pdl && !g_pdl_refused.load(std::memory_order_relaxed)) {
+    (void)cudaGetLastError();
+    g_pdl_refused.store(1, std::memory_order_relaxed);
+    cfg.numAttrs = 1;  // cluster dimension only
+    err = cudaLaunchKernelEx(&cfg, fn, p);
+  }
+  return err;
 }
 }  // namespace
 

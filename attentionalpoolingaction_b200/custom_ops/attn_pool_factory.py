@@ -89,8 +89,8 @@ class ApaTuning(ctypes.Structure):
         ("fused", ctypes.c_int32),
         ("max_ctas", ctypes.c_int32),
         ("no_cooperative", ctypes.c_int32),
+        ("no_pdl", ctypes.c_int32),
         ("debug_timestamps", ctypes.c_int32),
-        ("tma_percent", ctypes.c_int32),
         ("reserved", ctypes.c_int32 * 2),
     ]
 
@@ -185,11 +185,10 @@ def make_desc(batch, hw, channels, num_classes, frames=1, rank=1, flags=APA_FLAG
     return d
 
 
-def make_tuning(cluster_size=0, fused=-1, max_ctas=0, no_cooperative=0, debug_timestamps=0, tma_percent=0):
+def make_tuning(cluster_size=0, fused=-1, max_ctas=0, no_cooperative=0, no_pdl=0, debug_timestamps=0):
     t = ApaTuning()
     t.cluster_size, t.fused, t.max_ctas = int(cluster_size), int(fused), int(max_ctas)
-    t.no_cooperative, t.debug_timestamps = int(no_cooperative), int(debug_timestamps)
-    t.tma_percent = int(tma_percent)
+    t.no_cooperative, t.no_pdl, t.debug_timestamps = int(no_cooperative), int(no_pdl), int(debug_timestamps)
     return t
 
 

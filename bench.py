@@ -198,8 +198,10 @@ def main():
     ap.add_argument("--cluster", type=int, default=0, help="force CTAs per image (0 = auto)")
     ap.add_argument("--fused", type=int, default=-1, help="1 fused kernel, 0 two kernels, -1 auto")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--streams", type=int, default=2, help="independent batches in flight (1 or 2)")
-    ap.add_argument("--tma-percent", type=int, default=0, help="0 = library default")
+    ap.add_argument("--streams", type=int, default=1, help="independent batches in flight (1 or 2)")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch")
+    ap.add_argument("--early-trigger", type=int, default=0)
+    ap.add_argument("--no-coop", action="store_true", help="never use the cooperative launch attribute")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=30)
     args = ap.parse_args()
@@ -229,7 +231,8 @@ def main():
     fl = dict(orc.DEFAULT_FLAGS, **FLAGS)
     params = orc.make_params(K, C, flags=fl, seed=42)
     bits, rnk = ops.flags_from_cfg_net(fl)
-    tuning = ops.make_tuning(args.cluster, args.fused, tma_percent=args.tma_percent)
+    tuning = ops.make_tuning(args.cluster, args.fused, no_pdl=int(args.no_pdl), no_cooperative=int(args.no_coop))
+    tuning.reserved[0] = args.early_trigger
     nstreams = max(1, min(2, args.streams))
     # one op (= one workspace) per in-flight batch: consecutive steps are independent batches, so two
     # of them overlap on the GPU (one streams X from HBM while the other is in its latency-bound tail)

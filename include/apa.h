@@ -107,9 +107,9 @@ typedef struct ApaTuning {
   int32_t fused;        /* 1 = one kernel with a grid barrier, 0 = two kernels, -1 = auto             */
   int32_t max_ctas;     /* 0 = all SMs                                                                */
   int32_t no_cooperative; /* 1 = never use the cooperative-launch attribute for the fused kernel      */
+  int32_t no_pdl;       /* 1 = do not launch the fused kernel as a programmatic dependent of the      */
+                        /*     previous kernel in the stream (back-to-back calls then do not overlap) */
   int32_t debug_timestamps; /* 1 = fused kernel writes a per-CTA clock64 timeline at workspace+2048    */
-  int32_t tma_percent;  /* share of row tiles streamed by the TMA engine (rest: cp.async); 0 = default 50,
-                           1..100 literal, negative = 0 (cp.async only)                              */
   int32_t reserved[2];
 } ApaTuning;
 

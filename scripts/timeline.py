@@ -17,8 +17,7 @@ def main():
     fl = dict(orc.DEFAULT_FLAGS, SINGLE_LAYER_ATT=True)
     params = orc.make_params(K, C, flags=fl, seed=42)
     bits, rank = ops.flags_from_cfg_net(fl)
-    tun = ops.make_tuning(cluster, fused, debug_timestamps=1, tma_percent=pieces)
-    tun.reserved[0] = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+    tun = ops.make_tuning(cluster, fused, debug_timestamps=1, no_pdl=pieces, max_ctas=(int(sys.argv[6]) if len(sys.argv) > 6 else 0))
     op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, rank=rank, flags=bits, tuning=tun)
     xs = [torch.relu(torch.randn((B, HW, C), device="cuda")) for _ in range(8)]
     for x in xs:
@@ -40,15 +39,16 @@ def main():
     print("plan", dict(plan))
     print("kernel span (globaltimer) %.2f us" % ((ts[:, 63].max() - g0) / 1e3))
     print("CTA start skew (globaltimer) max %.2f us" % ((ts[:, 62].max() - g0) / 1e3))
+    st = np.sort((ts[:, 62] - g0) / 1e3)
+    print("CTA start times (us), every 16th:", np.round(st[::16], 2).tolist())
     names = ["start", "cluster_sync", "phase1_end", "dsmem_done", "grid_barrier", "end", "grid_arrive", "p2_operands"]
     ev = rel(ts[:, 0:8])
     for i, nm in enumerate(names):
         print("%-14s mean %.2f  min %.2f  max %.2f us" % (nm, ev[:, i].mean(), ev[:, i].min(), ev[:, i].max()))
     tiles = rel(ts[:, 8:32]); issue = rel(ts[:, 32:56])
     for cta in (0, n // 2):
-        print("CTA %d per-iteration [top, full-wait done, cp.async-wait done, bar done] (us):" % cta)
-        for i in range(6):
-            print("   it %d:" % i, np.round(tiles[cta, 4 * i:4 * i + 4], 2).tolist())
+        nt = int((ts[cta, 8:32] > 0).sum())
+        print("CTA %d tiles ready (us):" % cta, np.round(tiles[cta, :nt], 2).tolist())
         nt = int((ts[cta, 32:56] > 0).sum())
         print("CTA %d copies issued (us):" % cta, np.round(issue[cta, :nt], 2).tolist())
 

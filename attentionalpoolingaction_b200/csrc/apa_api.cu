@@ -1,6 +1,7 @@
 // apa_api.cu — the C ABI declared in include/apa.h: validation, workspace carving, path selection.
 // Host-side only; every kernel lives in apa_pool_fused.cu / apa_dense.cu.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -51,7 +52,7 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
     c.sn = take(B * R);
     c.smx = take(B * 2);
     if (want_attn) c.attn_raw = take(B * HW);
-    if (!single) c.a0 = take(B * HW);
+    if (!single) c.a0 = take(B * HW * 8);  // up to 8 partial-dot planes from the pose GEMM epilogue
   } else {
     if (!want_attn) c.A = take(B * HW * M * R);
     if (!want_topdown) c.T = take(B * HW * K * R);
@@ -212,9 +213,14 @@ int apa_attn_pool_fwd(const ApaDesc* d, const float* X, const ApaWeights* w, flo
   auto wsf = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   const int rows = B * HW;
 
-  // ---- PoseLogits scope (nets_factory.py:147-160): P = relu(X Wp + bp); PoseLogits = P Wq + bq
+  // ---- PoseLogits scope (nets_factory.py:147-160): P = relu(X Wp + bp); PoseLogits = P Wq + bq.
+  // When P only feeds the 1-wide attention conv (config 003, fused path, no PoseLogits requested) it is
+  // never written: the tensor-core GEMM's epilogue emits the partial dots relu(P).w_0 directly.
   float* P = nullptr;
-  if (need_pose_pre) {
+  const bool fuse_a0 = !single && c.path == 0 && pose_out == nullptr &&
+                       dense_gemm_tc_eligible(rows, d->pose_channels, C) &&
+                       dense_gemm_tc_dot_parts(d->pose_channels) <= 8 && getenv("APA_DENSE_SIMT") == nullptr;
+  if (need_pose_pre && !fuse_a0) {
     P = wsf(c.pose_pre);
     APA_CUDA(dense_gemm(X, C, 1, w->pose_w, d->pose_channels, w->pose_b, P, d->pose_channels, 1, 0, rows,
                         d->pose_channels, C, /*relu=*/1, stream));
@@ -235,7 +241,16 @@ int apa_attn_pool_fwd(const ApaDesc* d, const float* X, const ApaWeights* w, flo
     p.X = X;
     if (!single) {
       float* a0 = wsf(c.a0);
-      APA_CUDA(dense_gemm(S, Cs, 1, w->attn_w[0], 1, w->attn_b[0], a0, 1, 1, 0, rows, 1, Cs, 0, stream));
+      if (fuse_a0) {
+        APA_CUDA(dense_gemm_tc(X, C, 1, w->pose_w, d->pose_channels, w->pose_b, nullptr, 0, 1, 0, rows,
+                               d->pose_channels, C, /*relu=*/1, stream, w->attn_w[0], a0));
+        p.attn_in_parts = dense_gemm_tc_dot_parts(d->pose_channels);
+        p.attn_in_bias = 1;
+      } else {
+        APA_CUDA(dense_gemm(S, Cs, 1, w->attn_w[0], 1, w->attn_b[0], a0, 1, 1, 0, rows, 1, Cs, 0, stream));
+        p.attn_in_parts = 1;
+        p.attn_in_bias = 0;
+      }
       p.attn_in = a0;
     }
     for (int r = 0; r < R; ++r) {

@@ -6,8 +6,11 @@
 // K x K chain conv when PER_CLASS), :276-286 (softmax / relu), :299-309 (top-down convs),
 // :322-328 (multiply, spatial mean, rank sum), :354-374 (frame mean).
 //
-// Round-1 status: these are straightforward fp32 SIMT kernels (correct, coalesced, tiled) — the
-// tcgen05 3xTF32 replacement for dense_gemm is the next kernel on the list.
+// dense_gemm dispatches to the tcgen05 3xTF32 kernel (apa_gemm_tc.cu) when the problem is big enough;
+// the fp32 SIMT kernel below stays for tiny shapes (N == 1 attention conv, chain convs) and as the A/B
+// reference (APA_DENSE_SIMT=1).
+#include <stdlib.h>
+
 #include "apa_common.cuh"
 #include "apa_kernels.h"
 
@@ -198,6 +201,9 @@ cudaError_t dense_gemm(const float* X, int ldx, int xs, const float* W, int ldw,
                        float* Y, int ldy, int col_stride, int col_off, int M, int N, int Kd, int relu,
                        cudaStream_t stream) {
   if (M <= 0 || N <= 0) return cudaSuccess;
+  static const bool force_simt = (getenv("APA_DENSE_SIMT") != nullptr);  // A/B switch for tests and profiling
+  if (!force_simt && dense_gemm_tc_eligible(M, N, Kd))
+    return dense_gemm_tc(X, ldx, xs, W, ldw, bias, Y, ldy, col_stride, col_off, M, N, Kd, relu, stream);
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, 1);
   dense_gemm_kernel<<<grid, 256, 0, stream>>>(X, ldx, xs, W, ldw, bias, Y, ldy, col_stride, col_off, M, N, Kd,
                                               relu);
@@ -232,6 +238,8 @@ cudaError_t dense_pool(const float* A, const float* T, float* logits, int B, int
 }
 
 cudaError_t gram_launch(int B, int HW, int C, const float* X, float* G, cudaStream_t stream) {
+  static const bool force_simt = (getenv("APA_DENSE_SIMT") != nullptr);
+  if (!force_simt && C >= 64 && HW >= 16) return gram_tc(B, HW, C, X, G, stream);
   dim3 grid((C + TN - 1) / TN, (C + TM - 1) / TM, B);
   gram_kernel<<<grid, 256, 0, stream>>>(X, G, HW, C);
   return cudaGetLastError();

@@ -19,7 +19,9 @@ constexpr int kColTile = 16;    // classes per phase-2 pass
 // Parameters of the fused single-map (M == 1) kernel.  See apa_pool_fused.cu.
 struct FusedParams {
   const float* X;        // [B, HW, C]
-  const float* attn_in;  // optional precomputed a_0 [B*HW] (attention source is not X); else nullptr
+  const float* attn_in;  // optional precomputed a_0 as attn_in_parts partial sums [parts][B*HW] (attention
+                         // source is not X): a_0 = attn_b[0] * attn_in_bias + sum_p attn_in[p]; else nullptr
+  int attn_in_parts, attn_in_bias;
   const float* attn_w[APA_MAX_RANK];  // r==0: [C] (unused if attn_in); r>=1: scalar
   const float* attn_b[APA_MAX_RANK];  // scalars
   const float* td_w[APA_MAX_RANK];    // [C, K]
@@ -63,6 +65,15 @@ bool fused_supported(int C, int R);
 cudaError_t dense_gemm(const float* X, int ldx, int xs, const float* W, int ldw, const float* bias,
                        float* Y, int ldy, int col_stride, int col_off, int M, int N, int Kd, int relu,
                        cudaStream_t stream);
+// same contract on tcgen05 tensor cores (3xTF32 split, fp32 accumulate in TMEM); apa_gemm_tc.cu
+bool dense_gemm_tc_eligible(int M, int N, int Kd);
+// Y may be null; with dot_w/dot_out the epilogue also writes dense_gemm_tc_dot_parts(N) x [M] partial row dots
+// sum_n act(y[m,n]) dot_w[n] (one per half N-tile) so a following 1-wide conv never has to re-read Y.
+int dense_gemm_tc_dot_parts(int N);
+cudaError_t dense_gemm_tc(const float* X, int ldx, int xs, const float* W, int ldw, const float* bias, float* Y,
+                          int ldy, int col_stride, int col_off, int M, int N, int Kd, int relu, cudaStream_t stream,
+                          const float* dot_w = nullptr, float* dot_out = nullptr);
+cudaError_t gram_tc(int B, int HW, int C, const float* X, float* G, cudaStream_t stream);
 // attention finalisation for M == 1 given raw a_0 (chain, relu, softmax) -> attn_out [B,HW,(R)]
 cudaError_t attn_finalize_m1(const float* a0, const float* const* attn_w, const float* const* attn_b,
                              const float* smx, float* attn_out, int B, int HW, int R, int mode,

@@ -263,6 +263,7 @@ apa_pool_fused_kernel(const FusedParams p) {
 
     float4 wv[Q];
     float c0 = 0.f;
+    const float c_in = (p.attn_in != nullptr && p.attn_in_bias) ? __ldg(p.attn_b[0]) : 0.f;
     if (p.attn_in == nullptr) {
 #pragma unroll
       for (int q = 0; q < Q; ++q) wv[q] = __ldg(reinterpret_cast<const float4*>(p.attn_w[0] + col0 + q * 128));
@@ -342,7 +343,15 @@ apa_pool_fused_kernel(const FusedParams p) {
         } else {
 #pragma unroll
           for (int r = 0; r < TR; ++r)
-            a[r] = (r < rows) ? __ldg(p.attn_in + size_t(b) * p.HW + row_lo + it * TR + r) : 0.f;
+          {
+            float v = 0.f;
+            if (r < rows) {
+              const size_t gi = size_t(b) * p.HW + row_lo + it * TR + r;
+              v = c_in;
+              for (int q = 0; q < p.attn_in_parts; ++q) v += __ldg(p.attn_in + size_t(q) * p.B * p.HW + gi);
+            }
+            a[r] = v;
+          }
         }
         if (p.attn_raw != nullptr && tid == 0) {
 #pragma unroll

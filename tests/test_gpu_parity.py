@@ -136,6 +136,16 @@ def test_config003_pose_attention_rank2():
     orc.assert_parity(ep["PosePrelogitsBasedAttention"], ref_ep["PosePrelogitsBasedAttention"], TOL, "attention")
 
 
+def test_config003_fused_a0_epilogue():
+    """Config 003 without the PoseLogits end-point: the 2048->768 tensor-core GEMM never writes its output,
+    its epilogue emits relu(P).w_0 partial dots that the streaming kernel sums (plus the attention end-point)."""
+    from oracle import attn_pool_oracle as orc
+    for flags in (dict(), dict(RANK=2, RELU_ATT=True), dict(SOFTMAX_ATT=True)):
+        got, ep, ref, ref_ep = _run(5, 196, 2048, 393, flags, seed=21, want=(True, False, False))
+        orc.assert_parity(got, ref, TOL)
+        orc.assert_parity(ep["PosePrelogitsBasedAttention"], ref_ep["PosePrelogitsBasedAttention"], TOL, "attention")
+
+
 DENSE_CASES = [
     ("per_class", 2, 196, 2048, 393, dict(SINGLE, PER_CLASS=True), 1),
     ("per_class_softmax", 2, 49, 2048, 57, dict(SINGLE, PER_CLASS=True, SOFTMAX_ATT=True), 1),
@@ -257,9 +267,11 @@ def test_gram_matches_oracle():
     import torch
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     from oracle import attn_pool_oracle as orc
-    X = orc.make_features(2, 49, 256, seed=4)
-    G = ops.gram(torch.from_numpy(X).cuda()).cpu().numpy()
-    orc.assert_parity(G, orc.gram(X), TOL, "gram")
+    for (B, HW, C) in ((2, 49, 256), (3, 196, 512), (1, 784, 2048), (2, 9, 32)):
+        X = orc.make_features(B, HW, C, seed=4)
+        G = ops.gram(torch.from_numpy(X).cuda()).cpu().numpy()
+        orc.assert_parity(G, orc.gram(X), TOL, "gram %s" % ((B, HW, C),))
+        assert np.allclose(G, np.transpose(G, (0, 2, 1)), rtol=1e-4, atol=1e-4 * np.abs(G).max())
 
 
 def test_errors_are_loud():

@@ -62,6 +62,16 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
   return c;
 }
 
+bool use_local(const ApaDesc* d, const ApaWeights* w, const ApaTuning* t) {
+  if (!local_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) return false;
+  if (t && (t->fused == 0 || (t->cluster_size != 0 && t->cluster_size != 16) || t->max_ctas != 0)) return false;
+  if (t && t->reserved[1] == 1) return false;  // reserved[1] == 1: force the grid-barrier kernel (A/B tests)
+  if (w)
+    for (int r = 0; r < d->rank; ++r)
+      if (reinterpret_cast<uintptr_t>(w->topdown_w[r]) & 15u) return false;  // bulk copies need 16 B alignment
+  return true;
+}
+
 int check_desc(const ApaDesc* d) {
   if (d == nullptr) return APA_ERR_NULL;
   if (d->abi_version != APA_ABI_VERSION) return APA_ERR_UNSUPPORTED;
@@ -174,6 +184,14 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
     plan[2] = fp.cluster * fp.nclusters;
     plan[3] = fp.fused;
     plan[5] = int32_t(fp.smem);
+    if (use_local(desc, nullptr, tuning)) {
+      const int ncl = desc->batch / 4 < 9 ? desc->batch / 4 : 9;  // 148 SMs / 16
+      plan[1] = 16;
+      plan[2] = 16 * ncl;
+      plan[3] = 1;
+      plan[5] = int32_t(local_smem_bytes(desc->channels, desc->rank, desc->num_classes));
+      plan[6] = 1;  // cluster-local kernel
+    }
     launches += fp.fused ? 1 : 2;
     if (want_attn) launches += 1;
   } else {
@@ -185,12 +203,48 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
   return APA_OK;
 }
 
+}  // extern "C"
+
+namespace {
+int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logits, float* attn_out,
+             float* topdown_out, float* pose_out, void* workspace, size_t workspace_bytes,
+             const ApaTuning* tuning, void* stream_, const ApaPeerGather* gw);
+}
+
+extern "C" {
+
 int apa_attn_pool_fwd(const ApaDesc* d, const float* X, const ApaWeights* w, float* logits,
                       float* attn_out, float* topdown_out, float* pose_out, void* workspace,
                       size_t workspace_bytes, const ApaTuning* tuning, void* stream_) {
+  if (logits == nullptr) return APA_ERR_NULL;
+  return fwd_impl(d, X, w, logits, attn_out, topdown_out, pose_out, workspace, workspace_bytes, tuning, stream_,
+                  nullptr);
+}
+
+int apa_attn_pool_fwd_gather(const ApaDesc* d, const float* X, const ApaWeights* w, const ApaPeerGather* gw,
+                             void* workspace, size_t workspace_bytes, const ApaTuning* tuning, void* stream_) {
+  if (gw == nullptr) return APA_ERR_NULL;
+  if (gw->world < 1 || gw->world > APA_MAX_PEERS || gw->rank < 0 || gw->rank >= gw->world) return APA_ERR_SHAPE;
+  if (gw->done_counter == nullptr) return APA_ERR_NULL;
+  for (int q = 0; q < gw->world; ++q)
+    if (gw->peer_logits[q] == nullptr || gw->peer_flags[q] == nullptr) return APA_ERR_NULL;
   int st = check_desc(d);
   if (st != APA_OK) return st;
-  if (X == nullptr || w == nullptr || logits == nullptr || workspace == nullptr) return APA_ERR_NULL;
+  if (d->flags & APA_FLAG_PER_CLASS) return APA_ERR_UNSUPPORTED;  // the fused gather lives in the single-map kernels
+  if (!fused_supported(d->channels, d->rank)) return APA_ERR_UNSUPPORTED;
+  return fwd_impl(d, X, w, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, tuning, stream_, gw);
+}
+
+}  // extern "C"
+
+namespace {
+
+int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logits, float* attn_out,
+             float* topdown_out, float* pose_out, void* workspace, size_t workspace_bytes,
+             const ApaTuning* tuning, void* stream_, const ApaPeerGather* gw) {
+  int st = check_desc(d);
+  if (st != APA_OK) return st;
+  if (X == nullptr || w == nullptr || workspace == nullptr) return APA_ERR_NULL;
   const int B = d->batch, HW = d->hw, C = d->channels, K = d->num_classes, R = d->rank, F = d->frames;
   const bool single = (d->flags & APA_FLAG_SINGLE_LAYER_ATT) != 0;
   const bool per_class = (d->flags & APA_FLAG_PER_CLASS) != 0;
@@ -260,16 +314,34 @@ int apa_attn_pool_fwd(const ApaDesc* d, const float* X, const ApaWeights* w, flo
       p.td_b[r] = w->topdown_b[r];
     }
     p.logits = logits;
+    if (gw != nullptr) {
+      p.gw_world = gw->world;
+      p.gw_rank = gw->rank;
+      for (int q = 0; q < gw->world; ++q) {
+        p.gw_logits[q] = gw->peer_logits[q];
+        p.gw_flags[q] = gw->peer_flags[q];
+      }
+      p.gw_done = gw->done_counter;
+    }
     p.attn_raw = attn_out ? wsf(c.attn_raw) : nullptr;
     p.g = wsf(c.g);
     p.sn = wsf(c.sn);
     p.smx = wsf(c.smx);
     p.barrier = reinterpret_cast<unsigned long long*>(ws + c.ctrl) + ((plan.cluster * plan.nclusters) & 255);
-    p.early_trigger = (tuning && tuning->reserved[0]) ? 1 : 0;
+    // PDL trigger: by default as soon as a CTA starts consuming (measured best: the next launch's clusters take
+    // the free CTA slots as they appear); reserved[0] > 0 = that many tiles before the end, < 0 = at the end
+    p.trigger_lead = (tuning && tuning->reserved[0] != 0) ? (tuning->reserved[0] < 0 ? 0 : tuning->reserved[0]) : 1 << 20;
     p.ts = (tuning && tuning->debug_timestamps) ? reinterpret_cast<unsigned long long*>(ws + c.ts) : nullptr;
     p.B = B; p.HW = HW; p.C = C; p.K = K; p.R = R; p.F = F;
     p.inv_scale = 1.0f / (float(HW) * float(F));
-    APA_CUDA(fused_launch(p, plan, stream));
+    // small batches: the cluster-local kernel (no grid barrier, g never leaves shared memory)
+    bool launched = false;
+    if (use_local(d, w, tuning)) {
+      cudaError_t le = local_launch(p, mode, tuning, stream, nullptr);
+      if (le == cudaSuccess) launched = true;
+      else (void)cudaGetLastError();  // e.g. 16-CTA clusters not launchable here: general kernel below
+    }
+    if (!launched) APA_CUDA(fused_launch(p, plan, stream));
     if (attn_out)
       APA_CUDA(attn_finalize_m1(p.attn_raw, w->attn_w, w->attn_b, p.smx, attn_out, B, HW, R, mode, stream));
     return APA_OK;
@@ -292,6 +364,10 @@ int apa_attn_pool_fwd(const ApaDesc* d, const float* X, const ApaWeights* w, flo
   APA_CUDA(dense_pool(A, T, logits, B, HW, K, M, R, F, stream));
   return APA_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int apa_attn_pool_fwd_host(const ApaDesc* d, const float* X_host, const ApaWeights* w, float* logits_host,
                            float* x_staging, float* logits_staging, void* workspace,

@@ -164,6 +164,29 @@ __device__ __forceinline__ void griddep_launch_dependents() {
 }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------- fused all-gather (peer stores)
+// Called by ONE thread per CTA after that CTA's logits stores (and a CTA-level barrier).  The last CTA of the
+// launch to get here publishes step flags to every peer and waits for every peer's flag of the same step.
+__device__ __forceinline__ void peer_gather_finish(int world, int rank, unsigned long long* const* flags,
+                                                   unsigned long long* done, unsigned int nblocks) {
+  __threadfence_system();  // this CTA's peer stores are globally visible before it is counted
+  unsigned long long prev;
+  asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], 1;" : "=l"(prev) : "l"(done) : "memory");
+  if ((prev + 1) % nblocks != 0) return;
+  const unsigned long long step = (prev + 1) / nblocks;
+  for (int q = 0; q < world; ++q)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[q] + rank), "l"(step) : "memory");
+  const long long t0 = clock64();
+  for (int r = 0; r < world; ++r) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags[rank] + r) : "memory");
+      if (v >= step) break;
+      if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
+    } while (true);
+  }
+}
+
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -35,8 +35,13 @@ struct FusedParams {
   unsigned long long* ts;             // optional debug timeline, 64 words per CTA (see apa_pool_fused.cu)
   int B, HW, C, K, R, F;
   int do_phase1, do_phase2;           // fused: 1,1   split: (1,0) then (0,1)
-  int early_trigger;                  // 1: let the next launch start as soon as this one is resident
+  int trigger_lead;                   // PDL: trigger the next launch this many tiles before a CTA's last tile
   float inv_scale;                    // 1 / (HW * F)
+  // fused all-gather over peer memory (gw_world == 0: plain store to `logits`)
+  int gw_world, gw_rank;
+  float* gw_logits[APA_MAX_PEERS];
+  unsigned long long* gw_flags[APA_MAX_PEERS];
+  unsigned long long* gw_done;
 };
 
 struct FusedPlan {
@@ -59,6 +64,11 @@ void fused_make_plan_nodevice(int B, int HW, int C, int K, int R, int mode, cons
                               FusedPlan* plan);
 cudaError_t fused_launch(const FusedParams& p, const FusedPlan& plan, cudaStream_t stream);
 bool fused_supported(int C, int R);
+
+// ---- cluster-local small-batch form (apa_pool_local.cu): 16-CTA clusters, no grid barrier, g stays in smem
+bool local_eligible(int B, int HW, int C, int K, int R, int F);
+size_t local_smem_bytes(int C, int R, int K);
+cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out);
 
 // ---- dense path (apa_dense.cu)
 // Y[m, col_off + n*col_stride] (row stride ldy) = act(sum_k X[m*ldx + k*xs] W[k,n] + bias[n])

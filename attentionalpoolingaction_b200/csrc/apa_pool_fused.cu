@@ -238,7 +238,6 @@ apa_pool_fused_kernel(const FusedParams p) {
     cluster_wait();
   } else {
     cluster_arrive();
-    if (p.early_trigger) griddep_launch_dependents();
     cluster_wait();  // barrier inits of every CTA of the cluster are visible (remote arrives come later)
   }
   if (tid == 0) ts_mark(p.ts, 1);
@@ -289,6 +288,9 @@ apa_pool_fused_kernel(const FusedParams p) {
       for (int it = 0; it < ntiles; ++it, ++giter) {
         const int rows = min(TR, nrows - it * TR);
         const bool full = (rows == TR);  // CTA-uniform: fast path without per-row predicates
+        // programmatic dependent launch: let the next launch become resident a few tiles before this CTA
+        // stops streaming, so its prologue and first copies overlap the end of this stream
+        if (b + nclusters >= p.B && it == max(0, ntiles - 1 - p.trigger_lead)) griddep_launch_dependents();
         const float* st = reinterpret_cast<const float*>(smem + stage * L::kTileBytes) + col0;
         mbar_wait(&full_bar[stage], phase);
         if (tid == 0 && giter < 24) ts_mark(p.ts, 8 + int(giter));
@@ -405,7 +407,7 @@ apa_pool_fused_kernel(const FusedParams p) {
       // Programmatic dependent launch: once this CTA has streamed its last tile the NEXT launch may start
       // streaming (it co-resides, 2 CTAs/SM) while this one finishes its latency-bound tail; before the
       // first write to the (shared) workspace, make sure the PREVIOUS launch has completely finished.
-      if (b + nclusters >= p.B && !p.early_trigger) griddep_launch_dependents();
+      if (b + nclusters >= p.B && ntiles == 0) griddep_launch_dependents();
       if (img_iter == 0) griddep_wait();
 
       // ------------------------------------------------ combine the p row-slices of image b (DSMEM push)
@@ -609,13 +611,20 @@ apa_pool_fused_kernel(const FusedParams p) {
               for (int fr = 0; fr < p.F; ++fr) S += __ldcg(p.sn + size_t(v * p.F + fr) * R + j);
               sum = fmaf(__ldg(p.td_b[j] + k), S, sum);
             }
-            p.logits[size_t(v) * p.K + k] = sum * p.inv_scale;
+            const float val = sum * p.inv_scale;
+            if (p.gw_world > 0) {
+              const size_t off = (size_t(p.gw_rank) * Bv + size_t(v)) * p.K + k;
+              for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
+            } else {
+              p.logits[size_t(v) * p.K + k] = val;
+            }
           }
         }
         cluster_sync_all();  // outP / accS are reused by the next pass; also guards exit
       }
     }
   }
+  if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x);
   if (tid == 0) {
     ts_mark(p.ts, 5);
     if (p.ts) p.ts[size_t(blockIdx.x) * 64 + 63] = globaltimer_ns();

@@ -1,0 +1,591 @@
+// apa_pool_local.cu — the small-batch form of the fused head: everything after the HBM stream stays inside
+// one 16-CTA thread-block cluster, so there is NO grid barrier and the attention-weighted features g never
+// leave shared memory.  Same math as apa_pool_fused.cu (single attention map, rank 1..4, plain / relu /
+// spatial softmax); reference sites nets_factory.py:259-328, :350-352.
+//
+//   cluster = 16 CTAs = 4 images x 4 row-quarters.   CTA rank r: image i = r / 4, quarter q = r % 4.
+//   phase 1   as in the grid-barrier kernel: producer lane streams 4-row x C tiles (32 KB, cp.async.bulk)
+//             through a 3-stage mbarrier ring; 8 consumer warps form a[row] and accumulate g in registers.
+//   combine   the 4 CTAs of an image push their partial g into the CTA owning those C/4 channels (DSMEM),
+//             which sums them (softmax max/sum merge) into `gown` in ITS shared memory.
+//   phase 2   the contraction g.B is split over the 16 CTAs by CHANNEL: CTA j owns channels
+//             [j C/16, (j+1) C/16) for all 4 images and all K classes.  Its weight rows are one contiguous,
+//             16-byte aligned span of B_r, so the same producer lane streams them with cp.async.bulk through
+//             the same ring right behind the last X tile (they are in flight while the combine runs).
+//             Each thread owns classes {t, t+256, t+512}; 4 images x 3 classes of fp32 accumulators.
+//   reduce    every CTA publishes its [4, K] partial logits in shared memory; CTA j sums 1/16 of the outputs
+//             over the 16 CTAs through DSMEM in fixed order (bit-reproducible), adds the bias term and
+//             writes logits.
+// Cluster-scope mbarriers (remote arrive.release / local try_wait.acquire) order every exchange; nothing
+// remote touches a CTA after its last wait, so CTAs exit without a trailing cluster barrier.
+#include "apa_common.cuh"
+#include "apa_kernels.h"
+
+#include <atomic>
+#include <mutex>
+
+namespace apa {
+
+namespace {
+
+constexpr int kLC = 16;   // cluster size
+constexpr int kLP = 4;    // CTAs per image
+constexpr int kLI = 4;    // images per cluster
+constexpr int kLTR = 4;   // rows per X tile
+
+template <int Q, int RMAX>
+struct LSmem {
+  static constexpr int C = Q * 1024;
+  static constexpr int Cp = C / kLP;      // channels combined by one CTA of an image
+  static constexpr int CH = C / kLC;      // channels contracted by one CTA in phase 2
+  static constexpr int kStages = 3;
+  static constexpr size_t kTileBytes = size_t(kLTR) * C * 4;
+  static constexpr size_t kRing = kStages * kTileBytes;
+  // after the ring: exchange region (combine slots [4][R][Cp], later partial logits [4][K]) -- sized on the host
+  static constexpr size_t kOffXchg = kRing;
+};
+
+struct LLayout {  // byte offsets after the exchange region (computed on host and device identically)
+  size_t xchg_bytes, off_gown, off_gs, off_stat, off_part, off_scl, off_bars, total;
+};
+__host__ __device__ inline LLayout local_layout(int C, int R, int K) {
+  LLayout l;
+  const size_t slots = size_t(kLP) * R * (C / kLP) * 4;
+  const size_t outp = size_t(kLI) * K * 4;
+  l.xchg_bytes = ((slots > outp ? slots : outp) + 127) / 128 * 128;
+  size_t off = size_t(3) * kLTR * C * 4 + l.xchg_bytes;
+  l.off_gown = off; off += size_t(R) * (C / kLP) * 4 + 64;   // combined g slice + S_r
+  l.off_gs = off;   off += size_t(R) * (C / kLC) * kLI * 4;   // gS[r][ch][img]
+  l.off_stat = off; off += kLP * 8 * 4;
+  l.off_part = off; off += 2 * kLTR * 8 * 4;
+  l.off_scl = off;  off += 64;
+  l.off_bars = off; off += 8 * 16;
+  l.total = off;
+  return l;
+}
+
+__device__ __forceinline__ void lts_mark(unsigned long long* ts, int slot) {
+  if (ts != nullptr) ts[size_t(blockIdx.x) * 64 + slot] = clock64();
+}
+__device__ __forceinline__ unsigned long long lglobaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ float ldot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ void laxpy4(float* f, float a, const float4& x) {
+  f[0] = fmaf(a, x.x, f[0]);
+  f[1] = fmaf(a, x.y, f[1]);
+  f[2] = fmaf(a, x.z, f[2]);
+  f[3] = fmaf(a, x.w, f[3]);
+}
+
+template <int Q, int RMAX, int MODE, int NC>
+__global__ void __launch_bounds__(kFusedThreads, (RMAX == 1) ? 2 : 1)
+apa_pool_local_kernel(const FusedParams p) {
+  using L = LSmem<Q, RMAX>;
+  constexpr int C = L::C, Cp = L::Cp, CH = L::CH, TR = kLTR;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int R = p.R, K = p.K;
+  const LLayout lay = local_layout(C, R, K);
+  float* xchg = reinterpret_cast<float*>(smem + L::kOffXchg);
+  float* gown = reinterpret_cast<float*>(smem + lay.off_gown);   // [R][Cp] then S[R]
+  float* gS = reinterpret_cast<float*>(smem + lay.off_gs);       // [R][CH][4 images]
+  float* statS = reinterpret_cast<float*>(smem + lay.off_stat);  // [4 peers][8]
+  float* partS = reinterpret_cast<float*>(smem + lay.off_part);
+  float* scl = reinterpret_cast<float*>(smem + lay.off_scl);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+  uint64_t* full_bar = bars;          // [3]
+  uint64_t* empty_bar = bars + 4;     // [3]
+  uint64_t* parts_ready = bars + 8;   // 4 arrivals: the CTAs of my image pushed their partials
+  uint64_t* gown_ready = bars + 9;    // 16 arrivals: every CTA's combined slice is readable
+  uint64_t* out_ready = bars + 10;    // 16 arrivals: every CTA's partial logits are readable
+  uint64_t* all_done = bars + 11;     // 16 arrivals: every CTA finished reading my shared memory
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int img_in_cluster = int(crank) >> 2, q = int(crank) & 3;
+  const int cluster_id = blockIdx.x / kLC, nclusters = gridDim.x / kLC;
+  const int ngroups = p.B / kLI;
+  const int row_lo = (p.HW * q) / kLP, row_hi = (p.HW * (q + 1)) / kLP;
+  const int nrows = row_hi - row_lo, ntiles = (nrows + TR - 1) / TR;
+  const int WR = (K <= 512) ? 16 : 8;            // weight rows per ring stage (<= 32 KB)
+  const int wchunks = CH / WR;                   // per rank
+
+  // =========================================================================== producer warp
+  if (warp == kConsumerWarps) {
+    if (lane == 0) {
+      for (int i = 0; i < L::kStages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], kConsumerWarps);
+      }
+      mbar_init(parts_ready, kLP);
+      mbar_init(gown_ready, kLC);
+      mbar_init(out_ready, kLC);
+      mbar_init(all_done, kLC);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    cluster_arrive();
+    if (lane == 0) {
+      const uint64_t pol_x = l2_policy_evict_first(), pol_w = l2_policy_evict_last();
+      uint32_t stage = 0, phase = 0;
+      for (int g = cluster_id; g < ngroups; g += nclusters) {
+        const int b = g * kLI + img_in_cluster;
+        const float* xb = p.X + (size_t(b) * p.HW + row_lo) * C;
+        for (int t = 0; t < ntiles; ++t) {
+          const int rows = min(TR, nrows - t * TR);
+          const uint32_t bytes = uint32_t(rows) * C * 4u;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          bulk_g2s(smem + stage * L::kTileBytes, xb + size_t(t) * TR * C, bytes, &full_bar[stage], pol_x);
+          if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+        }
+        // this CTA's weight rows for phase 2 ride the same ring (they do not depend on phase 1)
+        for (int j = 0; j < R; ++j) {
+          const float* wsrc = p.td_w[j] + size_t(int(crank) * CH) * K;
+          for (int ch = 0; ch < wchunks; ++ch) {
+            const uint32_t bytes = uint32_t(WR) * K * 4u;
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            bulk_g2s(smem + stage * L::kTileBytes, wsrc + size_t(ch) * WR * K, bytes, &full_bar[stage], pol_w);
+            if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    griddep_launch_dependents();
+    cluster_wait();
+    return;  // the producer warp takes no part in the exchanges (they are mbarrier-based)
+  }
+  if (tid == 0) {
+    lts_mark(p.ts, 0);
+    if (p.ts) p.ts[size_t(blockIdx.x) * 64 + 62] = lglobaltimer_ns();
+  }
+  cluster_arrive();
+  cluster_wait();  // every CTA's barriers are initialised
+  if (tid == 0) lts_mark(p.ts, 1);
+
+  // =========================================================================== consumers
+  const int col0 = warp * (C / kConsumerWarps) + lane * 4;  // + q*128
+  float4 wv[Q];
+  float c0 = 0.f;
+  const float c_in = (p.attn_in != nullptr && p.attn_in_bias) ? __ldg(p.attn_b[0]) : 0.f;
+  if (p.attn_in == nullptr) {
+#pragma unroll
+    for (int qq = 0; qq < Q; ++qq) wv[qq] = __ldg(reinterpret_cast<const float4*>(p.attn_w[0] + col0 + qq * 128));
+    c0 = __ldg(p.attn_b[0]);
+  }
+  float cw[RMAX], cb[RMAX];
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) {
+    cw[j] = (j >= 1 && j < R) ? __ldg(p.attn_w[j]) : 0.f;
+    cb[j] = (j >= 1 && j < R) ? __ldg(p.attn_b[j]) : 0.f;
+  }
+  uint32_t stage = 0, phase = 0, giter = 0, grp_iter = 0;
+  for (int g = cluster_id; g < ngroups; g += nclusters, ++grp_iter) {
+    const int b = g * kLI + img_in_cluster;
+    const bool last_group = (g + nclusters >= ngroups);
+    float f[RMAX][Q * 4];
+    float s[RMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      s[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < Q * 4; ++i) f[j][i] = 0.f;
+    }
+    // ------------------------------------------------------------------ phase 1: stream this CTA's rows
+    for (int it = 0; it < ntiles; ++it, ++giter) {
+      const int rows = min(TR, nrows - it * TR);
+      const bool full = (rows == TR);
+      if (last_group && it == max(0, ntiles - 1 - p.trigger_lead)) griddep_launch_dependents();
+      const float* st = reinterpret_cast<const float*>(smem + stage * L::kTileBytes) + col0;
+      mbar_wait(&full_bar[stage], phase);
+      if (tid == 0 && giter < 24) lts_mark(p.ts, 8 + int(giter));
+      float4 x[TR][Q];
+      if (full) {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+          for (int qq = 0; qq < Q; ++qq) x[r][qq] = *reinterpret_cast<const float4*>(st + r * C + qq * 128);
+      } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+          for (int qq = 0; qq < Q; ++qq)
+            x[r][qq] = (r < rows) ? *reinterpret_cast<const float4*>(st + r * C + qq * 128)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float a[TR];
+      if (p.attn_in == nullptr) {
+        float pd[TR];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          pd[r] = ldot4(x[r][0], wv[0]);
+#pragma unroll
+          for (int qq = 1; qq < Q; ++qq) pd[r] += ldot4(x[r][qq], wv[qq]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+        float k0 = hi16 ? pd[2] : pd[0], s0 = hi16 ? pd[0] : pd[2];
+        float k1 = hi16 ? pd[3] : pd[1], s1 = hi16 ? pd[1] : pd[3];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        float kk = hi8 ? k1 : k0;
+        const float ss = hi8 ? k0 : k1;
+        kk += __shfl_xor_sync(0xffffffffu, ss, 8);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+        float* part = partS + (giter & 1u) * (TR * 8);
+        if ((lane & 7) == 0) part[(lane >> 3) * 8 + warp] = kk;
+        named_bar_sync(1, kConsumerThreads);
+        float v = part[lane];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+#pragma unroll
+        for (int r = 0; r < TR; ++r) a[r] = c0 + __shfl_sync(0xffffffffu, v, 8 * r);
+      } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          float v = 0.f;
+          if (r < rows) {
+            const size_t gi = size_t(b) * p.HW + row_lo + it * TR + r;
+            v = c_in;
+            for (int pp = 0; pp < p.attn_in_parts; ++pp) v += __ldg(p.attn_in + size_t(pp) * p.B * p.HW + gi);
+          }
+          a[r] = v;
+        }
+      }
+      if (p.attn_raw != nullptr && tid == 0) {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+          if (r < rows) p.attn_raw[size_t(b) * p.HW + row_lo + it * TR + r] = a[r];
+      }
+      float valid[TR];
+#pragma unroll
+      for (int r = 0; r < TR; ++r) valid[r] = (full || r < rows) ? 1.f : 0.f;
+      if (MODE == MODE_SOFTMAX) {
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < TR; ++r) tmax = fmaxf(tmax, valid[r] != 0.f ? a[r] : -INFINITY);
+        const float mnew = fmaxf(mx, tmax);
+        const float sc = (mnew == -INFINITY) ? 1.f : expf(mx - mnew);
+        mx = mnew;
+        s[0] *= sc;
+#pragma unroll
+        for (int i = 0; i < Q * 4; ++i) f[0][i] *= sc;
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          const float e = valid[r] != 0.f ? expf(a[r] - mx) : 0.f;
+          s[0] += e;
+#pragma unroll
+          for (int qq = 0; qq < Q; ++qq) laxpy4(&f[0][qq * 4], e, x[r][qq]);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          float ar = a[r];
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) {
+            if (j < R) {
+              if (j >= 1) ar = fmaf(cw[j], ar, cb[j]);
+              const float A = ((MODE == MODE_RELU) ? fmaxf(ar, 0.f) : ar) * valid[r];
+              s[j] += A;
+#pragma unroll
+              for (int qq = 0; qq < Q; ++qq) laxpy4(&f[j][qq * 4], A, x[r][qq]);
+            }
+          }
+        }
+      }
+      if (p.attn_in != nullptr) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      }
+      if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+    }
+
+    if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 2);
+    // ------------------------------------------------------------------ combine the 4 quarters of my image
+    // (the exchange region and gown of every CTA are free: all_done of the previous group was waited below)
+    {
+      const uint32_t base_rank = crank & ~3u;
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq) {
+        const int c = col0 + qq * 128;
+        const uint32_t owner_q = uint32_t(c / Cp);
+        const int cl = c - int(owner_q) * Cp;
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j)
+          if (j < R)
+            st_dsmem_f4(dsmem_addr(xchg + (size_t(q) * R + j) * Cp + cl, base_rank + owner_q),
+                        make_float4(f[j][qq * 4 + 0], f[j][qq * 4 + 1], f[j][qq * 4 + 2], f[j][qq * 4 + 3]));
+      }
+      if (tid < kLP) {
+        const uint32_t ra = dsmem_addr(statS + size_t(q) * 8, base_rank + uint32_t(tid));
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) st_dsmem_f(ra + 4u * j, s[j]);
+        st_dsmem_f(ra + 16u, mx);
+      }
+      fence_acq_rel_cluster();
+      named_bar_sync(1, kConsumerThreads);
+      if (tid < kLP) mbar_arrive_cluster(parts_ready, base_rank + uint32_t(tid));
+      mbar_wait_cluster(parts_ready, grp_iter & 1u);
+    }
+    if (MODE == MODE_SOFTMAX) {
+      if (tid < kLP) {
+        float M = -INFINITY;
+        for (int pp = 0; pp < kLP; ++pp) M = fmaxf(M, statS[pp * 8 + 4]);
+        float S = 0.f;
+        for (int pp = 0; pp < kLP; ++pp) S += expf(statS[pp * 8 + 4] - M) * statS[pp * 8 + 0];
+        scl[tid] = expf(statS[tid * 8 + 4] - M) / S;
+        if (tid == 0 && q == 0 && p.smx != nullptr) {
+          p.smx[2 * b + 0] = M;
+          p.smx[2 * b + 1] = S;
+        }
+      }
+      named_bar_sync(1, kConsumerThreads);
+    }
+    {
+      const int n4 = Cp / 4;
+      for (int idx = tid; idx < R * n4; idx += kConsumerThreads) {
+        const int j = idx / n4, cl = (idx - j * n4) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int pp = 0; pp < kLP; ++pp) {
+          const float4 v = *reinterpret_cast<const float4*>(xchg + (size_t(pp) * R + j) * Cp + cl);
+          const float sc = (MODE == MODE_SOFTMAX) ? scl[pp] : 1.f;
+          acc.x = fmaf(sc, v.x, acc.x);
+          acc.y = fmaf(sc, v.y, acc.y);
+          acc.z = fmaf(sc, v.z, acc.z);
+          acc.w = fmaf(sc, v.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(gown + j * Cp + cl) = acc;
+      }
+      if (tid < R) {
+        float S = 1.f;
+        if (MODE != MODE_SOFTMAX) {
+          S = 0.f;
+          for (int pp = 0; pp < kLP; ++pp) S += statS[pp * 8 + tid];
+        }
+        gown[R * Cp + tid] = S;
+      }
+    }
+    fence_acq_rel_cluster();
+    named_bar_sync(1, kConsumerThreads);
+    if (tid < kLC) mbar_arrive_cluster(gown_ready, uint32_t(tid));
+    mbar_wait_cluster(gown_ready, grp_iter & 1u);  // every CTA's combined slice (and its S_r) is readable
+    if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 3);
+
+    // ------------------------------------------------------------------ gather my channel block of g, all 4 images
+    // channels [crank*CH, +CH) of image i live in CTA rank 4i + (crank*CH)/Cp at offset (crank*CH) % Cp
+    {
+      const int n4 = CH / 4;
+      const uint32_t src_q = uint32_t((int(crank) * CH) / Cp);
+      const int src_off = (int(crank) * CH) % Cp;
+      for (int idx = tid; idx < kLI * R * n4; idx += kConsumerThreads) {
+        const int i = idx / (R * n4), rem = idx - i * (R * n4);
+        const int j = rem / n4, c4 = rem - j * n4;
+        const float4 v = ld_dsmem_f4(dsmem_addr(gown + j * Cp + src_off + c4 * 4, uint32_t(4 * i) + src_q));
+        float* dst = gS + (size_t(j) * CH + c4 * 4) * kLI + i;
+        dst[0 * kLI] = v.x; dst[1 * kLI] = v.y; dst[2 * kLI] = v.z; dst[3 * kLI] = v.w;
+      }
+      named_bar_sync(1, kConsumerThreads);
+    }
+
+    if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 6);
+    // ------------------------------------------------------------------ phase 2: my channels x all classes
+    float acc[kLI][NC];
+#pragma unroll
+    for (int i = 0; i < kLI; ++i)
+#pragma unroll
+      for (int n = 0; n < NC; ++n) acc[i][n] = 0.f;
+    for (int j = 0; j < R; ++j) {
+      for (int ch = 0; ch < wchunks; ++ch) {
+        const float* ws = reinterpret_cast<const float*>(smem + stage * L::kTileBytes);
+        mbar_wait(&full_bar[stage], phase);
+        const float* gj = gS + (size_t(j) * CH + ch * WR) * kLI;
+        for (int c = 0; c < WR; ++c) {
+          const float4 gv = *reinterpret_cast<const float4*>(gj + c * kLI);  // 4 images, broadcast
+#pragma unroll
+          for (int n = 0; n < NC; ++n) {
+            const int k = tid + n * kConsumerThreads;
+            const float w = (k < K) ? ws[c * K + k] : 0.f;
+            acc[0][n] = fmaf(gv.x, w, acc[0][n]);
+            acc[1][n] = fmaf(gv.y, w, acc[1][n]);
+            acc[2][n] = fmaf(gv.z, w, acc[2][n]);
+            acc[3][n] = fmaf(gv.w, w, acc[3][n]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    if (last_group && ntiles == 0) griddep_launch_dependents();
+    if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 7);
+
+    // ------------------------------------------------------------------ publish partial logits, reduce 1/16 of them
+    // (the exchange region is free: every CTA of my image finished reading its slots before arriving on
+    //  gown_ready, and I waited for all 16 arrivals above)
+#pragma unroll
+    for (int i = 0; i < kLI; ++i)
+#pragma unroll
+      for (int n = 0; n < NC; ++n) {
+        const int k = tid + n * kConsumerThreads;
+        if (k < K) xchg[i * K + k] = acc[i][n];
+      }
+    fence_acq_rel_cluster();
+    named_bar_sync(1, kConsumerThreads);
+    if (tid < kLC) mbar_arrive_cluster(out_ready, uint32_t(tid));
+    mbar_wait_cluster(out_ready, grp_iter & 1u);
+    if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 4);
+    if (grp_iter == 0) griddep_wait();  // first global write of this launch: previous launch fully done
+    {
+      const int nout = kLI * K;
+      const int per = (nout + kLC - 1) / kLC;
+      const int o_lo = int(crank) * per, o_hi = min(nout, o_lo + per);
+      for (int o = o_lo + tid; o < o_hi; o += kConsumerThreads) {
+        const int i = o / K, k = o - i * K;
+        float part[kLC];
+#pragma unroll
+        for (int c = 0; c < kLC; ++c) part[c] = ld_dsmem_f_nv(dsmem_addr(xchg + o, uint32_t(c)));
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < kLC; ++c) sum += part[c];
+        for (int j = 0; j < R; ++j)
+          sum = fmaf(__ldg(p.td_b[j] + k), ld_dsmem_f_nv(dsmem_addr(gown + R * Cp + j, uint32_t(4 * i))), sum);
+        const float val = sum * p.inv_scale;
+        if (p.gw_world > 0) {
+          const size_t off = (size_t(p.gw_rank) * p.B + size_t(g * kLI + i)) * K + k;
+          for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
+        } else {
+          p.logits[size_t(g * kLI + i) * K + k] = val;
+        }
+      }
+    }
+    // every CTA tells every other that it no longer reads its shared memory; wait for the same from all
+    // (frees xchg / gown / statS for the next group, and makes it safe to exit)
+    named_bar_sync(1, kConsumerThreads);
+    if (tid < kLC) mbar_arrive_cluster(all_done, uint32_t(tid));
+    mbar_wait_cluster(all_done, grp_iter & 1u);
+  }
+  if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x);
+  if (tid == 0) {
+    lts_mark(p.ts, 5);
+    if (p.ts) p.ts[size_t(blockIdx.x) * 64 + 63] = lglobaltimer_ns();
+  }
+}
+
+using LKernelFn = void (*)(const FusedParams);
+
+template <int Q, int RMAX, int MODE>
+LKernelFn lsel_nc(int nc) {
+  if (nc == 1) return &apa_pool_local_kernel<Q, RMAX, MODE, 1>;
+  if (nc == 2) return &apa_pool_local_kernel<Q, RMAX, MODE, 2>;
+  return &apa_pool_local_kernel<Q, RMAX, MODE, 3>;
+}
+LKernelFn local_select(int Q, int rmax, int mode, int nc) {
+  if (Q != 2) return nullptr;
+  if (rmax == 1) {
+    if (mode == MODE_PLAIN) return lsel_nc<2, 1, MODE_PLAIN>(nc);
+    if (mode == MODE_RELU) return lsel_nc<2, 1, MODE_RELU>(nc);
+    return lsel_nc<2, 1, MODE_SOFTMAX>(nc);
+  }
+  if (mode == MODE_PLAIN) return lsel_nc<2, APA_MAX_RANK, MODE_PLAIN>(nc);
+  if (mode == MODE_RELU) return lsel_nc<2, APA_MAX_RANK, MODE_RELU>(nc);
+  return nullptr;
+}
+
+std::mutex g_lmu;
+struct LEntry { int dev; LKernelFn fn; size_t smem; int nmax; };
+LEntry g_lcache[32];
+int g_ln = 0;
+std::atomic<int> g_local_pdl_refused{0};
+
+}  // namespace
+
+bool local_eligible(int B, int HW, int C, int K, int R, int F) {
+  (void)HW;
+  return C == 2048 && F == 1 && B % kLI == 0 && B >= kLI && K >= 1 && K <= 3 * kConsumerThreads && R >= 1 &&
+         R <= APA_MAX_RANK && (size_t(K) * 8 * 4) <= size_t(32) * 1024;
+}
+
+cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out) {
+  const int Q = p.C / 1024, rmax = (p.R == 1) ? 1 : APA_MAX_RANK;
+  const int nc = (p.K + kConsumerThreads - 1) / kConsumerThreads;
+  LKernelFn fn = local_select(Q, rmax, mode, nc);
+  if (fn == nullptr) return cudaErrorInvalidValue;
+  const size_t smem = local_layout(p.C, p.R, p.K).total;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  int nmax = -1;
+  {
+    std::lock_guard<std::mutex> lk(g_lmu);
+    for (int i = 0; i < g_ln; ++i)
+      if (g_lcache[i].dev == dev && g_lcache[i].fn == fn && g_lcache[i].smem == smem) nmax = g_lcache[i].nmax;
+  }
+  if (nmax < 0) {
+    err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (err != cudaSuccess) return err;
+    (void)cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kLC, 1, 1);
+    cfg.blockDim = dim3(kFusedThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kLC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > 0 && n > sms / kLC) n = sms / kLC;  // one CTA slot per SM: the next launch co-resides
+    nmax = n;
+    std::lock_guard<std::mutex> lk(g_lmu);
+    if (g_ln < 32) g_lcache[g_ln++] = {dev, fn, smem, nmax};
+  }
+  if (nmax <= 0) return cudaErrorInvalidConfiguration;
+  int ncl = p.B / kLI;
+  if (ncl > nmax) ncl = nmax;
+  if (grid_out) *grid_out = ncl * kLC;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ncl * kLC, 1, 1);
+  cfg.blockDim = dim3(kFusedThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kLC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  int na = 1;
+  const bool pdl = !(tuning && tuning->no_pdl) && !g_local_pdl_refused.load(std::memory_order_relaxed);
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  err = cudaLaunchKernelEx(&cfg, fn, p);
+  if (err != cudaSuccess && pdl) {
+    (void)cudaGetLastError();
+    g_local_pdl_refused.store(1, std::memory_order_relaxed);
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, fn, p);
+  }
+  return err;
+}
+
+size_t local_smem_bytes(int C, int R, int K) { return local_layout(C, R, K).total; }
+
+}  // namespace apa

@@ -46,6 +46,7 @@ ABI_SYMBOLS = (
     "apa_attn_pool_workspace_init",
     "apa_attn_pool_fwd",
     "apa_attn_pool_fwd_host",
+    "apa_attn_pool_fwd_gather",
     "apa_gram_fwd",
     "apa_attn_pool_plan",
 )
@@ -95,6 +96,19 @@ class ApaTuning(ctypes.Structure):
     ]
 
 
+APA_MAX_PEERS = 8
+
+
+class ApaPeerGather(ctypes.Structure):
+    _fields_ = [
+        ("world", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("peer_logits", ctypes.c_void_p * APA_MAX_PEERS),
+        ("peer_flags", ctypes.c_void_p * APA_MAX_PEERS),
+        ("done_counter", ctypes.c_void_p),
+    ]
+
+
 class ApaError(RuntimeError):
     def __init__(self, status, where=""):
         self.status = int(status)
@@ -127,6 +141,10 @@ def _load():
     lib.apa_attn_pool_fwd_host.argtypes = [c.POINTER(ApaDesc), c.c_void_p, c.POINTER(ApaWeights), c.c_void_p,
                                            c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t,
                                            c.POINTER(ApaTuning), c.c_void_p]
+    lib.apa_attn_pool_fwd_gather.restype = c.c_int
+    lib.apa_attn_pool_fwd_gather.argtypes = [c.POINTER(ApaDesc), c.c_void_p, c.POINTER(ApaWeights),
+                                             c.POINTER(ApaPeerGather), c.c_void_p, c.c_size_t,
+                                             c.POINTER(ApaTuning), c.c_void_p]
     lib.apa_gram_fwd.restype = c.c_int
     lib.apa_gram_fwd.argtypes = [c.c_int32, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.apa_attn_pool_plan.restype = c.c_int
@@ -207,8 +225,8 @@ def attn_pool_plan(desc, tuning=None, want_attn=False, want_topdown=False, want_
                                  int(want_attn), int(want_topdown), int(want_pose), ctypes.byref(out))
     if st != APA_OK:
         raise ApaError(st, "apa_attn_pool_plan")
-    keys = ("path", "cluster_size", "grid", "fused", "launches", "smem_bytes")
-    return OrderedDict(zip(keys, list(out)[:6]))
+    keys = ("path", "cluster_size", "grid", "fused", "launches", "smem_bytes", "cluster_local")
+    return OrderedDict(zip(keys, list(out)[:7]))
 
 
 def strerror(status):
@@ -338,6 +356,22 @@ class AttnPoolOp(object):
             end_points["TopDownAttention"] = topdown
         end_points["Logits"] = logits
         return logits, end_points
+
+    def forward_gather(self, X, gather):
+        """Batch-sharded multi-GPU call: this rank's logits are stored straight into every peer's gathered
+        buffer by the kernel (`gather` is an ApaPeerGather, see attentionalpoolingaction_b200.dist.PeerGather)."""
+        torch = self._torch
+        if X.dim() == 4:
+            X = X.reshape(X.shape[0], X.shape[1] * X.shape[2], X.shape[3])
+        X = X.contiguous()
+        d, ws, _ = self._workspace(X.shape[0], (False, False, False))
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        st = _lib.apa_attn_pool_fwd_gather(ctypes.byref(d), _ptr(X), ctypes.byref(self.weights),
+                                           ctypes.byref(gather), _ptr(ws), ws.numel(),
+                                           ctypes.byref(self.tuning) if self.tuning is not None else None,
+                                           ctypes.c_void_p(stream))
+        if st != APA_OK:
+            raise ApaError(st, "apa_attn_pool_fwd_gather")
 
     def forward_host(self, X_host, logits_host=None):
         """Plugin-style call with HOST buffers (pinned for speed): H2D copy, head, D2H copy, sync."""

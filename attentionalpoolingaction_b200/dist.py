@@ -71,3 +71,51 @@ class ShardedHead(object):
         if self.num_videos % world == 0:
             return all_gather_logits(local, group=self.group)
         return all_gather_logits_uneven(local, self.num_videos, group=self.group)
+
+
+class PeerGather(object):
+    """The all-gather of the logits fused into the kernel: a symmetric [world * b, K] buffer on every rank;
+    each rank's kernel stores its block into every peer's buffer over NVLink and signals a step flag
+    (include/apa.h: ApaPeerGather).  Built on torch.distributed symmetric memory for the peer mappings only.
+    `world == 1` (no process group) degenerates to a local buffer, which is how single-GPU tests cover it."""
+
+    def __init__(self, videos_per_rank, num_classes, device, group=None):
+        import torch
+        from .custom_ops import attn_pool_factory as ops
+        self.rank, self.world = 0, 1
+        self._keep = []
+        use_dist = False
+        try:
+            import torch.distributed as dist
+            use_dist = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        except Exception:
+            use_dist = False
+        g = ops.ApaPeerGather()
+        if use_dist:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self.rank, self.world = dist.get_rank(grp), dist.get_world_size(grp)
+            if self.world > ops.APA_MAX_PEERS:
+                raise ValueError("at most %d ranks" % ops.APA_MAX_PEERS)
+            self.out = symm_mem.empty((self.world * videos_per_rank, num_classes), dtype=torch.float32, device=device)
+            self.flags = symm_mem.empty((64,), dtype=torch.int64, device=device)
+            self.out.zero_()
+            self.flags.zero_()
+            torch.cuda.synchronize(device)
+            h_out = symm_mem.rendezvous(self.out, grp)
+            h_flags = symm_mem.rendezvous(self.flags, grp)
+            self._keep += [h_out, h_flags]
+            for q in range(self.world):
+                g.peer_logits[q] = int(h_out.buffer_ptrs[q])
+                g.peer_flags[q] = int(h_flags.buffer_ptrs[q])
+            dist.barrier(grp)
+        else:
+            self.out = torch.zeros((videos_per_rank, num_classes), dtype=torch.float32, device=device)
+            self.flags = torch.zeros((64,), dtype=torch.int64, device=device)
+            g.peer_logits[0] = self.out.data_ptr()
+            g.peer_flags[0] = self.flags.data_ptr()
+        self.done = torch.zeros((8,), dtype=torch.int64, device=device)
+        g.world, g.rank = self.world, self.rank
+        g.done_counter = self.done.data_ptr()
+        self.struct = g

@@ -200,8 +200,11 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--streams", type=int, default=1, help="independent batches in flight (1 or 2)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch")
-    ap.add_argument("--early-trigger", type=int, default=0)
+    ap.add_argument("--trigger-lead", type=int, default=0, help="PDL trigger lead in tiles (0 = library default, -1 = none)")
     ap.add_argument("--no-coop", action="store_true", help="never use the cooperative launch attribute")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: all-gather fused into the kernel as NVLink peer stores, or a NCCL all_gather per step")
+    ap.add_argument("--general", action="store_true", help="force the grid-barrier kernel (not the cluster-local one)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=30)
     args = ap.parse_args()
@@ -232,7 +235,8 @@ def main():
     params = orc.make_params(K, C, flags=fl, seed=42)
     bits, rnk = ops.flags_from_cfg_net(fl)
     tuning = ops.make_tuning(args.cluster, args.fused, no_pdl=int(args.no_pdl), no_cooperative=int(args.no_coop))
-    tuning.reserved[0] = args.early_trigger
+    tuning.reserved[0] = args.trigger_lead
+    tuning.reserved[1] = int(args.general)
     nstreams = max(1, min(2, args.streams))
     # one op (= one workspace) per in-flight batch: consecutive steps are independent batches, so two
     # of them overlap on the GPU (one streams X from HBM while the other is in its latency-bound tail)
@@ -248,9 +252,22 @@ def main():
     logits_l = [torch.empty((B_PER_GPU, K), device=dev) for _ in range(nstreams)]
     logits = logits_l[0]
     gathered_l = [torch.empty((world * B_PER_GPU, K), device=dev) if world > 1 else None for _ in range(nstreams)]
+    collective = "none"
+    peer_l = None
+    if world > 1:
+        collective = args.collective
+        if collective == "peer":
+            try:
+                peer_l = [apa_dist.PeerGather(B_PER_GPU, K, dev) for _ in range(nstreams)]
+            except Exception as e:  # symmetric memory not available on this box: NCCL all_gather
+                sys.stderr.write("peer gather unavailable (%s); using NCCL all_gather\n" % e)
+                collective = "nccl"
 
     def step(i, with_collective=True):
         j = i % nstreams
+        if world > 1 and with_collective and collective == "peer":
+            opl[j].forward_gather(ring[i % nbuf], peer_l[j].struct)   # kernel stores into every peer's buffer
+            return
         opl[j](ring[i % nbuf], logits=logits_l[j])
         if world > 1 and with_collective:
             apa_dist.all_gather_logits(logits_l[j], gathered_l[j])
@@ -381,7 +398,9 @@ def main():
             "config": {
                 "workload": "configs[1]: rank-1 attn pool, synthetic 14x14x2048 feats, K=393, batch=32 per GPU",
                 "per_gpu_batch": B_PER_GPU, "global_batch": world * B_PER_GPU,
-                "parallelism": "batch-sharded x%d, one all-gather of logits per step" % world if world > 1
+                "parallelism": ("batch-sharded x%d, one all-gather of logits per step (%s)" % (
+                                    world, "fused into the kernel: NVLink peer stores + step flags"
+                                    if collective == "peer" else "NCCL all_gather_into_tensor")) if world > 1
                                else "single GPU",
                 "l2": "inputs rotate over %d buffers x %.1f MB (%.0f MB > 2x 126 MB L2): every step reads HBM"
                       % (nbuf, X_BYTES / 1e6, nbuf * X_BYTES / 1e6),
@@ -395,7 +414,7 @@ def main():
             "gpu_launches": args.steps * int(plan["launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "apa_pool_fused_kernel", "us_per_launch": ms_roof * 1e3,
+                         "kernel": "apa_pool_local_kernel" if plan.get("cluster_local") else "apa_pool_fused_kernel", "us_per_launch": ms_roof * 1e3,
                          "duration": "CUDA-event time of the loop / launches (%d independent launches in flight)"
                                      % nstreams,
                          "algorithmic_bytes_per_launch": ALGO_BYTES, "launches_timed": n_roof},
@@ -407,7 +426,12 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    # Captured CUDA graphs hold NCCL kernels; tearing the communicator down under them can hang.  Everything
+    # is printed and synchronised: leave without running destructors.
+    os._exit(0)
 
 
 if __name__ == "__main__":

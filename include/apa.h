@@ -152,6 +152,28 @@ int apa_attn_pool_fwd_host(const ApaDesc* desc, const float* X_host, const ApaWe
                            void* workspace, size_t workspace_bytes, const ApaTuning* tuning,
                            void* stream);
 
+/* The single collective of the multi-GPU path, fused into the kernel: instead of writing `logits`, every rank
+ * stores its [batch/frames, K] block straight into the gathered buffer of every peer (NVLink peer stores from
+ * the kernel's last step) at row offset rank * batch/frames, then publishes a per-rank step flag; the kernel
+ * returns only once the flags of all ranks for this step have arrived, so stream completion on a rank means
+ * its gathered buffer is complete.  peer_* are device pointers valid on THIS GPU (symmetric memory / IPC
+ * mappings); flags and done_counter are zeroed once by the caller; every rank must issue the same calls. */
+#define APA_MAX_PEERS 8
+typedef struct ApaPeerGather {
+  int32_t world;                                     /* 1..APA_MAX_PEERS                                   */
+  int32_t rank;                                      /* this rank                                          */
+  float* peer_logits[APA_MAX_PEERS];                 /* peer q's gathered buffer [world * batch/frames, K]  */
+  unsigned long long* peer_flags[APA_MAX_PEERS];     /* peer q's flag array [world]                         */
+  unsigned long long* done_counter;                  /* local                                              */
+} ApaPeerGather;
+
+/* apa_attn_pool_fwd for the batch-sharded multi-GPU path (single-map head only): logits go to the peers'
+ * gathered buffers as described above.  Replaces kernel + ncclAllGather; the reference has no collective
+ * at all (in-graph towers, models/slim/deployment/model_deploy.py:145).                                */
+int apa_attn_pool_fwd_gather(const ApaDesc* desc, const float* X, const ApaWeights* weights,
+                             const ApaPeerGather* gather, void* workspace, size_t workspace_bytes,
+                             const ApaTuning* tuning, void* stream);
+
 /* Full second-order pooling G[b] = X[b]^T X[b]  ([batch, C, C], symmetric).  Not present in the
  * reference code; defined from the paper's second-order pooling equation (BASELINE config 5). */
 int apa_gram_fwd(int32_t batch, int32_t hw, int32_t channels, const float* X, float* G,
@@ -159,7 +181,8 @@ int apa_gram_fwd(int32_t batch, int32_t hw, int32_t channels, const float* X, fl
 
 /* Introspection for tests/bench: how the last-validated desc would be executed.
  * Fills plan[0]=path (0 fused-rank1-map, 1 dense), [1]=cluster_size, [2]=grid CTAs,
- * [3]=fused(0/1), [4]=kernel launches per call, [5]=smem bytes, [6..7] reserved.            */
+ * [3]=fused(0/1), [4]=kernel launches per call, [5]=smem bytes, [6]=1 if the cluster-local small-batch
+ * kernel (16-CTA clusters, no grid barrier) is used, [7] reserved.                          */
 int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_attn,
                        int want_topdown, int want_pose, int32_t plan[8]);
 

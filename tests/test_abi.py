@@ -85,8 +85,8 @@ def test_workspace_sizes():
     assert ops.attn_pool_workspace(cfg3) >= 128 * 196 * 768 * 4
 
 
-@pytest.mark.parametrize("B,frames,K,expect_cluster", [(32, 1, 393, 4), (16, 1, 393, 8), (128, 1, 393, 1),
-                                                      (2, 1, 393, 16)])
+@pytest.mark.parametrize("B,frames,K,expect_cluster", [(32, 1, 393, 16), (30, 1, 393, 4), (15, 1, 393, 8),
+                                                      (130, 1, 393, 1), (2, 1, 393, 16), (320, 10, 600, 2)])
 def test_plan_without_device(B, frames, K, expect_cluster):
     """Plan introspection falls back to the nominal 148-SM B200 when no device is visible."""
     import torch
@@ -96,6 +96,7 @@ def test_plan_without_device(B, frames, K, expect_cluster):
     plan = ops.attn_pool_plan(ops.make_desc(B, 196, 2048, K, frames=frames))
     assert plan["path"] == 0 and plan["fused"] == 1 and plan["launches"] == 1
     assert plan["cluster_size"] == expect_cluster
+    assert plan["cluster_local"] == (1 if (B % 4 == 0 and frames == 1) else 0)
     assert plan["grid"] <= 148 and plan["grid"] % plan["cluster_size"] == 0
     assert plan["smem_bytes"] <= 227 * 1024
     dense = ops.attn_pool_plan(ops.make_desc(2, 196, 2048, 393, flags=ops.APA_FLAG_SINGLE_LAYER_ATT |

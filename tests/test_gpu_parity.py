@@ -78,6 +78,41 @@ def test_cluster_sizes_and_split_launch(cluster, fused):
         orc.assert_parity(got, ref, TOL)
 
 
+LOCAL_CASES = [
+    # the cluster-local small-batch kernel: B % 4 == 0, F == 1, C == 2048 (id, B, HW, K, flags)
+    ("b32_k393", 32, 196, 393, SINGLE),
+    ("b4_k600_nc3", 4, 196, 600, SINGLE),
+    ("b8_softmax", 8, 196, 393, dict(SINGLE, SOFTMAX_ATT=True)),
+    ("b8_rank3_relu", 8, 225, 393, dict(SINGLE, RANK=3, RELU_ATT=True)),
+    ("b12_k1", 12, 49, 1, SINGLE),
+    ("b4_hw3_ragged", 4, 3, 37, dict(SINGLE, SOFTMAX_ATT=True)),
+    ("b100_multigroup", 100, 49, 129, SINGLE),
+    ("b48_k768_rank2", 48, 36, 768, dict(SINGLE, RANK=2)),
+    ("b8_pose_source", 8, 196, 393, dict(RANK=2)),
+]
+
+
+@pytest.mark.parametrize("case", LOCAL_CASES, ids=[c[0] for c in LOCAL_CASES])
+def test_cluster_local_kernel(case):
+    """The 16-CTA-cluster kernel (no grid barrier) against the oracle, and bit-for-bit run-to-run."""
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    _, B, HW, K, flags = case
+    fl = dict(orc.DEFAULT_FLAGS, **flags)
+    bits, rank = ops.flags_from_cfg_net(fl)
+    plan = ops.attn_pool_plan(ops.make_desc(B, HW, 2048, K, rank=rank, flags=bits))
+    assert plan["cluster_local"] == 1 and plan["cluster_size"] == 16
+    got, _, ref, _ = _run(B, HW, 2048, K, flags, seed=31)
+    orc.assert_parity(got, ref, TOL)
+    # the general (grid-barrier) kernel on the same inputs agrees to fp32 rounding
+    t = ops.make_tuning()
+    t.reserved[1] = 1
+    got2, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
+    orc.assert_parity(got2, ref, TOL)
+    assert np.abs(got - got2).max() <= 1e-5 * max(1e-30, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("no_pdl", [0, 1])
 def test_back_to_back_launches(no_pdl):
     """Back-to-back calls on one stream overlap (programmatic dependent launch): the next launch streams
@@ -99,6 +134,29 @@ def test_back_to_back_launches(no_pdl):
         ref, _ = orc.attn_pool_head(X, params, fl, 393, want_pose=False)
         for i in range(4):
             orc.assert_parity(outs[i].cpu().numpy(), np.roll(ref, i, axis=0), TOL)
+
+
+@pytest.mark.parametrize("B,general", [(32, 0), (32, 1), (9, 0)])
+def test_fused_gather_single_rank(B, general):
+    """apa_attn_pool_fwd_gather with world == 1: the peer-store epilogue + step flags on one GPU."""
+    import torch
+    from attentionalpoolingaction_b200 import dist as apa_dist
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    fl, params, X = _setup(B, 196, 2048, 393, SINGLE, seed=17)
+    bits, rank = ops.flags_from_cfg_net(fl)
+    t = ops.make_tuning()
+    t.reserved[1] = general
+    op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 393, 196, rank=rank, flags=bits,
+                        tuning=t, device="cuda:0")
+    pg = apa_dist.PeerGather(B, 393, torch.device("cuda:0"))
+    Xd = torch.from_numpy(X).cuda()
+    for _ in range(5):
+        op.forward_gather(Xd, pg.struct)
+    torch.cuda.synchronize()
+    ref, _ = orc.attn_pool_head(X, params, fl, 393, want_pose=False)
+    orc.assert_parity(pg.out.cpu().numpy(), ref, TOL)
+    assert int(pg.flags[0].item()) == 5        # one step flag per launch
 
 
 def test_two_batches_in_flight():

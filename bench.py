@@ -5,9 +5,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A *step* is one pass of the hot path over one batch: BASELINE.json configs[1] — rank-1
-attentional pooling, 32 feature maps of 14x14x2048 fp32 per GPU, K=393 — one fused kernel launch
-(plus, at N>1, the single all-gather of the [32,393] logits).  Weak scaling: every rank owns 32
-images per step.  Prints ONE JSON line on rank 0 (contract in the task statement):
+attentional pooling, 32 feature maps of 14x14x2048 fp32 per GPU, K=393 — ONE kernel launch; at N>1
+the single all-gather of the [32,393] logits is fused into that kernel (NVLink peer stores + step
+flags, `--collective nccl` for a NCCL all_gather instead).  Consecutive steps are independent batches:
+two are kept in flight (`--streams 2`, each lane with its own workspace) and back-to-back launches on
+a lane overlap through programmatic dependent launch.  Weak scaling: every rank owns 32 images per step.  Prints ONE JSON line on rank 0 (contract in the task statement):
   value        whole-job images/s with X resident in HBM (CUDA events, max over ranks)
   e2e          same metric through the C-ABI host-buffer entry (apa_attn_pool_fwd_host): pinned
                host X -> device, head, logits -> host, inside the timed region
@@ -198,7 +200,7 @@ def main():
     ap.add_argument("--cluster", type=int, default=0, help="force CTAs per image (0 = auto)")
     ap.add_argument("--fused", type=int, default=-1, help="1 fused kernel, 0 two kernels, -1 auto")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--streams", type=int, default=1, help="independent batches in flight (1 or 2)")
+    ap.add_argument("--streams", type=int, default=2, help="independent batches in flight (1 or 2)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch")
     ap.add_argument("--trigger-lead", type=int, default=0, help="PDL trigger lead in tiles (0 = library default, -1 = none)")
     ap.add_argument("--no-coop", action="store_true", help="never use the cooperative launch attribute")
@@ -276,7 +278,9 @@ def main():
     step(0)
     torch.cuda.synchronize()
     ref, _ = orc.attn_pool_head(ring[0][:4].cpu().numpy(), params, fl, K, want_pose=False)
-    parity = orc.rel_err(logits[:4].cpu().numpy(), ref)
+    mine = (peer_l[0].out[rank * B_PER_GPU:rank * B_PER_GPU + 4] if (world > 1 and collective == "peer")
+            else logits[:4])
+    parity = orc.rel_err(mine.cpu().numpy(), ref)
     assert parity <= 1e-4, "bench parity check failed: %.3e" % parity
 
     side = torch.cuda.Stream(device=dev)

@@ -6,18 +6,20 @@
 //   cluster = 16 CTAs = 4 images x 4 row-quarters.   CTA rank r: image i = r / 4, quarter q = r % 4.
 //   phase 1   as in the grid-barrier kernel: producer lane streams 4-row x C tiles (32 KB, cp.async.bulk)
 //             through a 3-stage mbarrier ring; 8 consumer warps form a[row] and accumulate g in registers.
-//   combine   the 4 CTAs of an image push their partial g into the CTA owning those C/4 channels (DSMEM),
-//             which sums them (softmax max/sum merge) into `gown` in ITS shared memory.
-//   phase 2   the contraction g.B is split over the 16 CTAs by CHANNEL: CTA j owns channels
-//             [j C/16, (j+1) C/16) for all 4 images and all K classes.  Its weight rows are one contiguous,
-//             16-byte aligned span of B_r, so the same producer lane streams them with cp.async.bulk through
-//             the same ring right behind the last X tile (they are in flight while the combine runs).
-//             Each thread owns classes {t, t+256, t+512}; 4 images x 3 classes of fp32 accumulators.
-//   reduce    every CTA publishes its [4, K] partial logits in shared memory; CTA j sums 1/16 of the outputs
-//             over the 16 CTAs through DSMEM in fixed order (bit-reproducible), adds the bias term and
-//             writes logits.
-// Cluster-scope mbarriers (remote arrive.release / local try_wait.acquire) order every exchange; nothing
-// remote touches a CTA after its last wait, so CTAs exit without a trailing cluster barrier.
+//   exchange 1  phase 2 splits the contraction g.B over the 16 CTAs by CHANNEL: CTA j owns channels
+//             [j C/16, (j+1) C/16) for all 4 images and all K classes.  So every CTA PUSHES (st.shared::cluster)
+//             each 128-channel block of its partial g straight to the CTA that will contract it, plus its
+//             (attention mass, running max) to everybody; one 16-arrival mbarrier round publishes them and
+//             the owner sums the 4 row-quarters of each image (softmax max/sum merge) into the operand layout.
+//   phase 2   CTA j's rows of B_r are one contiguous, 16-byte aligned span, so the same producer lane streams
+//             them with cp.async.bulk through the same ring right behind the last X tile (in flight while
+//             exchange 1 runs).  Each thread owns classes {t, t+256, t+512}; 4 images x 3 classes of fp32
+//             accumulators; g is one broadcast LDS.128 per channel.
+//   exchange 2  every CTA pushes its partial logits to the CTA that reduces those outputs (1/16 each); a second
+//             16-arrival round, then a local fixed-order sum (bit-reproducible), bias, logits.
+// Cluster-scope mbarriers (remote arrive.release / local try_wait.acquire) order both exchanges; after its last
+// wait nothing remote touches a CTA, so CTAs exit without a trailing cluster barrier.  A third barrier
+// (slots_free) exists only for clusters that process more than one group of 4 images.
 #include "apa_common.cuh"
 #include "apa_kernels.h"
 
@@ -36,30 +38,27 @@ constexpr int kLTR = 4;   // rows per X tile
 template <int Q, int RMAX>
 struct LSmem {
   static constexpr int C = Q * 1024;
-  static constexpr int Cp = C / kLP;      // channels combined by one CTA of an image
   static constexpr int CH = C / kLC;      // channels contracted by one CTA in phase 2
   static constexpr int kStages = 3;
   static constexpr size_t kTileBytes = size_t(kLTR) * C * 4;
-  static constexpr size_t kRing = kStages * kTileBytes;
-  // after the ring: exchange region (combine slots [4][R][Cp], later partial logits [4][K]) -- sized on the host
-  static constexpr size_t kOffXchg = kRing;
 };
 
-struct LLayout {  // byte offsets after the exchange region (computed on host and device identically)
-  size_t xchg_bytes, off_gown, off_gs, off_stat, off_part, off_scl, off_bars, total;
+struct LLayout {  // byte offsets after the ring (computed on host and device identically)
+  size_t off_gslots, off_outslots, off_stat, off_part, off_scl, off_bars, total;
+  int per;  // outputs reduced by one CTA
 };
 __host__ __device__ inline LLayout local_layout(int C, int R, int K) {
   LLayout l;
-  const size_t slots = size_t(kLP) * R * (C / kLP) * 4;
-  const size_t outp = size_t(kLI) * K * 4;
-  l.xchg_bytes = ((slots > outp ? slots : outp) + 127) / 128 * 128;
-  size_t off = size_t(3) * kLTR * C * 4 + l.xchg_bytes;
-  l.off_gown = off; off += size_t(R) * (C / kLP) * 4 + 64;   // combined g slice + S_r
-  l.off_gs = off;   off += size_t(R) * (C / kLC) * kLI * 4;   // gS[r][ch][img]
-  l.off_stat = off; off += kLP * 8 * 4;
-  l.off_part = off; off += 2 * kLTR * 8 * 4;
-  l.off_scl = off;  off += 64;
-  l.off_bars = off; off += 8 * 16;
+  l.per = (kLI * K + kLC - 1) / kLC;
+  size_t off = size_t(3) * kLTR * C * 4;
+  // partial g pushed by every CTA of the cluster: [image][quarter][r][C/16]; after the local sum the head of
+  // this region is reused for gS[r][C/16][image] (the operand layout of phase 2)
+  l.off_gslots = off;   off += size_t(kLI) * kLP * R * (C / kLC) * 4;
+  l.off_outslots = off; off += (size_t(kLC) * l.per * 4 + 127) / 128 * 128;   // partial logits [source][per]
+  l.off_stat = off;     off += kLC * 8 * 4;                                   // (s_r, max) of every CTA
+  l.off_part = off;     off += 2 * kLTR * 8 * 4;
+  l.off_scl = off;      off += kLC * 4;
+  l.off_bars = off;     off += 8 * 16;
   l.total = off;
   return l;
 }
@@ -86,23 +85,23 @@ template <int Q, int RMAX, int MODE, int NC>
 __global__ void __launch_bounds__(kFusedThreads, (RMAX == 1) ? 2 : 1)
 apa_pool_local_kernel(const FusedParams p) {
   using L = LSmem<Q, RMAX>;
-  constexpr int C = L::C, Cp = L::Cp, CH = L::CH, TR = kLTR;
+  constexpr int C = L::C, CH = L::CH, TR = kLTR;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int R = p.R, K = p.K;
   const LLayout lay = local_layout(C, R, K);
-  float* xchg = reinterpret_cast<float*>(smem + L::kOffXchg);
-  float* gown = reinterpret_cast<float*>(smem + lay.off_gown);   // [R][Cp] then S[R]
-  float* gS = reinterpret_cast<float*>(smem + lay.off_gs);       // [R][CH][4 images]
-  float* statS = reinterpret_cast<float*>(smem + lay.off_stat);  // [4 peers][8]
+  float* gslots = reinterpret_cast<float*>(smem + lay.off_gslots);      // [4 images][4 quarters][R][CH]
+  float* gS = gslots;                                                   // [R][CH][4 images] after the sum
+  float* outslots = reinterpret_cast<float*>(smem + lay.off_outslots);  // [16 sources][per]
+  float* statS = reinterpret_cast<float*>(smem + lay.off_stat);         // [16 CTAs][8]
+  const int per = lay.per;
   float* partS = reinterpret_cast<float*>(smem + lay.off_part);
   float* scl = reinterpret_cast<float*>(smem + lay.off_scl);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
   uint64_t* full_bar = bars;          // [3]
   uint64_t* empty_bar = bars + 4;     // [3]
-  uint64_t* parts_ready = bars + 8;   // 4 arrivals: the CTAs of my image pushed their partials
-  uint64_t* gown_ready = bars + 9;    // 16 arrivals: every CTA's combined slice is readable
-  uint64_t* out_ready = bars + 10;    // 16 arrivals: every CTA's partial logits are readable
-  uint64_t* all_done = bars + 11;     // 16 arrivals: every CTA finished reading my shared memory
+  uint64_t* parts_ready = bars + 8;   // 16 arrivals: every CTA pushed its partial g blocks and stats here
+  uint64_t* out_ready = bars + 9;     // 16 arrivals: every CTA pushed its partial logits here
+  uint64_t* slots_free = bars + 10;   // 16 arrivals: every CTA consumed what was pushed to it (multi-group)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
@@ -121,10 +120,9 @@ apa_pool_local_kernel(const FusedParams p) {
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], kConsumerWarps);
       }
-      mbar_init(parts_ready, kLP);
-      mbar_init(gown_ready, kLC);
+      mbar_init(parts_ready, kLC);
       mbar_init(out_ready, kLC);
-      mbar_init(all_done, kLC);
+      mbar_init(slots_free, kLC);
       fence_mbar_init();
     }
     __syncwarp();
@@ -312,94 +310,80 @@ apa_pool_local_kernel(const FusedParams p) {
     }
 
     if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 2);
-    // ------------------------------------------------------------------ combine the 4 quarters of my image
-    // (the exchange region and gown of every CTA are free: all_done of the previous group was waited below)
+    // ------------------------------------------------------------------ exchange 1: partial g -> phase-2 owners
+    if (grp_iter > 0) mbar_wait_cluster(slots_free, (grp_iter - 1) & 1u);  // everyone consumed the last group
     {
-      const uint32_t base_rank = crank & ~3u;
 #pragma unroll
       for (int qq = 0; qq < Q; ++qq) {
         const int c = col0 + qq * 128;
-        const uint32_t owner_q = uint32_t(c / Cp);
-        const int cl = c - int(owner_q) * Cp;
+        const uint32_t owner = uint32_t(c / CH);
+        const int cl = c - int(owner) * CH;
 #pragma unroll
         for (int j = 0; j < RMAX; ++j)
           if (j < R)
-            st_dsmem_f4(dsmem_addr(xchg + (size_t(q) * R + j) * Cp + cl, base_rank + owner_q),
+            st_dsmem_f4(dsmem_addr(gslots + ((size_t(img_in_cluster) * kLP + q) * R + j) * CH + cl, owner),
                         make_float4(f[j][qq * 4 + 0], f[j][qq * 4 + 1], f[j][qq * 4 + 2], f[j][qq * 4 + 3]));
       }
-      if (tid < kLP) {
-        const uint32_t ra = dsmem_addr(statS + size_t(q) * 8, base_rank + uint32_t(tid));
+      if (tid < kLC) {  // my (s_r, max) to every CTA's stat table
+        const uint32_t ra = dsmem_addr(statS + size_t(crank) * 8, uint32_t(tid));
 #pragma unroll
         for (int j = 0; j < RMAX; ++j) st_dsmem_f(ra + 4u * j, s[j]);
         st_dsmem_f(ra + 16u, mx);
       }
       fence_acq_rel_cluster();
       named_bar_sync(1, kConsumerThreads);
-      if (tid < kLP) mbar_arrive_cluster(parts_ready, base_rank + uint32_t(tid));
+      if (tid < kLC) mbar_arrive_cluster(parts_ready, uint32_t(tid));
       mbar_wait_cluster(parts_ready, grp_iter & 1u);
     }
-    if (MODE == MODE_SOFTMAX) {
-      if (tid < kLP) {
-        float M = -INFINITY;
-        for (int pp = 0; pp < kLP; ++pp) M = fmaxf(M, statS[pp * 8 + 4]);
-        float S = 0.f;
-        for (int pp = 0; pp < kLP; ++pp) S += expf(statS[pp * 8 + 4] - M) * statS[pp * 8 + 0];
-        scl[tid] = expf(statS[tid * 8 + 4] - M) / S;
-        if (tid == 0 && q == 0 && p.smx != nullptr) {
-          p.smx[2 * b + 0] = M;
-          p.smx[2 * b + 1] = S;
-        }
-      }
-      named_bar_sync(1, kConsumerThreads);
-    }
-    {
-      const int n4 = Cp / 4;
-      for (int idx = tid; idx < R * n4; idx += kConsumerThreads) {
-        const int j = idx / n4, cl = (idx - j * n4) * 4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int pp = 0; pp < kLP; ++pp) {
-          const float4 v = *reinterpret_cast<const float4*>(xchg + (size_t(pp) * R + j) * Cp + cl);
-          const float sc = (MODE == MODE_SOFTMAX) ? scl[pp] : 1.f;
-          acc.x = fmaf(sc, v.x, acc.x);
-          acc.y = fmaf(sc, v.y, acc.y);
-          acc.z = fmaf(sc, v.z, acc.z);
-          acc.w = fmaf(sc, v.w, acc.w);
-        }
-        *reinterpret_cast<float4*>(gown + j * Cp + cl) = acc;
-      }
-      if (tid < R) {
-        float S = 1.f;
-        if (MODE != MODE_SOFTMAX) {
-          S = 0.f;
-          for (int pp = 0; pp < kLP; ++pp) S += statS[pp * 8 + tid];
-        }
-        gown[R * Cp + tid] = S;
-      }
-    }
-    fence_acq_rel_cluster();
-    named_bar_sync(1, kConsumerThreads);
-    if (tid < kLC) mbar_arrive_cluster(gown_ready, uint32_t(tid));
-    mbar_wait_cluster(gown_ready, grp_iter & 1u);  // every CTA's combined slice (and its S_r) is readable
     if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 3);
-
-    // ------------------------------------------------------------------ gather my channel block of g, all 4 images
-    // channels [crank*CH, +CH) of image i live in CTA rank 4i + (crank*CH)/Cp at offset (crank*CH) % Cp
+    // per (image, quarter) softmax scale (1 otherwise); every CTA holds the stats of all 16 CTAs
+    if (tid < kLC) {
+      float v = 1.f;
+      if (MODE == MODE_SOFTMAX) {
+        const int i4 = tid & ~3;
+        float M = -INFINITY;
+        for (int pp = 0; pp < kLP; ++pp) M = fmaxf(M, statS[(i4 + pp) * 8 + 4]);
+        float S = 0.f;
+        for (int pp = 0; pp < kLP; ++pp) S += expf(statS[(i4 + pp) * 8 + 4] - M) * statS[(i4 + pp) * 8 + 0];
+        v = expf(statS[tid * 8 + 4] - M) / S;
+        if ((tid & 3) == 0 && tid == int(crank) && p.smx != nullptr) {  // quarter 0 of each image records (max, sum)
+          p.smx[2 * (g * kLI + (tid >> 2)) + 0] = M;
+          p.smx[2 * (g * kLI + (tid >> 2)) + 1] = S;
+        }
+      }
+      scl[tid] = v;
+    }
+    named_bar_sync(1, kConsumerThreads);
     {
-      const int n4 = CH / 4;
-      const uint32_t src_q = uint32_t((int(crank) * CH) / Cp);
-      const int src_off = (int(crank) * CH) % Cp;
-      for (int idx = tid; idx < kLI * R * n4; idx += kConsumerThreads) {
-        const int i = idx / (R * n4), rem = idx - i * (R * n4);
-        const int j = rem / n4, c4 = rem - j * n4;
-        const float4 v = ld_dsmem_f4(dsmem_addr(gown + j * Cp + src_off + c4 * 4, uint32_t(4 * i) + src_q));
-        float* dst = gS + (size_t(j) * CH + c4 * 4) * kLI + i;
-        dst[0 * kLI] = v.x; dst[1 * kLI] = v.y; dst[2 * kLI] = v.z; dst[3 * kLI] = v.w;
+      // sum the 4 quarters of every (image, r, channel) into registers, then rewrite the region as gS[r][ch][image]
+      constexpr int PT = (kLI * RMAX * CH + kConsumerThreads - 1) / kConsumerThreads;
+      float sums[PT];
+      const int total = kLI * R * CH;
+#pragma unroll
+      for (int u = 0; u < PT; ++u) {
+        const int e = tid + u * kConsumerThreads;  // e = (i * R + j) * CH + c
+        float acc = 0.f;
+        if (e < total) {
+          const int i = e / (R * CH), rem = e - i * (R * CH);
+#pragma unroll
+          for (int pp = 0; pp < kLP; ++pp)
+            acc = fmaf(scl[i * kLP + pp], gslots[(size_t(i) * kLP + pp) * R * CH + rem], acc);
+        }
+        sums[u] = acc;
+      }
+      named_bar_sync(1, kConsumerThreads);
+#pragma unroll
+      for (int u = 0; u < PT; ++u) {
+        const int e = tid + u * kConsumerThreads;
+        if (e < total) {
+          const int i = e / (R * CH), rem = e - i * (R * CH);  // rem = j * CH + c
+          gS[size_t(rem) * kLI + i] = sums[u];
+        }
       }
       named_bar_sync(1, kConsumerThreads);
     }
-
     if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 6);
+
     // ------------------------------------------------------------------ phase 2: my channels x all classes
     float acc[kLI][NC];
 #pragma unroll
@@ -431,36 +415,42 @@ apa_pool_local_kernel(const FusedParams p) {
     if (last_group && ntiles == 0) griddep_launch_dependents();
     if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 7);
 
-    // ------------------------------------------------------------------ publish partial logits, reduce 1/16 of them
-    // (the exchange region is free: every CTA of my image finished reading its slots before arriving on
-    //  gown_ready, and I waited for all 16 arrivals above)
+    // ------------------------------------------------------------------ exchange 2: partial logits -> reducers
+    {
 #pragma unroll
-    for (int i = 0; i < kLI; ++i)
+      for (int i = 0; i < kLI; ++i)
 #pragma unroll
-      for (int n = 0; n < NC; ++n) {
-        const int k = tid + n * kConsumerThreads;
-        if (k < K) xchg[i * K + k] = acc[i][n];
-      }
-    fence_acq_rel_cluster();
-    named_bar_sync(1, kConsumerThreads);
-    if (tid < kLC) mbar_arrive_cluster(out_ready, uint32_t(tid));
-    mbar_wait_cluster(out_ready, grp_iter & 1u);
+        for (int n = 0; n < NC; ++n) {
+          const int k = tid + n * kConsumerThreads;
+          if (k < K) {
+            const int o = i * K + k;
+            const uint32_t red = uint32_t(o / per);
+            st_dsmem_f(dsmem_addr(outslots + size_t(crank) * per + (o - int(red) * per), red), acc[i][n]);
+          }
+        }
+      fence_acq_rel_cluster();
+      named_bar_sync(1, kConsumerThreads);
+      if (tid < kLC) mbar_arrive_cluster(out_ready, uint32_t(tid));
+      mbar_wait_cluster(out_ready, grp_iter & 1u);
+    }
     if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 4);
     if (grp_iter == 0) griddep_wait();  // first global write of this launch: previous launch fully done
     {
       const int nout = kLI * K;
-      const int per = (nout + kLC - 1) / kLC;
-      const int o_lo = int(crank) * per, o_hi = min(nout, o_lo + per);
-      for (int o = o_lo + tid; o < o_hi; o += kConsumerThreads) {
+      const int o = int(crank) * per + tid;
+      if (tid < per && o < nout) {
         const int i = o / K, k = o - i * K;
-        float part[kLC];
-#pragma unroll
-        for (int c = 0; c < kLC; ++c) part[c] = ld_dsmem_f_nv(dsmem_addr(xchg + o, uint32_t(c)));
         float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < kLC; ++c) sum += part[c];
-        for (int j = 0; j < R; ++j)
-          sum = fmaf(__ldg(p.td_b[j] + k), ld_dsmem_f_nv(dsmem_addr(gown + R * Cp + j, uint32_t(4 * i))), sum);
+        for (int c = 0; c < kLC; ++c) sum += outslots[c * per + tid];
+        for (int j = 0; j < R; ++j) {
+          float S = 1.f;
+          if (MODE != MODE_SOFTMAX) {
+            S = 0.f;
+            for (int pp = 0; pp < kLP; ++pp) S += statS[(i * kLP + pp) * 8 + j];
+          }
+          sum = fmaf(__ldg(p.td_b[j] + k), S, sum);
+        }
         const float val = sum * p.inv_scale;
         if (p.gw_world > 0) {
           const size_t off = (size_t(p.gw_rank) * p.B + size_t(g * kLI + i)) * K + k;
@@ -470,12 +460,12 @@ apa_pool_local_kernel(const FusedParams p) {
         }
       }
     }
-    // every CTA tells every other that it no longer reads its shared memory; wait for the same from all
-    // (frees xchg / gown / statS for the next group, and makes it safe to exit)
-    named_bar_sync(1, kConsumerThreads);
-    if (tid < kLC) mbar_arrive_cluster(all_done, uint32_t(tid));
-    mbar_wait_cluster(all_done, grp_iter & 1u);
+    if (!last_group) {  // tell everyone my slots / stat table may be overwritten by the next group's pushes
+      named_bar_sync(1, kConsumerThreads);
+      if (tid < kLC) mbar_arrive_cluster(slots_free, uint32_t(tid));
+    }
   }
+  named_bar_sync(1, kConsumerThreads);  // this CTA's logits stores precede the gather bookkeeping below
   if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x);
   if (tid == 0) {
     lts_mark(p.ts, 5);

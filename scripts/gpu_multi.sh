@@ -2,11 +2,10 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=${1:-2}
-true
-echo "peer gather test rc=$? : $(grep -E 'PEER_GATHER|iter' gpurun_out/peer_gather_test_$N.log | tail -3 | tr '\n' ' ')"
-tail -4 gpurun_out/peer_gather_test_$N.log | cut -c1-200
+( timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 scripts/test_peer_gather.py ) > gpurun_out/peer_gather_test_$N.log 2>&1
+echo "peer gather test rc=$? : $(grep -E 'PEER_GATHER' gpurun_out/peer_gather_test_$N.log | tail -1)"
 port=29530
-for args in "--collective peer" "--collective peer --streams 2" "--collective nccl --streams 2"; do
+for args in "" "--collective nccl"; do
   tag=$(echo "$args" | tr -d ' ')
   port=$((port+1))
   ( timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 1001 --warmup 10 --cpu-seconds 1 --e2e-steps 3 $args ) > gpurun_out/bench_${N}gpu_$tag.log 2>&1

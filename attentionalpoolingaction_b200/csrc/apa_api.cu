@@ -322,6 +322,9 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
         p.gw_flags[q] = gw->peer_flags[q];
       }
       p.gw_done = gw->done_counter;
+      // world > 1: the waiting for the peers' flags is done by a 1-warp kernel queued behind this launch, so
+      // no CTA of the head kernel sits on an SM (and a cluster slot) while NVLink round trips complete
+      p.gw_inline_wait = (gw->world == 1 || (tuning && tuning->reserved[1] == 2)) ? 1 : 0;
     }
     p.attn_raw = attn_out ? wsf(c.attn_raw) : nullptr;
     p.g = wsf(c.g);
@@ -336,12 +339,16 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
     p.inv_scale = 1.0f / (float(HW) * float(F));
     // small batches: the cluster-local kernel (no grid barrier, g never leaves shared memory)
     bool launched = false;
+    int grid = fused_grid(plan);
     if (use_local(d, w, tuning)) {
-      cudaError_t le = local_launch(p, mode, tuning, stream, nullptr);
+      cudaError_t le = local_launch(p, mode, tuning, stream, &grid);
       if (le == cudaSuccess) launched = true;
-      else (void)cudaGetLastError();  // e.g. 16-CTA clusters not launchable here: general kernel below
+      else { (void)cudaGetLastError(); grid = fused_grid(plan); }  // e.g. 16-CTA clusters not launchable here
     }
     if (!launched) APA_CUDA(fused_launch(p, plan, stream));
+    if (gw != nullptr && !p.gw_inline_wait)
+      APA_CUDA(peer_gather_wait_launch(gw->world, gw->rank, gw->peer_flags, gw->done_counter, unsigned(grid),
+                                       !(tuning && tuning->no_pdl), stream));
     if (attn_out)
       APA_CUDA(attn_finalize_m1(p.attn_raw, w->attn_w, w->attn_b, p.smx, attn_out, B, HW, R, mode, stream));
     return APA_OK;

@@ -168,7 +168,8 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 // Called by ONE thread per CTA after that CTA's logits stores (and a CTA-level barrier).  The last CTA of the
 // launch to get here publishes step flags to every peer and waits for every peer's flag of the same step.
 __device__ __forceinline__ void peer_gather_finish(int world, int rank, unsigned long long* const* flags,
-                                                   unsigned long long* done, unsigned int nblocks) {
+                                                   unsigned long long* done, unsigned int nblocks,
+                                                   bool wait_for_peers) {
   __threadfence_system();  // this CTA's peer stores are globally visible before it is counted
   unsigned long long prev;
   asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], 1;" : "=l"(prev) : "l"(done) : "memory");
@@ -176,6 +177,7 @@ __device__ __forceinline__ void peer_gather_finish(int world, int rank, unsigned
   const unsigned long long step = (prev + 1) / nblocks;
   for (int q = 0; q < world; ++q)
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[q] + rank), "l"(step) : "memory");
+  if (!wait_for_peers) return;  // a 1-warp kernel right behind this launch does the waiting (peer_gather_wait_kernel)
   const long long t0 = clock64();
   for (int r = 0; r < world; ++r) {
     unsigned long long v;

@@ -195,7 +195,58 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
     }
 }
 
+// Waits (one thread) until the step flags of all `world` ranks have reached this rank's own step, i.e. until
+// every peer's block of the gathered logits has landed here.  Launched as a programmatic dependent of the
+// gather kernel: triggers its own dependents at once (the next head launch may start streaming), then waits
+// for the gather kernel to finish before reading the step counter.
+struct PeerWaitParams {
+  unsigned long long* flags[APA_MAX_PEERS];
+  unsigned long long* done;
+  unsigned int nblocks;
+  int world, rank;
+};
+__global__ void peer_gather_wait_kernel(const PeerWaitParams w) {
+  griddep_launch_dependents();
+  griddep_wait();
+  if (threadIdx.x != 0) return;
+  unsigned long long d;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(d) : "l"(w.done) : "memory");
+  const unsigned long long step = d / w.nblocks;
+  const long long t0 = clock64();
+  for (int r = 0; r < w.world; ++r) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.flags[w.rank] + r) : "memory");
+      if (v >= step) break;
+      if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
+    } while (true);
+  }
+}
+
 }  // namespace
+
+cudaError_t peer_gather_wait_launch(int world, int rank, unsigned long long* const* flags, unsigned long long* done,
+                                    unsigned int nblocks, bool pdl, cudaStream_t stream) {
+  PeerWaitParams w;
+  for (int q = 0; q < APA_MAX_PEERS; ++q) w.flags[q] = q < world ? flags[q] : nullptr;
+  w.done = done; w.nblocks = nblocks; w.world = world; w.rank = rank;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1, 1, 1);
+  cfg.blockDim = dim3(32, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, peer_gather_wait_kernel, w);
+  if (err != cudaSuccess && pdl) {
+    (void)cudaGetLastError();
+    cfg.numAttrs = 0;
+    err = cudaLaunchKernelEx(&cfg, peer_gather_wait_kernel, w);
+  }
+  return err;
+}
 
 cudaError_t dense_gemm(const float* X, int ldx, int xs, const float* W, int ldw, const float* bias,
                        float* Y, int ldy, int col_stride, int col_off, int M, int N, int Kd, int relu,

@@ -42,6 +42,7 @@ struct FusedParams {
   float* gw_logits[APA_MAX_PEERS];
   unsigned long long* gw_flags[APA_MAX_PEERS];
   unsigned long long* gw_done;
+  int gw_inline_wait;                 // 1: the last CTA itself waits for the peers' step flags
 };
 
 struct FusedPlan {
@@ -69,6 +70,7 @@ bool fused_supported(int C, int R);
 bool local_eligible(int B, int HW, int C, int K, int R, int F);
 size_t local_smem_bytes(int C, int R, int K);
 cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out);
+int fused_grid(const FusedPlan& plan);
 
 // ---- dense path (apa_dense.cu)
 // Y[m, col_off + n*col_stride] (row stride ldy) = act(sum_k X[m*ldx + k*xs] W[k,n] + bias[n])
@@ -94,6 +96,9 @@ cudaError_t dense_relu(float* A, size_t n, cudaStream_t stream);
 // logits[v,k] = 1/(HW F) sum_f sum_hw sum_r A[b,hw,m(k),r] T[b,hw,k,r]
 cudaError_t dense_pool(const float* A, const float* T, float* logits, int B, int HW, int K, int M,
                        int R, int F, cudaStream_t stream);
+// 1-warp kernel queued right behind a gather launch: waits until every peer's flag reached this rank's step
+cudaError_t peer_gather_wait_launch(int world, int rank, unsigned long long* const* flags, unsigned long long* done,
+                                    unsigned int nblocks, bool pdl, cudaStream_t stream);
 cudaError_t gram_launch(int B, int HW, int C, const float* X, float* G, cudaStream_t stream);
 
 }  // namespace apa

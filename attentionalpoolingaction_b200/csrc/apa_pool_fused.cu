@@ -624,7 +624,7 @@ apa_pool_fused_kernel(const FusedParams p) {
       }
     }
   }
-  if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x);
+  if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x, p.gw_inline_wait != 0);
   if (tid == 0) {
     ts_mark(p.ts, 5);
     if (p.ts) p.ts[size_t(blockIdx.x) * 64 + 63] = globaltimer_ns();
@@ -858,6 +858,8 @@ cudaError_t launch_one(KernelFn fn, const FusedParams& p, const FusedPlan& plan,
   return err;
 }
 }  // namespace
+
+int fused_grid(const FusedPlan& plan) { return plan.cluster * plan.nclusters; }
 
 cudaError_t fused_launch(const FusedParams& p, const FusedPlan& plan, cudaStream_t stream) {
   KernelFn fn = select_kernel(plan.Q, plan.rmax, plan.mode);

@@ -466,7 +466,7 @@ apa_pool_local_kernel(const FusedParams p) {
     }
   }
   named_bar_sync(1, kConsumerThreads);  // this CTA's logits stores precede the gather bookkeeping below
-  if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x);
+  if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x, p.gw_inline_wait != 0);
   if (tid == 0) {
     lts_mark(p.ts, 5);
     if (p.ts) p.ts[size_t(blockIdx.x) * 64 + 63] = lglobaltimer_ns();

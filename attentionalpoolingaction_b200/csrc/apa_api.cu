@@ -185,11 +185,14 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
     plan[3] = fp.fused;
     plan[5] = int32_t(fp.smem);
     if (use_local(desc, nullptr, tuning)) {
-      const int ncl = desc->batch / 4 < 9 ? desc->batch / 4 : 9;  // 148 SMs / 16
+      int li = 4;
+      size_t lsm = 0;
+      local_plan(desc->batch, desc->channels, desc->rank, desc->num_classes, tuning, &li, &lsm);
+      const int ncl = desc->batch / li < 9 ? desc->batch / li : 9;  // 148 SMs / 16
       plan[1] = 16;
       plan[2] = 16 * ncl;
       plan[3] = 1;
-      plan[5] = int32_t(local_smem_bytes(desc->channels, desc->rank, desc->num_classes));
+      plan[5] = int32_t(lsm);
       plan[6] = 1;  // cluster-local kernel
     }
     launches += fp.fused ? 1 : 2;

@@ -68,7 +68,7 @@ bool fused_supported(int C, int R);
 
 // ---- cluster-local small-batch form (apa_pool_local.cu): 16-CTA clusters, no grid barrier, g stays in smem
 bool local_eligible(int B, int HW, int C, int K, int R, int F);
-size_t local_smem_bytes(int C, int R, int K);
+void local_plan(int B, int C, int R, int K, const ApaTuning* tuning, int* images_per_cluster, size_t* smem);
 cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out);
 int fused_grid(const FusedPlan& plan);
 

@@ -31,32 +31,35 @@ namespace apa {
 namespace {
 
 constexpr int kLC = 16;   // cluster size
-constexpr int kLP = 4;    // CTAs per image
-constexpr int kLI = 4;    // images per cluster
-constexpr int kLTR = 4;   // rows per X tile
+constexpr int kLI = 4;    // images per cluster in the default shapes (8 in the throughput shape)
+// Two shapes of the ring: (TR=4 rows, 3 stages) -> 2 CTAs per SM, and (TR=3 rows, 2 stages) -> 3 CTAs per SM
+// (<= 76,800 B of shared memory and <= 72 registers per thread), which keeps three launches resident per SM.
 
-template <int Q, int RMAX>
+template <int Q, int RMAX, int TR_, int STG>
 struct LSmem {
   static constexpr int C = Q * 1024;
   static constexpr int CH = C / kLC;      // channels contracted by one CTA in phase 2
-  static constexpr int kStages = 3;
-  static constexpr size_t kTileBytes = size_t(kLTR) * C * 4;
+  static constexpr int kStages = STG;
 };
 
 struct LLayout {  // byte offsets after the ring (computed on host and device identically)
   size_t off_gslots, off_outslots, off_stat, off_part, off_scl, off_bars, total;
-  int per;  // outputs reduced by one CTA
+  size_t stage_bytes;  // one ring stage: TR rows of X, or WR rows of B_r, whichever is larger
+  int per;             // outputs reduced by one CTA
 };
-__host__ __device__ inline LLayout local_layout(int C, int R, int K) {
+__host__ __device__ inline int local_wr(int K) { return (K <= 512) ? 16 : 8; }  // weight rows per ring stage
+__host__ __device__ inline LLayout local_layout(int C, int R, int K, int TR, int STG, int LI) {
   LLayout l;
-  l.per = (kLI * K + kLC - 1) / kLC;
-  size_t off = size_t(3) * kLTR * C * 4;
+  l.per = (LI * K + kLC - 1) / kLC;
+  const size_t xb = size_t(TR) * C * 4, wb = size_t(local_wr(K)) * K * 4;
+  l.stage_bytes = ((xb > wb ? xb : wb) + 1023) / 1024 * 1024;
+  size_t off = size_t(STG) * l.stage_bytes;
   // partial g pushed by every CTA of the cluster: [image][quarter][r][C/16]; after the local sum the head of
   // this region is reused for gS[r][C/16][image] (the operand layout of phase 2)
-  l.off_gslots = off;   off += size_t(kLI) * kLP * R * (C / kLC) * 4;
+  l.off_gslots = off;   off += size_t(kLC) * R * (C / kLC) * 4;
   l.off_outslots = off; off += (size_t(kLC) * l.per * 4 + 127) / 128 * 128;   // partial logits [source][per]
   l.off_stat = off;     off += kLC * 8 * 4;                                   // (s_r, max) of every CTA
-  l.off_part = off;     off += 2 * kLTR * 8 * 4;
+  l.off_part = off;     off += 2 * 4 * 8 * 4;
   l.off_scl = off;      off += kLC * 4;
   l.off_bars = off;     off += 8 * 16;
   l.total = off;
@@ -81,14 +84,18 @@ __device__ __forceinline__ void laxpy4(float* f, float a, const float4& x) {
   f[3] = fmaf(a, x.w, f[3]);
 }
 
-template <int Q, int RMAX, int MODE, int NC>
-__global__ void __launch_bounds__(kFusedThreads, (RMAX == 1) ? 2 : 1)
+template <int Q, int RMAX, int MODE, int NC, int TR, int STG, int LI>
+__global__ void __launch_bounds__(kFusedThreads, (RMAX == 1) ? ((STG == 2) ? 3 : 2) : 1)
 apa_pool_local_kernel(const FusedParams p) {
-  using L = LSmem<Q, RMAX>;
-  constexpr int C = L::C, CH = L::CH, TR = kLTR;
+  using L = LSmem<Q, RMAX, TR, STG>;
+  constexpr int C = L::C, CH = L::CH;
+  constexpr int LP = kLC / LI;  // CTAs (row slices) per image
+  static_assert(LI == 4 || LI == 8, "images per cluster");
+  static_assert(TR == 3 || TR == 4, "the row butterfly below is written for up to 4 rows per tile");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int R = p.R, K = p.K;
-  const LLayout lay = local_layout(C, R, K);
+  const LLayout lay = local_layout(C, R, K, TR, STG, LI);
+  const size_t stage_bytes = lay.stage_bytes;
   float* gslots = reinterpret_cast<float*>(smem + lay.off_gslots);      // [4 images][4 quarters][R][CH]
   float* gS = gslots;                                                   // [R][CH][4 images] after the sum
   float* outslots = reinterpret_cast<float*>(smem + lay.off_outslots);  // [16 sources][per]
@@ -105,12 +112,12 @@ apa_pool_local_kernel(const FusedParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
-  const int img_in_cluster = int(crank) >> 2, q = int(crank) & 3;
+  const int img_in_cluster = int(crank) / LP, q = int(crank) % LP;
   const int cluster_id = blockIdx.x / kLC, nclusters = gridDim.x / kLC;
-  const int ngroups = p.B / kLI;
-  const int row_lo = (p.HW * q) / kLP, row_hi = (p.HW * (q + 1)) / kLP;
+  const int ngroups = p.B / LI;
+  const int row_lo = (p.HW * q) / LP, row_hi = (p.HW * (q + 1)) / LP;
   const int nrows = row_hi - row_lo, ntiles = (nrows + TR - 1) / TR;
-  const int WR = (K <= 512) ? 16 : 8;            // weight rows per ring stage (<= 32 KB)
+  const int WR = local_wr(K);                    // weight rows per ring stage
   const int wchunks = CH / WR;                   // per rank
 
   // =========================================================================== producer warp
@@ -131,14 +138,14 @@ apa_pool_local_kernel(const FusedParams p) {
       const uint64_t pol_x = l2_policy_evict_first(), pol_w = l2_policy_evict_last();
       uint32_t stage = 0, phase = 0;
       for (int g = cluster_id; g < ngroups; g += nclusters) {
-        const int b = g * kLI + img_in_cluster;
+        const int b = g * LI + img_in_cluster;
         const float* xb = p.X + (size_t(b) * p.HW + row_lo) * C;
         for (int t = 0; t < ntiles; ++t) {
           const int rows = min(TR, nrows - t * TR);
           const uint32_t bytes = uint32_t(rows) * C * 4u;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          bulk_g2s(smem + stage * L::kTileBytes, xb + size_t(t) * TR * C, bytes, &full_bar[stage], pol_x);
+          bulk_g2s(smem + stage * stage_bytes, xb + size_t(t) * TR * C, bytes, &full_bar[stage], pol_x);
           if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
         }
         // this CTA's weight rows for phase 2 ride the same ring (they do not depend on phase 1)
@@ -148,7 +155,7 @@ apa_pool_local_kernel(const FusedParams p) {
             const uint32_t bytes = uint32_t(WR) * K * 4u;
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            bulk_g2s(smem + stage * L::kTileBytes, wsrc + size_t(ch) * WR * K, bytes, &full_bar[stage], pol_w);
+            bulk_g2s(smem + stage * stage_bytes, wsrc + size_t(ch) * WR * K, bytes, &full_bar[stage], pol_w);
             if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -185,7 +192,7 @@ apa_pool_local_kernel(const FusedParams p) {
   }
   uint32_t stage = 0, phase = 0, giter = 0, grp_iter = 0;
   for (int g = cluster_id; g < ngroups; g += nclusters, ++grp_iter) {
-    const int b = g * kLI + img_in_cluster;
+    const int b = g * LI + img_in_cluster;
     const bool last_group = (g + nclusters >= ngroups);
     float f[RMAX][Q * 4];
     float s[RMAX];
@@ -201,7 +208,7 @@ apa_pool_local_kernel(const FusedParams p) {
       const int rows = min(TR, nrows - it * TR);
       const bool full = (rows == TR);
       if (last_group && it == max(0, ntiles - 1 - p.trigger_lead)) griddep_launch_dependents();
-      const float* st = reinterpret_cast<const float*>(smem + stage * L::kTileBytes) + col0;
+      const float* st = reinterpret_cast<const float*>(smem + stage * stage_bytes) + col0;
       mbar_wait(&full_bar[stage], phase);
       if (tid == 0 && giter < 24) lts_mark(p.ts, 8 + int(giter));
       float4 x[TR][Q];
@@ -230,8 +237,9 @@ apa_pool_local_kernel(const FusedParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
         const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+        const float pd3 = (TR > 3) ? pd[TR - 1] : 0.f;
         float k0 = hi16 ? pd[2] : pd[0], s0 = hi16 ? pd[0] : pd[2];
-        float k1 = hi16 ? pd[3] : pd[1], s1 = hi16 ? pd[1] : pd[3];
+        float k1 = hi16 ? pd3 : pd[1], s1 = hi16 ? pd[1] : pd3;
         k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
         k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
         float kk = hi8 ? k1 : k0;
@@ -240,7 +248,7 @@ apa_pool_local_kernel(const FusedParams p) {
         kk += __shfl_xor_sync(0xffffffffu, kk, 4);
         kk += __shfl_xor_sync(0xffffffffu, kk, 2);
         kk += __shfl_xor_sync(0xffffffffu, kk, 1);
-        float* part = partS + (giter & 1u) * (TR * 8);
+        float* part = partS + (giter & 1u) * 32;
         if ((lane & 7) == 0) part[(lane >> 3) * 8 + warp] = kk;
         named_bar_sync(1, kConsumerThreads);
         float v = part[lane];
@@ -321,7 +329,7 @@ apa_pool_local_kernel(const FusedParams p) {
 #pragma unroll
         for (int j = 0; j < RMAX; ++j)
           if (j < R)
-            st_dsmem_f4(dsmem_addr(gslots + ((size_t(img_in_cluster) * kLP + q) * R + j) * CH + cl, owner),
+            st_dsmem_f4(dsmem_addr(gslots + ((size_t(img_in_cluster) * LP + q) * R + j) * CH + cl, owner),
                         make_float4(f[j][qq * 4 + 0], f[j][qq * 4 + 1], f[j][qq * 4 + 2], f[j][qq * 4 + 3]));
       }
       if (tid < kLC) {  // my (s_r, max) to every CTA's stat table
@@ -340,25 +348,25 @@ apa_pool_local_kernel(const FusedParams p) {
     if (tid < kLC) {
       float v = 1.f;
       if (MODE == MODE_SOFTMAX) {
-        const int i4 = tid & ~3;
+        const int i4 = tid & ~(LP - 1);
         float M = -INFINITY;
-        for (int pp = 0; pp < kLP; ++pp) M = fmaxf(M, statS[(i4 + pp) * 8 + 4]);
+        for (int pp = 0; pp < LP; ++pp) M = fmaxf(M, statS[(i4 + pp) * 8 + 4]);
         float S = 0.f;
-        for (int pp = 0; pp < kLP; ++pp) S += expf(statS[(i4 + pp) * 8 + 4] - M) * statS[(i4 + pp) * 8 + 0];
+        for (int pp = 0; pp < LP; ++pp) S += expf(statS[(i4 + pp) * 8 + 4] - M) * statS[(i4 + pp) * 8 + 0];
         v = expf(statS[tid * 8 + 4] - M) / S;
-        if ((tid & 3) == 0 && tid == int(crank) && p.smx != nullptr) {  // quarter 0 of each image records (max, sum)
-          p.smx[2 * (g * kLI + (tid >> 2)) + 0] = M;
-          p.smx[2 * (g * kLI + (tid >> 2)) + 1] = S;
+        if ((tid % LP) == 0 && tid == int(crank) && p.smx != nullptr) {  // slice 0 of each image records (max, sum)
+          p.smx[2 * (g * LI + (tid / LP)) + 0] = M;
+          p.smx[2 * (g * LI + (tid / LP)) + 1] = S;
         }
       }
       scl[tid] = v;
     }
     named_bar_sync(1, kConsumerThreads);
     {
-      // sum the 4 quarters of every (image, r, channel) into registers, then rewrite the region as gS[r][ch][image]
-      constexpr int PT = (kLI * RMAX * CH + kConsumerThreads - 1) / kConsumerThreads;
+      // sum the row slices of every (image, r, channel) into registers, then rewrite the region as gS[r][ch][image]
+      constexpr int PT = (LI * RMAX * CH + kConsumerThreads - 1) / kConsumerThreads;
       float sums[PT];
-      const int total = kLI * R * CH;
+      const int total = LI * R * CH;
 #pragma unroll
       for (int u = 0; u < PT; ++u) {
         const int e = tid + u * kConsumerThreads;  // e = (i * R + j) * CH + c
@@ -366,8 +374,8 @@ apa_pool_local_kernel(const FusedParams p) {
         if (e < total) {
           const int i = e / (R * CH), rem = e - i * (R * CH);
 #pragma unroll
-          for (int pp = 0; pp < kLP; ++pp)
-            acc = fmaf(scl[i * kLP + pp], gslots[(size_t(i) * kLP + pp) * R * CH + rem], acc);
+          for (int pp = 0; pp < LP; ++pp)
+            acc = fmaf(scl[i * LP + pp], gslots[(size_t(i) * LP + pp) * R * CH + rem], acc);
         }
         sums[u] = acc;
       }
@@ -377,7 +385,7 @@ apa_pool_local_kernel(const FusedParams p) {
         const int e = tid + u * kConsumerThreads;
         if (e < total) {
           const int i = e / (R * CH), rem = e - i * (R * CH);  // rem = j * CH + c
-          gS[size_t(rem) * kLI + i] = sums[u];
+          gS[size_t(rem) * LI + i] = sums[u];
         }
       }
       named_bar_sync(1, kConsumerThreads);
@@ -385,26 +393,31 @@ apa_pool_local_kernel(const FusedParams p) {
     if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 6);
 
     // ------------------------------------------------------------------ phase 2: my channels x all classes
-    float acc[kLI][NC];
+    float acc[LI][NC];
 #pragma unroll
-    for (int i = 0; i < kLI; ++i)
+    for (int i = 0; i < LI; ++i)
 #pragma unroll
       for (int n = 0; n < NC; ++n) acc[i][n] = 0.f;
     for (int j = 0; j < R; ++j) {
       for (int ch = 0; ch < wchunks; ++ch) {
-        const float* ws = reinterpret_cast<const float*>(smem + stage * L::kTileBytes);
+        const float* ws = reinterpret_cast<const float*>(smem + stage * stage_bytes);
         mbar_wait(&full_bar[stage], phase);
-        const float* gj = gS + (size_t(j) * CH + ch * WR) * kLI;
+        const float* gj = gS + (size_t(j) * CH + ch * WR) * LI;
         for (int c = 0; c < WR; ++c) {
-          const float4 gv = *reinterpret_cast<const float4*>(gj + c * kLI);  // 4 images, broadcast
+          float4 gv[LI / 4];  // all images of the cluster, broadcast
+#pragma unroll
+          for (int h = 0; h < LI / 4; ++h) gv[h] = *reinterpret_cast<const float4*>(gj + c * LI + h * 4);
 #pragma unroll
           for (int n = 0; n < NC; ++n) {
             const int k = tid + n * kConsumerThreads;
             const float w = (k < K) ? ws[c * K + k] : 0.f;
-            acc[0][n] = fmaf(gv.x, w, acc[0][n]);
-            acc[1][n] = fmaf(gv.y, w, acc[1][n]);
-            acc[2][n] = fmaf(gv.z, w, acc[2][n]);
-            acc[3][n] = fmaf(gv.w, w, acc[3][n]);
+#pragma unroll
+            for (int h = 0; h < LI / 4; ++h) {
+              acc[h * 4 + 0][n] = fmaf(gv[h].x, w, acc[h * 4 + 0][n]);
+              acc[h * 4 + 1][n] = fmaf(gv[h].y, w, acc[h * 4 + 1][n]);
+              acc[h * 4 + 2][n] = fmaf(gv[h].z, w, acc[h * 4 + 2][n]);
+              acc[h * 4 + 3][n] = fmaf(gv[h].w, w, acc[h * 4 + 3][n]);
+            }
           }
         }
         __syncwarp();
@@ -418,7 +431,7 @@ apa_pool_local_kernel(const FusedParams p) {
     // ------------------------------------------------------------------ exchange 2: partial logits -> reducers
     {
 #pragma unroll
-      for (int i = 0; i < kLI; ++i)
+      for (int i = 0; i < LI; ++i)
 #pragma unroll
         for (int n = 0; n < NC; ++n) {
           const int k = tid + n * kConsumerThreads;
@@ -436,7 +449,7 @@ apa_pool_local_kernel(const FusedParams p) {
     if (tid == 0 && grp_iter == 0) lts_mark(p.ts, 4);
     if (grp_iter == 0) griddep_wait();  // first global write of this launch: previous launch fully done
     {
-      const int nout = kLI * K;
+      const int nout = LI * K;
       const int o = int(crank) * per + tid;
       if (tid < per && o < nout) {
         const int i = o / K, k = o - i * K;
@@ -447,16 +460,16 @@ apa_pool_local_kernel(const FusedParams p) {
           float S = 1.f;
           if (MODE != MODE_SOFTMAX) {
             S = 0.f;
-            for (int pp = 0; pp < kLP; ++pp) S += statS[(i * kLP + pp) * 8 + j];
+            for (int pp = 0; pp < LP; ++pp) S += statS[(i * LP + pp) * 8 + j];
           }
           sum = fmaf(__ldg(p.td_b[j] + k), S, sum);
         }
         const float val = sum * p.inv_scale;
         if (p.gw_world > 0) {
-          const size_t off = (size_t(p.gw_rank) * p.B + size_t(g * kLI + i)) * K + k;
+          const size_t off = (size_t(p.gw_rank) * p.B + size_t(g * LI + i)) * K + k;
           for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
         } else {
-          p.logits[size_t(g * kLI + i) * K + k] = val;
+          p.logits[size_t(g * LI + i) * K + k] = val;
         }
       }
     }
@@ -475,22 +488,45 @@ apa_pool_local_kernel(const FusedParams p) {
 
 using LKernelFn = void (*)(const FusedParams);
 
-template <int Q, int RMAX, int MODE>
+template <int Q, int RMAX, int MODE, int TR, int STG, int LI>
 LKernelFn lsel_nc(int nc) {
-  if (nc == 1) return &apa_pool_local_kernel<Q, RMAX, MODE, 1>;
-  if (nc == 2) return &apa_pool_local_kernel<Q, RMAX, MODE, 2>;
-  return &apa_pool_local_kernel<Q, RMAX, MODE, 3>;
+  if (nc == 1) return &apa_pool_local_kernel<Q, RMAX, MODE, 1, TR, STG, LI>;
+  if (nc == 2) return &apa_pool_local_kernel<Q, RMAX, MODE, 2, TR, STG, LI>;
+  return &apa_pool_local_kernel<Q, RMAX, MODE, 3, TR, STG, LI>;
 }
-LKernelFn local_select(int Q, int rmax, int mode, int nc) {
+// The three shapes of the kernel.  slots = resident CTAs per SM the ring is sized for.
+//   0: 4-row tiles x 3 stages, 4 images x 4 row-quarters per cluster   (2 CTAs / SM; every rank)
+//   1: 3-row tiles x 2 stages, 4 images x 4 row-quarters per cluster   (3 CTAs / SM; rank 1)
+//   2: 3-row tiles x 2 stages, 8 images x 2 row-halves per cluster     (3 CTAs / SM; rank 1, B % 8 == 0):
+//      half as many CTAs per launch, each streaming twice as long before the same latency-bound tail, so
+//      more launches co-reside and the tail costs half the CTA-slot time (throughput shape)
+struct LShape { int tr, stg, li; };
+constexpr LShape kShapes[3] = {{4, 3, 4}, {3, 2, 4}, {3, 2, 8}};
+
+LKernelFn local_select(int Q, int rmax, int mode, int nc, int shape) {
   if (Q != 2) return nullptr;
   if (rmax == 1) {
-    if (mode == MODE_PLAIN) return lsel_nc<2, 1, MODE_PLAIN>(nc);
-    if (mode == MODE_RELU) return lsel_nc<2, 1, MODE_RELU>(nc);
-    return lsel_nc<2, 1, MODE_SOFTMAX>(nc);
+    if (shape == 2) {
+      if (mode == MODE_PLAIN) return lsel_nc<2, 1, MODE_PLAIN, 3, 2, 8>(nc);
+      if (mode == MODE_RELU) return lsel_nc<2, 1, MODE_RELU, 3, 2, 8>(nc);
+      return lsel_nc<2, 1, MODE_SOFTMAX, 3, 2, 8>(nc);
+    }
+    if (shape == 1) {
+      if (mode == MODE_PLAIN) return lsel_nc<2, 1, MODE_PLAIN, 3, 2, 4>(nc);
+      if (mode == MODE_RELU) return lsel_nc<2, 1, MODE_RELU, 3, 2, 4>(nc);
+      return lsel_nc<2, 1, MODE_SOFTMAX, 3, 2, 4>(nc);
+    }
+    if (mode == MODE_PLAIN) return lsel_nc<2, 1, MODE_PLAIN, 4, 3, 4>(nc);
+    if (mode == MODE_RELU) return lsel_nc<2, 1, MODE_RELU, 4, 3, 4>(nc);
+    return lsel_nc<2, 1, MODE_SOFTMAX, 4, 3, 4>(nc);
   }
-  if (mode == MODE_PLAIN) return lsel_nc<2, APA_MAX_RANK, MODE_PLAIN>(nc);
-  if (mode == MODE_RELU) return lsel_nc<2, APA_MAX_RANK, MODE_RELU>(nc);
+  if (mode == MODE_PLAIN) return lsel_nc<2, APA_MAX_RANK, MODE_PLAIN, 4, 3, 4>(nc);
+  if (mode == MODE_RELU) return lsel_nc<2, APA_MAX_RANK, MODE_RELU, 4, 3, 4>(nc);
   return nullptr;
+}
+constexpr size_t kThreeSlotSmem = 76800;  // (228 KB - 3 x 1 KB reserved) / 3
+size_t shape_smem(int C, int R, int K, int shape) {
+  return local_layout(C, R, K, kShapes[shape].tr, kShapes[shape].stg, kShapes[shape].li).total;
 }
 
 std::mutex g_lmu;
@@ -507,12 +543,23 @@ bool local_eligible(int B, int HW, int C, int K, int R, int F) {
          R <= APA_MAX_RANK && (size_t(K) * 8 * 4) <= size_t(32) * 1024;
 }
 
+int local_shape(int B, int C, int R, int K, const ApaTuning* tuning) {
+  // reserved[1]: 4 / 5 / 6 force shape 0 / 1 / 2 (when the problem allows it); otherwise the widest that fits
+  const int force = tuning ? tuning->reserved[1] : 0;
+  if (R != 1 || force == 4) return 0;
+  if (force == 5) return 1;
+  if (B % 8 == 0 && (force == 6 || shape_smem(C, R, K, 2) <= kThreeSlotSmem)) return 2;
+  return (shape_smem(C, R, K, 1) <= kThreeSlotSmem) ? 1 : 0;
+}
+
 cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out) {
   const int Q = p.C / 1024, rmax = (p.R == 1) ? 1 : APA_MAX_RANK;
   const int nc = (p.K + kConsumerThreads - 1) / kConsumerThreads;
-  LKernelFn fn = local_select(Q, rmax, mode, nc);
+  const int shape = local_shape(p.B, p.C, p.R, p.K, tuning);
+  const int li = kShapes[shape].li;
+  LKernelFn fn = local_select(Q, rmax, mode, nc, shape);
   if (fn == nullptr) return cudaErrorInvalidValue;
-  const size_t smem = local_layout(p.C, p.R, p.K).total;
+  const size_t smem = shape_smem(p.C, p.R, p.K, shape);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   int dev = 0;
   cudaError_t err = cudaGetDevice(&dev);
@@ -547,7 +594,7 @@ cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning
     if (g_ln < 32) g_lcache[g_ln++] = {dev, fn, smem, nmax};
   }
   if (nmax <= 0) return cudaErrorInvalidConfiguration;
-  int ncl = p.B / kLI;
+  int ncl = p.B / li;
   if (ncl > nmax) ncl = nmax;
   if (grid_out) *grid_out = ncl * kLC;
   cudaLaunchConfig_t cfg = {};
@@ -576,6 +623,10 @@ cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning
   return err;
 }
 
-size_t local_smem_bytes(int C, int R, int K) { return local_layout(C, R, K).total; }
+void local_plan(int B, int C, int R, int K, const ApaTuning* tuning, int* images_per_cluster, size_t* smem) {
+  const int shape = local_shape(B, C, R, K, tuning);
+  if (images_per_cluster) *images_per_cluster = kShapes[shape].li;
+  if (smem) *smem = shape_smem(C, R, K, shape);
+}
 
 }  // namespace apa

@@ -21,6 +21,7 @@ X from HBM.  `--impl reference` times the CPU port (TF-1.1 itself cannot be inst
 from __future__ import annotations
 
 import argparse
+import math
 import json
 import os
 import statistics
@@ -200,13 +201,16 @@ def main():
     ap.add_argument("--cluster", type=int, default=0, help="force CTAs per image (0 = auto)")
     ap.add_argument("--fused", type=int, default=-1, help="1 fused kernel, 0 two kernels, -1 auto")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--streams", type=int, default=2, help="independent batches in flight (1 or 2)")
+    ap.add_argument("--streams", type=int, default=4, help="independent batches in flight (1..4)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch")
     ap.add_argument("--trigger-lead", type=int, default=0, help="PDL trigger lead in tiles (0 = library default, -1 = none)")
     ap.add_argument("--no-coop", action="store_true", help="never use the cooperative launch attribute")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: all-gather fused into the kernel as NVLink peer stores, or a NCCL all_gather per step")
     ap.add_argument("--general", action="store_true", help="force the grid-barrier kernel (not the cluster-local one)")
+    ap.add_argument("--shape", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="cluster-local kernel shape (-1 = library default; 0: 4 img/cluster, 2 CTAs/SM; "
+                         "1: 4 img/cluster, 3 CTAs/SM; 2: 8 img/cluster, 3 CTAs/SM)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=30)
     args = ap.parse_args()
@@ -238,8 +242,8 @@ def main():
     bits, rnk = ops.flags_from_cfg_net(fl)
     tuning = ops.make_tuning(args.cluster, args.fused, no_pdl=int(args.no_pdl), no_cooperative=int(args.no_coop))
     tuning.reserved[0] = args.trigger_lead
-    tuning.reserved[1] = int(args.general)
-    nstreams = max(1, min(2, args.streams))
+    tuning.reserved[1] = 1 if args.general else (0 if args.shape < 0 else 4 + args.shape)
+    nstreams = max(1, min(4, args.streams))
     # one op (= one workspace) per in-flight batch: consecutive steps are independent batches, so two
     # of them overlap on the GPU (one streams X from HBM while the other is in its latency-bound tail)
     opl = [ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, rank=rnk,
@@ -303,7 +307,7 @@ def main():
         if args.no_graph or nsteps == 0:
             return (lambda: enqueue(nsteps, with_collective)), "stream"
         try:
-            ring_steps = nbuf * nstreams // (2 if nbuf % 2 == 0 and nstreams == 2 else 1)
+            ring_steps = math.lcm(nbuf, nstreams)
             full, rem = divmod(nsteps, ring_steps)
             graphs = []
             with torch.cuda.stream(side):

@@ -111,6 +111,14 @@ def test_cluster_local_kernel(case):
     got2, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
     orc.assert_parity(got2, ref, TOL)
     assert np.abs(got - got2).max() <= 1e-5 * max(1e-30, np.abs(ref).max())
+    # both ring shapes of the cluster-local kernel (4-row x 3-stage: 2 CTAs/SM, 3-row x 2-stage: 3 CTAs/SM)
+    for force in (4, 5, 6):
+        t = ops.make_tuning()
+        t.reserved[1] = force
+        got3, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
+        orc.assert_parity(got3, ref, TOL)
+        got4, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
+        assert np.array_equal(got3, got4)
 
 
 @pytest.mark.parametrize("no_pdl", [0, 1])

@@ -10,6 +10,7 @@
 
 namespace {
 
+
 using namespace apa;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -24,7 +25,7 @@ constexpr size_t kCtrlBytes = 2048;         // 256 x u64 arrival counters, index
 constexpr size_t kTsBytes = 320 * 64 * 8;  // debug timeline: up to 320 CTAs x 64 stamps
 
 struct Carve {
-  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, total;
+  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, total;
   int path;  // 0 fused single-map, 1 dense
 };
 
@@ -53,6 +54,11 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
     c.smx = take(B * 2);
     if (want_attn) c.attn_raw = take(B * HW);
     if (!single) c.a0 = take(B * HW * 8);  // up to 8 partial-dot planes from the pose GEMM epilogue
+    if (split_eligible(d->channels, d->rank)) {  // two-kernel pipeline: per-row-slice partial g and stats
+      const size_t lp = size_t(split_lp_cap(d->batch, d->hw));
+      c.gpart = take(B * lp * R * C);
+      c.gstat = take(B * lp * 8);
+    }
   } else {
     if (!want_attn) c.A = take(B * HW * M * R);
     if (!want_topdown) c.T = take(B * HW * K * R);
@@ -60,6 +66,20 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
   if (!single || want_pose) c.pose_pre = take(B * HW * size_t(d->pose_channels));
   c.total = off;
   return c;
+}
+
+// ApaTuning.reserved[1] selects the form of the fused single-map head (A/B tests, tools):
+//   0 auto   1 grid-barrier kernel   2 (gather) inline peer wait   4/5/6 cluster-local shapes 0/1/2
+//   7 two-kernel STREAM + CONTRACT pipeline   8 never the pipeline
+bool use_split(const ApaDesc* d, const ApaTuning* t) {
+  if (!split_eligible(d->channels, d->rank)) return false;
+  const int force = t ? t->reserved[1] : 0;
+  if (force == 7) return true;
+  if (force != 0 && force != 2) return false;
+  if (t && (t->fused >= 0 || t->max_ctas != 0 || t->cluster_size != 0)) return false;  // explicit single-kernel requests
+  // measured (scripts/bench_forms.py): the pipeline wins when several frames are averaged per video (its
+  // contraction sums the frames' partial g before the matrix product); otherwise the single-kernel forms do
+  return d->frames > 1;
 }
 
 bool use_local(const ApaDesc* d, const ApaWeights* w, const ApaTuning* t) {
@@ -195,7 +215,19 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
       plan[5] = int32_t(lsm);
       plan[6] = 1;  // cluster-local kernel
     }
-    launches += fp.fused ? 1 : 2;
+    bool two = !fp.fused;
+    if (use_split(desc, tuning)) {
+      const int lp = split_lp(desc->batch, desc->hw, tuning);
+      const int units = desc->batch * lp, cap = 148 * (desc->rank == 1 ? 3 : 1);
+      plan[1] = lp;                                  // row slices per image
+      plan[2] = units < cap ? units : cap;           // STREAM grid
+      plan[3] = 0;
+      plan[5] = int32_t(split_stream_smem(desc->channels));
+      plan[6] = 2;                                   // STREAM + CONTRACT pipeline
+      plan[7] = split_contract_grid(desc->num_classes);
+      two = true;
+    }
+    launches += two ? 2 : 1;
     if (want_attn) launches += 1;
   } else {
     const int R = desc->rank;
@@ -343,7 +375,15 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
     // small batches: the cluster-local kernel (no grid barrier, g never leaves shared memory)
     bool launched = false;
     int grid = fused_grid(plan);
-    if (use_local(d, w, tuning)) {
+    if (use_split(d, tuning)) {
+      p.gpart = wsf(c.gpart);
+      p.gstat = wsf(c.gstat);
+      int g1 = 0, g2 = 0;
+      cudaError_t se = split_launch(p, mode, tuning, stream, &g1, &g2);
+      if (se == cudaSuccess) { launched = true; grid = g2; }  // the CONTRACT CTAs do the gather bookkeeping
+      else (void)cudaGetLastError();
+    }
+    if (!launched && use_local(d, w, tuning)) {
       cudaError_t le = local_launch(p, mode, tuning, stream, &grid);
       if (le == cudaSuccess) launched = true;
       else { (void)cudaGetLastError(); grid = fused_grid(plan); }  // e.g. 16-CTA clusters not launchable here

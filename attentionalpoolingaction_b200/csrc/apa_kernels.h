@@ -43,6 +43,10 @@ struct FusedParams {
   unsigned long long* gw_flags[APA_MAX_PEERS];
   unsigned long long* gw_done;
   int gw_inline_wait;                 // 1: the last CTA itself waits for the peers' step flags
+  // two-kernel pipeline (apa_pool_split.cu)
+  float* gpart;                       // workspace [B, lp, R, C]: per-row-slice partial g
+  float* gstat;                       // workspace [B, lp, 8]: (s_r[4], running max) per row slice
+  int lp;                             // row slices per image
 };
 
 struct FusedPlan {
@@ -71,6 +75,15 @@ bool local_eligible(int B, int HW, int C, int K, int R, int F);
 void local_plan(int B, int C, int R, int K, const ApaTuning* tuning, int* images_per_cluster, size_t* smem);
 cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out);
 int fused_grid(const FusedPlan& plan);
+
+// ---- two-kernel pipeline (apa_pool_split.cu): lean STREAM kernel (partial g -> workspace) + CONTRACT kernel
+bool split_eligible(int C, int R);
+int split_lp_cap(int B, int HW);                             // workspace is sized for this many row slices
+int split_lp(int B, int HW, const ApaTuning* tuning);
+int split_contract_grid(int K);
+size_t split_stream_smem(int C);
+cudaError_t split_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream,
+                         int* stream_grid, int* contract_grid);
 
 // ---- dense path (apa_dense.cu)
 // Y[m, col_off + n*col_stride] (row stride ldy) = act(sum_k X[m*ldx + k*xs] W[k,n] + bias[n])

@@ -225,8 +225,10 @@ def attn_pool_plan(desc, tuning=None, want_attn=False, want_topdown=False, want_
                                  int(want_attn), int(want_topdown), int(want_pose), ctypes.byref(out))
     if st != APA_OK:
         raise ApaError(st, "apa_attn_pool_plan")
-    keys = ("path", "cluster_size", "grid", "fused", "launches", "smem_bytes", "cluster_local")
-    return OrderedDict(zip(keys, list(out)[:7]))
+    # cluster_local: 0 grid-barrier kernel, 1 cluster-local kernel, 2 STREAM + CONTRACT pipeline (then
+    # cluster_size = row slices per image, grid = STREAM grid, contract_grid = CONTRACT grid)
+    keys = ("path", "cluster_size", "grid", "fused", "launches", "smem_bytes", "cluster_local", "contract_grid")
+    return OrderedDict(zip(keys, list(out)[:8]))
 
 
 def strerror(status):

@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: all-gather fused into the kernel as NVLink peer stores, or a NCCL all_gather per step")
     ap.add_argument("--general", action="store_true", help="force the grid-barrier kernel (not the cluster-local one)")
+    ap.add_argument("--split", action="store_true", help="force the two-kernel STREAM + CONTRACT pipeline")
     ap.add_argument("--shape", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="cluster-local kernel shape (-1 = library default; 0: 4 img/cluster, 2 CTAs/SM; "
                          "1: 4 img/cluster, 3 CTAs/SM; 2: 8 img/cluster, 3 CTAs/SM)")
@@ -242,7 +243,7 @@ def main():
     bits, rnk = ops.flags_from_cfg_net(fl)
     tuning = ops.make_tuning(args.cluster, args.fused, no_pdl=int(args.no_pdl), no_cooperative=int(args.no_coop))
     tuning.reserved[0] = args.trigger_lead
-    tuning.reserved[1] = 1 if args.general else (0 if args.shape < 0 else 4 + args.shape)
+    tuning.reserved[1] = 1 if args.general else (7 if args.split else (0 if args.shape < 0 else 4 + args.shape))
     nstreams = max(1, min(4, args.streams))
     # one op (= one workspace) per in-flight batch: consecutive steps are independent batches, so two
     # of them overlap on the GPU (one streams X from HBM while the other is in its latency-bound tail)

@@ -110,7 +110,10 @@ typedef struct ApaTuning {
   int32_t no_pdl;       /* 1 = do not launch the fused kernel as a programmatic dependent of the      */
                         /*     previous kernel in the stream (back-to-back calls then do not overlap) */
   int32_t debug_timestamps; /* 1 = fused kernel writes a per-CTA clock64 timeline at workspace+2048    */
-  int32_t reserved[2];
+  int32_t reserved[2];  /* [0] PDL trigger lead in tiles (0 = default, <0 = at the end of the stream).      */
+                        /* [1] form of the single-map head, for A/B tests: 0 auto, 1 grid-barrier kernel,   */
+                        /*     2 inline peer wait (gather), 4/5/6 cluster-local shapes 0/1/2,               */
+                        /*     7 two-kernel STREAM + CONTRACT pipeline (cluster_size = row slices / image)  */
 } ApaTuning;
 
 /* Library/ABI version (APA_ABI_VERSION of the build). */
@@ -182,7 +185,8 @@ int apa_gram_fwd(int32_t batch, int32_t hw, int32_t channels, const float* X, fl
 /* Introspection for tests/bench: how the last-validated desc would be executed.
  * Fills plan[0]=path (0 fused-rank1-map, 1 dense), [1]=cluster_size, [2]=grid CTAs,
  * [3]=fused(0/1), [4]=kernel launches per call, [5]=smem bytes, [6]=1 if the cluster-local small-batch
- * kernel (16-CTA clusters, no grid barrier) is used, [7] reserved.                          */
+ * kernel (16-CTA clusters, no grid barrier) is used, 2 for the STREAM + CONTRACT pipeline (then [1] = row
+ * slices per image, [2] = STREAM grid, [7] = CONTRACT grid).                                 */
 int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_attn,
                        int want_topdown, int want_pose, int32_t plan[8]);
 

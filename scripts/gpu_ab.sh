@@ -7,7 +7,9 @@ out=gpurun_out/ab_$(basename "$1").log
 while IFS= read -r cfg; do
   [ -z "$cfg" ] && continue
   echo -n "$cfg: " >> $out
-  timeout 300 python bench.py $cfg --steps 4200 --warmup 84 --cpu-seconds 0.2 --e2e-steps 3 2>&1 | tail -1 | python -c "
+  envp="${cfg%%|*}"; args="${cfg#*|}"
+  [ "$envp" = "$cfg" ] && envp=""
+  env $envp timeout 300 python bench.py $args --steps 4200 --warmup 84 --cpu-seconds 0.2 --e2e-steps 3 2>&1 | tail -1 | python -c "
 import sys, json
 l = sys.stdin.read().strip()
 try:

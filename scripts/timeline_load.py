@@ -23,7 +23,7 @@ def main():
     bits, rank = ops.flags_from_cfg_net(fl)
     tun = ops.make_tuning(debug_timestamps=1)
     tun.reserved[0] = lead
-    tun.reserved[1] = 4 + shape
+    tun.reserved[1] = 7 if shape == 7 else 4 + shape
     P = {k: torch.from_numpy(v) for k, v in params.items()}
     opl = [ops.AttnPoolOp(P, K, HW, rank=rank, flags=bits, tuning=tun) for _ in range(NOPS)]
     xs = [torch.relu(torch.randn((B, HW, C), device="cuda")) for _ in range(8)]
@@ -53,11 +53,39 @@ def main():
                 cur.wait_stream(s)
     g.replay(); torch.cuda.synchronize()
     g.replay(); torch.cuda.synchronize()
-    rows = []
+    rows, crows = [], []
     for j, op in enumerate(opl):
         d, ws, _ = op._workspace(B, (False, False, False))
-        ts = ws[2048:2048 + 320 * 64 * 8].view(torch.int64).reshape(320, 64).cpu().numpy()[:ops.attn_pool_plan(d, tun)["grid"]]
-        rows.append(ts)
+        plan = ops.attn_pool_plan(d, tun)
+        ts = ws[2048:2048 + 320 * 64 * 8].view(torch.int64).reshape(320, 64).cpu().numpy()
+        rows.append(ts[:min(160, plan["grid"])])
+        if plan["cluster_local"] == 2:
+            crows.append(ts[160:160 + min(160, plan["contract_grid"])])
+    if crows:
+        t0 = min(r[:, 62].min() for r in rows)
+        order = np.argsort([r[:, 62].min() for r in rows])
+        print("streams %d STREAM+CONTRACT pipeline lead %d; us since the first of the last %d launches started" % (S, lead, NOPS))
+        print("launch | STREAM start(min..max) end(min..max)  per-CTA: first tile, stream end, end | CONTRACT start(min..max) end(min..max) per-CTA: waited, g loaded, contracted, end")
+        for j in order:
+            a, c = rows[j], crows[j]
+            ra = (a[:, 0:64] - a[:, 0:1]) / 1.965 / 1e3
+            rc = (c[:, 0:8] - c[:, 0:1]) / 1.965 / 1e3
+            print("%4d | %6.2f..%6.2f  %6.2f..%6.2f   %5.2f %5.2f %5.2f | %6.2f..%6.2f  %6.2f..%6.2f   %5.2f %5.2f %5.2f %5.2f" % (
+                j, (a[:, 62].min() - t0) / 1e3, (a[:, 62].max() - t0) / 1e3, (a[:, 63].min() - t0) / 1e3, (a[:, 63].max() - t0) / 1e3,
+                ra[:, 8].mean(), ra[:, 2].mean(), ra[:, 5].mean(),
+                (c[:, 62].min() - t0) / 1e3, (c[:, 62].max() - t0) / 1e3, (c[:, 63].min() - t0) / 1e3, (c[:, 63].max() - t0) / 1e3,
+                rc[:, 1].mean(), rc[:, 2].mean(), rc[:, 3].mean(), rc[:, 5].mean()))
+        ends = sorted((crows[j][:, 63].max() - t0) / 1e3 for j in order)
+        print("end-to-end spacing (us):", np.round(np.diff(ends), 2).tolist())
+        mid = rows[order[NOPS // 2]]
+        tiles = (mid[:, 8:32] - mid[:, 0:1]) / 1.965 / 1e3
+        nt = int((mid[0, 8:32] > 0).sum())
+        print("middle launch, CTA 0 tiles ready (us):", np.round(tiles[0, :nt], 2).tolist())
+        smid = mid[:, 61]
+        cnt = np.bincount(smid.astype(np.int64), minlength=148)
+        print("middle launch: STREAM CTAs on %d distinct SMs; CTAs per SM histogram (0,1,2,3+):" % int((cnt > 0).sum()),
+              [int((cnt == 0).sum()), int((cnt == 1).sum()), int((cnt == 2).sum()), int((cnt >= 3).sum())])
+        return
     t0 = min(r[:, 62].min() for r in rows)
     ghz = 1.965
     order = np.argsort([r[:, 62].min() for r in rows])

@@ -121,6 +121,67 @@ def test_cluster_local_kernel(case):
         assert np.array_equal(got3, got4)
 
 
+def _split_tuning(lp=0, no_pdl=0):
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    t = ops.make_tuning(lp, -1, no_pdl=no_pdl)
+    t.reserved[1] = 7     # force the two-kernel STREAM + CONTRACT pipeline
+    return t
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_split_pipeline_parity(case):
+    """The two-kernel pipeline (lean streaming kernel -> partial g in the workspace -> cluster contraction)
+    on every single-map shape: ranks, relu/softmax, frames, C = 1024, K = 1..600, B = 1..200; bit-reproducible."""
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    _, B, HW, C, K, flags, F = case
+    fl = dict(orc.DEFAULT_FLAGS, **flags)
+    bits, rank = ops.flags_from_cfg_net(fl)
+    plan = ops.attn_pool_plan(ops.make_desc(B, HW, C, K, frames=F, rank=rank, flags=bits), _split_tuning())
+    assert plan["cluster_local"] == 2 and plan["launches"] == 2
+    got, _, ref, _ = _run(B, HW, C, K, flags, F=F, tuning=_split_tuning())
+    orc.assert_parity(got, ref, TOL)
+    got2, _, _, _ = _run(B, HW, C, K, flags, F=F, tuning=_split_tuning())
+    assert np.array_equal(got, got2)
+
+
+@pytest.mark.parametrize("lp", [1, 2, 4, 8, 16])
+def test_split_pipeline_row_slices(lp):
+    """Any number of row slices per image (ApaTuning.cluster_size) gives the same logits to fp32 rounding."""
+    from oracle import attn_pool_oracle as orc
+    for flags in (SINGLE, dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=2, RELU_ATT=True)):
+        got, _, ref, _ = _run(9, 196, 2048, 393, flags, seed=3, tuning=_split_tuning(lp))
+        orc.assert_parity(got, ref, TOL)
+        got, _, ref, _ = _run(9, 196, 2048, 393, flags, seed=3, tuning=_split_tuning(lp, no_pdl=1))
+        orc.assert_parity(got, ref, TOL)
+
+
+def test_split_pipeline_back_to_back_and_end_points():
+    """40 queued launches share one workspace (STREAM(n+1) overlaps CONTRACT(n)); plus the attention end point
+    (softmax normalisation read back from the pipeline's stats) and the pose-source attention (config 003)."""
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    for flags in (SINGLE, dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=2, RELU_ATT=True)):
+        fl, params, X = _setup(32, 196, 2048, 393, flags, seed=12)
+        bits, rank = ops.flags_from_cfg_net(fl)
+        op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 393, 196, rank=rank, flags=bits,
+                            tuning=_split_tuning(), device="cuda:0")
+        xs = [torch.from_numpy(np.roll(X, i, axis=0).copy()).cuda() for i in range(4)]
+        outs = [torch.empty((32, 393), device="cuda") for _ in range(4)]
+        for rep in range(10):
+            for i in range(4):
+                op(xs[i], logits=outs[i])
+        torch.cuda.synchronize()
+        ref, _ = orc.attn_pool_head(X, params, fl, 393, want_pose=False)
+        for i in range(4):
+            orc.assert_parity(outs[i].cpu().numpy(), np.roll(ref, i, axis=0), TOL)
+    for flags in (dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=3, RELU_ATT=True), dict(RANK=2), dict(SOFTMAX_ATT=True)):
+        got, ep, ref, ref_ep = _run(5, 196, 2048, 393, flags, seed=21, want=(True, False, False), tuning=_split_tuning())
+        orc.assert_parity(got, ref, TOL)
+        orc.assert_parity(ep["PosePrelogitsBasedAttention"], ref_ep["PosePrelogitsBasedAttention"], TOL, "attention")
+
+
 @pytest.mark.parametrize("no_pdl", [0, 1])
 def test_back_to_back_launches(no_pdl):
     """Back-to-back calls on one stream overlap (programmatic dependent launch): the next launch streams
@@ -144,7 +205,7 @@ def test_back_to_back_launches(no_pdl):
             orc.assert_parity(outs[i].cpu().numpy(), np.roll(ref, i, axis=0), TOL)
 
 
-@pytest.mark.parametrize("B,general", [(32, 0), (32, 1), (9, 0)])
+@pytest.mark.parametrize("B,general", [(32, 0), (32, 1), (9, 0), (32, 7), (9, 7)])
 def test_fused_gather_single_rank(B, general):
     """apa_attn_pool_fwd_gather with world == 1: the peer-store epilogue + step flags on one GPU."""
     import torch

@@ -62,10 +62,16 @@ FUSED_CASES = [
 
 @pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
 def test_fused_path_parity(case):
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     from oracle import attn_pool_oracle as orc
     _, B, HW, C, K, flags, F = case
     got, _, ref, _ = _run(B, HW, C, K, flags, F=F)
     orc.assert_parity(got, ref, TOL)
+    if F > 1:   # the default for several frames per video is the pipeline: cover the grid-barrier kernel too
+        t = ops.make_tuning()
+        t.reserved[1] = 1
+        got, _, ref, _ = _run(B, HW, C, K, flags, F=F, tuning=t)
+        orc.assert_parity(got, ref, TOL)
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])

@@ -1,25 +1,26 @@
-// apa_pool_local.cu — the small-batch form of the fused head: everything after the HBM stream stays inside
+// apa_pool_local.cu — the cluster-local form of the fused head: everything after the HBM stream stays inside
 // one 16-CTA thread-block cluster, so there is NO grid barrier and the attention-weighted features g never
 // leave shared memory.  Same math as apa_pool_fused.cu (single attention map, rank 1..4, plain / relu /
 // spatial softmax); reference sites nets_factory.py:259-328, :350-352.
 //
-//   cluster = 16 CTAs = 4 images x 4 row-quarters.   CTA rank r: image i = r / 4, quarter q = r % 4.
-//   phase 1   as in the grid-barrier kernel: producer lane streams 4-row x C tiles (32 KB, cp.async.bulk)
-//             through a 3-stage mbarrier ring; 8 consumer warps form a[row] and accumulate g in registers.
+//   cluster = 16 CTAs = LI images x LP row slices (LI x LP = 16; LI = 4 or 8).  CTA rank r: image r / LP, slice r % LP.
+//   phase 1   as in the grid-barrier kernel: producer lane streams TR-row x C tiles (cp.async.bulk) through an
+//             STG-stage mbarrier ring; 8 consumer warps form a[row] and accumulate g in registers.
 //   exchange 1  phase 2 splits the contraction g.B over the 16 CTAs by CHANNEL: CTA j owns channels
-//             [j C/16, (j+1) C/16) for all 4 images and all K classes.  So every CTA PUSHES (st.shared::cluster)
+//             [j C/16, (j+1) C/16) for all LI images and all K classes.  So every CTA PUSHES (st.shared::cluster)
 //             each 128-channel block of its partial g straight to the CTA that will contract it, plus its
 //             (attention mass, running max) to everybody; one 16-arrival mbarrier round publishes them and
-//             the owner sums the 4 row-quarters of each image (softmax max/sum merge) into the operand layout.
+//             the owner sums the row slices of each image (softmax max/sum merge) into the operand layout.
 //   phase 2   CTA j's rows of B_r are one contiguous, 16-byte aligned span, so the same producer lane streams
 //             them with cp.async.bulk through the same ring right behind the last X tile (in flight while
-//             exchange 1 runs).  Each thread owns classes {t, t+256, t+512}; 4 images x 3 classes of fp32
-//             accumulators; g is one broadcast LDS.128 per channel.
+//             exchange 1 runs).  Each thread owns classes {t, t+256, t+512}; LI images x 3 classes of fp32
+//             accumulators; g is broadcast LDS.128s per channel.
 //   exchange 2  every CTA pushes its partial logits to the CTA that reduces those outputs (1/16 each); a second
 //             16-arrival round, then a local fixed-order sum (bit-reproducible), bias, logits.
 // Cluster-scope mbarriers (remote arrive.release / local try_wait.acquire) order both exchanges; after its last
 // wait nothing remote touches a CTA, so CTAs exit without a trailing cluster barrier.  A third barrier
-// (slots_free) exists only for clusters that process more than one group of 4 images.
+// (slots_free) exists only for clusters that process more than one group of LI images.
+// (TR, STG, LI) come in three shapes, see kShapes below and DESIGN.md section 4.2.
 #include "apa_common.cuh"
 #include "apa_kernels.h"
 

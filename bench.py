@@ -8,7 +8,7 @@ A *step* is one pass of the hot path over one batch: BASELINE.json configs[1] â€
 attentional pooling, 32 feature maps of 14x14x2048 fp32 per GPU, K=393 â€” ONE kernel launch; at N>1
 the single all-gather of the [32,393] logits is fused into that kernel (NVLink peer stores + step
 flags, `--collective nccl` for a NCCL all_gather instead).  Consecutive steps are independent batches:
-two are kept in flight (`--streams 2`, each lane with its own workspace) and back-to-back launches on
+four are kept in flight (`--streams 4`, each lane with its own workspace) and back-to-back launches on
 a lane overlap through programmatic dependent launch.  Weak scaling: every rank owns 32 images per step.  Prints ONE JSON line on rank 0 (contract in the task statement):
   value        whole-job images/s with X resident in HBM (CUDA events, max over ranks)
   e2e          same metric through the C-ABI host-buffer entry (apa_attn_pool_fwd_host): pinned

@@ -112,6 +112,37 @@ def test_plan_without_device(B, frames, K, expect_cluster):
     assert ops.attn_pool_plan(ops.make_desc(320, 196, 2048, 600, frames=10), t)["cluster_local"] == 0
 
 
+
+@pytest.mark.parametrize("kw,expect", [
+    # (descriptor, tuning code) -> (cluster_local, cluster_size, grid, launches, smem_bytes)
+    (dict(B=32), (1, 16, 64, 1, 73024)),                 # config 2: cluster-local throughput shape (8 images / cluster)
+    (dict(B=36), (1, 16, 144, 1, 66752)),                # B % 8 != 0: 4 images / cluster, 3 CTAs / SM
+    (dict(B=32, rank=2), (1, 16, 128, 1, 122048)),       # rank chain: 2-CTA/SM shape
+    (dict(B=32, K=600), (1, 16, 128, 1, 67904)),         # K = 600: the 8-image shape no longer fits 3 per SM
+    (dict(B=30), (0, 4, 120, 1, 107472)),                # odd batch: grid-barrier kernel
+    (dict(B=32, C=1024), (0, 4, 128, 1, 103376)),
+    (dict(B=32, K=800), (0, 4, 128, 1, 107472)),         # K > 768: not cluster-local
+    (dict(B=320, F=10, K=600), (2, 1, 320, 2, 74048)),   # several frames per video: STREAM + CONTRACT pipeline
+    (dict(B=32, code=4), (1, 16, 128, 1, 113856)),       # forced shapes / forms
+    (dict(B=32, code=5), (1, 16, 128, 1, 66752)),
+    (dict(B=32, code=7), (2, 4, 128, 2, 74048)),
+    (dict(B=32, code=1), (0, 4, 128, 1, 107472)),
+])
+def test_dispatch_policy_without_device(kw, expect):
+    """Which form of the single-map head a descriptor gets, pinned on the nominal B200."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("device present: plan comes from the occupancy query")
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    kw = dict(kw)
+    t = ops.make_tuning()
+    t.reserved[1] = kw.pop("code", 0)
+    d = ops.make_desc(kw.get("B"), 196, kw.get("C", 2048), kw.get("K", 393), frames=kw.get("F", 1), rank=kw.get("rank", 1))
+    p = ops.attn_pool_plan(d, t)
+    assert (p["cluster_local"], p["cluster_size"], p["grid"], p["launches"], p["smem_bytes"]) == expect
+    assert p["path"] == 0
+
+
 def test_forward_without_gpu_fails_loudly():
     """No CPU fallback: on a box without a GPU the forward entry returns an error, never a result."""
     import torch

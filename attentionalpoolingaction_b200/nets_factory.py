@@ -50,29 +50,65 @@ def get_network_fn(name, num_classes, num_pose_keypoints, cfg, weight_decay=0.0,
     state = {}
 
     def network_fn(images, end_point_names=()):
-        frames_per_video = 1
-        if images.dim() == 5:                       # nets_factory.py:121-125
-            frames_per_video = images.shape[1]
-            images = images.reshape((-1,) + tuple(images.shape[2:]))
+        return _run_head(state, images, params, flags, rank, num_classes, num_pose_keypoints, end_point_names, tuning)
+
+    network_fn.default_image_size = 224
+    return network_fn
+
+
+def _run_head(state, images, params, flags, rank, num_classes, num_pose_keypoints, end_point_names, tuning,
+              frames_per_video=1):
+    """Shared by `network_fn` and `attn_pool_head`: one AttnPoolOp per (HW, C, frames) in `state`."""
+    if images.dim() == 5:                       # nets_factory.py:121-125
+        frames_per_video = images.shape[1]
+        images = images.reshape((-1,) + tuple(images.shape[2:]))
+    if images.dim() == 3:                       # [B*F, HW, C]: no spatial axes to restore
+        B, HW, C = images.shape
+        H = W = None
+    else:
         B, H, W, C = images.shape
-        key = (H * W, C, frames_per_video)
-        op = state.get(key)
-        if op is None:
-            op = ops.AttnPoolOp(params, num_classes, H * W, channels=C, frames=frames_per_video, rank=rank,
-                                flags=flags, num_pose_keypoints=num_pose_keypoints, tuning=tuning,
-                                device=images.device)
-            state[key] = op
-        want = set(end_point_names)
-        logits, eps = op(images.reshape(B, H * W, C),
-                         want_attn="PosePrelogitsBasedAttention" in want,
-                         want_topdown="TopDownAttention" in want,
-                         want_pose="PoseLogits" in want)
-        # restore the spatial axes the reference's end-points carry
+        HW = H * W
+    key = (HW, C, frames_per_video)
+    op = state.get(key)
+    if op is None:
+        op = ops.AttnPoolOp(params, num_classes, HW, channels=C, frames=frames_per_video, rank=rank,
+                            flags=flags, num_pose_keypoints=num_pose_keypoints, tuning=tuning,
+                            device=images.device)
+        state[key] = op
+    want = set(end_point_names)
+    logits, eps = op(images.reshape(B, HW, C),
+                     want_attn="PosePrelogitsBasedAttention" in want,
+                     want_topdown="TopDownAttention" in want,
+                     want_pose="PoseLogits" in want)
+    if H is not None:   # restore the spatial axes the reference's end-points carry
         for k in ("PosePrelogitsBasedAttention", "TopDownAttention", "PoseLogits"):
             if k in eps:
                 t = eps[k]
                 eps[k] = t.reshape((B, H, W) + tuple(t.shape[2:]))
-        return logits, eps
+    return logits, eps
 
-    network_fn.default_image_size = 224
-    return network_fn
+
+_HEAD_STATE = {}   # id(params) -> (params, {shape key -> AttnPoolOp}); holds the dict so the id stays unique
+
+
+def attn_pool_head(X, params, cfg_net_flags, num_classes, is_training=False, frames_per_video=1,
+                   num_pose_keypoints=16, end_point_names=(), tuning=None):
+    """Functional form of the head: conv5 features in, `(logits, end_points)` out.
+
+    X: float32 CUDA tensor `[B*F, H, W, C]` or `[B*F, HW, C]`; `params`: TF variable name -> array/tensor
+    (nets_factory.py:260-269, :300-303, :151-159); `cfg_net_flags`: `cfg.NET`-like object or dict with the
+    `USE_POSE_PRELOGITS_BASED_ATTENTION_*` flags (src/config.py:182-209).  The device-resident copy of the
+    variables and the workspace are cached per `params` object, so repeated calls cost one kernel launch.
+    """
+    if is_training:
+        raise NotImplementedError("forward/eval only: the training graph (dropout, backward) is a 'next' row")
+    if params is None:
+        raise ValueError("params (TF variable name -> array) is required: the head has trained variables")
+    flags, rank = ops.flags_from_cfg_net(cfg_net_flags)
+    entry = _HEAD_STATE.get(id(params))
+    if entry is None or entry[0] is not params:
+        entry = (params, {})
+        _HEAD_STATE[id(params)] = entry
+    state = entry[1].setdefault((flags, rank, int(num_classes), int(num_pose_keypoints)), {})
+    return _run_head(state, X, params, flags, rank, num_classes, num_pose_keypoints, end_point_names, tuning,
+                     frames_per_video=frames_per_video)

@@ -394,6 +394,12 @@ def test_network_fn_shim():
     assert tuple(ep["PosePrelogitsBasedAttention"].shape) == (6, 15, 15, 1)
     orc.assert_parity(ep["PosePrelogitsBasedAttention"].reshape(6, 225, 1).cpu().numpy(),
                       ref_ep["PosePrelogitsBasedAttention"], TOL)
+    # the functional form runs the same op
+    pt = {k: torch.from_numpy(v) for k, v in params.items()}
+    logits2, ep2 = nets_factory.attn_pool_head(torch.from_numpy(X).cuda().reshape(6, 15, 15, 2048), pt, fl, 393,
+                                               frames_per_video=3)
+    orc.assert_parity(logits2.cpu().numpy(), ref, TOL)
+    assert list(ep2) == ["Logits"]
 
 
 def test_gram_matches_oracle():

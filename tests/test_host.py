@@ -67,6 +67,67 @@ def test_get_network_fn_argument_checks():
         nets_factory.get_network_fn("resnet_v1_101", 393, 16, cfg, params={})
 
 
+def test_head_call_logic_with_a_stand_in_op(monkeypatch):
+    """`network_fn` / `attn_pool_head` host logic (frame folding, one op per shape, end-point axes, caching per
+    `params` object) with the CUDA op replaced by a recorder: no GPU involved, nothing numeric checked."""
+    import torch
+    from attentionalpoolingaction_b200 import config, nets_factory
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    built = []
+
+    class FakeOp(object):
+        def __init__(self, params, num_classes, hw, channels=2048, frames=1, rank=1, flags=0,
+                     num_pose_keypoints=16, tuning=None, device=None):
+            self.args = dict(K=num_classes, hw=hw, C=channels, F=frames, rank=rank, flags=flags)
+            built.append(self)
+
+        def __call__(self, X, want_attn=False, want_topdown=False, want_pose=False, logits=None):
+            B, HW, C = X.shape
+            assert HW == self.args["hw"] and C == self.args["C"]
+            R = self.args["rank"]
+            tail = (R,) if R > 1 else ()
+            eps = {"Logits": torch.zeros(B // self.args["F"], self.args["K"])}
+            if want_attn:
+                eps["PosePrelogitsBasedAttention"] = torch.zeros((B, HW, 1) + tail)
+            if want_topdown:
+                eps["TopDownAttention"] = torch.zeros((B, HW, self.args["K"]) + tail)
+            if want_pose:
+                eps["PoseLogits"] = torch.zeros(B, HW, 16)
+            return eps["Logits"], eps
+
+    monkeypatch.setattr(ops, "AttnPoolOp", FakeOp)
+    cfg = config.default_cfg()
+    cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION = True
+    cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION_SINGLE_LAYER_ATT = True
+    cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION_RANK = 2
+    params = {"dummy": 0}
+    fn = nets_factory.get_network_fn("resnet_v1_101", 393, 16, cfg, params=params)
+    logits, eps = fn(torch.zeros(6, 7, 7, 2048), end_point_names=("PosePrelogitsBasedAttention", "TopDownAttention"))
+    assert logits.shape == (6, 393)
+    assert eps["PosePrelogitsBasedAttention"].shape == (6, 7, 7, 1, 2)      # nets_factory.py:271-274,287
+    assert eps["TopDownAttention"].shape == (6, 7, 7, 393, 2)               # :305-309
+    logits, _ = fn(torch.zeros(2, 3, 7, 7, 2048))                           # [B, F, H, W, C] (:119-125)
+    assert logits.shape == (2, 393) and built[-1].args["F"] == 3
+    fn(torch.zeros(4, 7, 7, 2048))
+    assert len(built) == 2                                                  # same (HW, C, frames): op re-used
+
+    flags = {"SINGLE_LAYER_ATT": True, "RANK": 1}
+    n0 = len(built)
+    logits, eps = nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), params, flags, 600)
+    assert logits.shape == (8, 600) and list(eps) == ["Logits"]
+    nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), params, flags, 600)
+    assert len(built) == n0 + 1                                             # cached per params object
+    logits, eps = nets_factory.attn_pool_head(torch.zeros(20, 7, 7, 2048), params, flags, 600, frames_per_video=10,
+                                              end_point_names=("PoseLogits",))
+    assert logits.shape == (2, 600) and eps["PoseLogits"].shape == (20, 7, 7, 16)
+    nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), dict(params), flags, 600)
+    assert len(built) == n0 + 3                                             # another params object: another op
+    with pytest.raises(NotImplementedError):
+        nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), params, flags, 600, is_training=True)
+    with pytest.raises(ValueError):
+        nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), None, flags, 600)
+
+
 def test_shard_bounds_cover_batch_exactly():
     from attentionalpoolingaction_b200 import dist
     for n in (1, 7, 8, 32, 256, 257):

@@ -21,11 +21,12 @@ inline int mode_of(int flags) {
   return MODE_PLAIN;
 }
 
-constexpr size_t kCtrlBytes = 2048;         // 256 x u64 arrival counters, indexed by gridDim.x
+constexpr size_t kCtrlBytes = 4096;         // [0, 2048): 256 x u64 grid-barrier counters, indexed by gridDim.x
+constexpr size_t kFlowCtrOff = 2048;        // [2048, 4096): the flow form's ticket / done / arrival counters
 constexpr size_t kTsBytes = 320 * 64 * 8;  // debug timeline: up to 320 CTAs x 64 stamps
 
 struct Carve {
-  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, total;
+  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, cpart, gsum, fl_img, fl_arr, total;
   int path;  // 0 fused single-map, 1 dense
 };
 
@@ -54,10 +55,17 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
     c.smx = take(B * 2);
     if (want_attn) c.attn_raw = take(B * HW);
     if (!single) c.a0 = take(B * HW * 8);  // up to 8 partial-dot planes from the pose GEMM epilogue
-    if (split_eligible(d->channels, d->rank)) {  // two-kernel pipeline: per-row-slice partial g and stats
-      const size_t lp = size_t(split_lp_cap(d->batch, d->hw));
-      c.gpart = take(B * lp * R * C);
-      c.gstat = take(B * lp * 8);
+    if (split_eligible(d->channels, d->rank)) {  // pipeline / flow forms: partial g and stats per row run
+      size_t slots = B * size_t(split_lp_cap(d->batch, d->hw));
+      if (flow_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) {
+        if (flow_gpart_slots(d->batch) > slots) slots = flow_gpart_slots(d->batch);
+        c.cpart = take(flow_cpart_floats(d->batch, d->num_classes, d->frames));
+        c.gsum = take(B * 4);
+        c.fl_img = take(B * 2);  // u64 per image
+        c.fl_arr = take(flow_slices(d->batch, d->num_classes, d->frames) * 2);
+      }
+      c.gpart = take(slots * R * C);
+      c.gstat = take(slots * 8);
     }
   } else {
     if (!want_attn) c.A = take(B * HW * M * R);
@@ -68,14 +76,21 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
   return c;
 }
 
-// ApaTuning.reserved[1] selects the form of the fused single-map head (A/B tests, tools):
-//   0 auto   1 grid-barrier kernel   2 (gather) inline peer wait   4/5/6 cluster-local shapes 0/1/2
-//   7 two-kernel STREAM + CONTRACT pipeline   8 never the pipeline
+// ApaTuning.form (APA_FORM_*) selects the form of the fused single-map head (A/B tests, tools).
+bool use_flow(const ApaDesc* d, const ApaTuning* t) {
+  if (!flow_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) return false;
+  const int force = t ? t->form : 0;
+  if (force == APA_FORM_FLOW) return true;
+  if (force != APA_FORM_AUTO) return false;
+  if (t && (t->fused >= 0 || t->cluster_size != 0)) return false;  // explicit requests for the older forms
+  return false;
+}
+
 bool use_split(const ApaDesc* d, const ApaTuning* t) {
   if (!split_eligible(d->channels, d->rank)) return false;
-  const int force = t ? t->reserved[1] : 0;
-  if (force == 7) return true;
-  if (force != 0 && force != 2) return false;
+  const int force = t ? t->form : 0;
+  if (force == APA_FORM_PIPELINE) return true;
+  if (force != APA_FORM_AUTO) return false;
   if (t && (t->fused >= 0 || t->max_ctas != 0 || t->cluster_size != 0)) return false;  // explicit single-kernel requests
   // measured (scripts/bench_forms.py): the pipeline wins when several frames are averaged per video (its
   // contraction sums the frames' partial g before the matrix product); otherwise the single-kernel forms do
@@ -85,7 +100,7 @@ bool use_split(const ApaDesc* d, const ApaTuning* t) {
 bool use_local(const ApaDesc* d, const ApaWeights* w, const ApaTuning* t) {
   if (!local_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) return false;
   if (t && (t->fused == 0 || (t->cluster_size != 0 && t->cluster_size != 16) || t->max_ctas != 0)) return false;
-  if (t && t->reserved[1] == 1) return false;  // reserved[1] == 1: force the grid-barrier kernel (A/B tests)
+  if (t && (t->form == APA_FORM_GRID_BARRIER || t->form == APA_FORM_FLOW)) return false;
   if (w)
     for (int r = 0; r < d->rank; ++r)
       if (reinterpret_cast<uintptr_t>(w->topdown_w[r]) & 15u) return false;  // bulk copies need 16 B alignment
@@ -169,7 +184,9 @@ size_t apa_attn_pool_workspace(const ApaDesc* desc, int want_attn, int want_topd
 int apa_attn_pool_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
   if (workspace == nullptr) return APA_ERR_NULL;
   if (workspace_bytes < kCtrlBytes || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APA_ERR_WORKSPACE;
-  APA_CUDA(cudaMemsetAsync(workspace, 0, kCtrlBytes, static_cast<cudaStream_t>(stream)));
+  // every counter of every form lives in the workspace and starts from zero (control block, per-image and
+  // per-slice arrival counters of the flow form): clear all of it once
+  APA_CUDA(cudaMemsetAsync(workspace, 0, workspace_bytes, static_cast<cudaStream_t>(stream)));
   return APA_OK;
 }
 
@@ -216,7 +233,15 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
       plan[6] = 1;  // cluster-local kernel
     }
     bool two = !fp.fused;
-    if (use_split(desc, tuning)) {
+    if (use_flow(desc, tuning)) {
+      plan[1] = 0;
+      plan[2] = flow_stream_ctas(desc->batch, desc->hw, tuning) + 8 * flow_class_slices(desc->num_classes);
+      plan[3] = 1;
+      plan[5] = int32_t(flow_smem(desc->channels));
+      plan[6] = 3;                                   // flow form: STREAM + CONTRACT CTAs in one launch
+      plan[7] = 8 * flow_class_slices(desc->num_classes);
+      two = false;
+    } else if (use_split(desc, tuning)) {
       const int lp = split_lp(desc->batch, desc->hw, tuning);
       const int units = desc->batch * lp, cap = 148 * (desc->rank == 1 ? 3 : 1);
       plan[1] = lp;                                  // row slices per image
@@ -308,7 +333,7 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
   float* P = nullptr;
   const bool fuse_a0 = !single && c.path == 0 && pose_out == nullptr &&
                        dense_gemm_tc_eligible(rows, d->pose_channels, C) &&
-                       dense_gemm_tc_dot_parts(d->pose_channels) <= 8 && getenv("APA_DENSE_SIMT") == nullptr;
+                       dense_gemm_tc_dot_parts(d->pose_channels) <= 8 && !dense_force_simt();
   if (need_pose_pre && !fuse_a0) {
     P = wsf(c.pose_pre);
     APA_CUDA(dense_gemm(X, C, 1, w->pose_w, d->pose_channels, w->pose_b, P, d->pose_channels, 1, 0, rows,
@@ -359,7 +384,7 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
       p.gw_done = gw->done_counter;
       // world > 1: the waiting for the peers' flags is done by a 1-warp kernel queued behind this launch, so
       // no CTA of the head kernel sits on an SM (and a cluster slot) while NVLink round trips complete
-      p.gw_inline_wait = (gw->world == 1 || (tuning && tuning->reserved[1] == 2)) ? 1 : 0;
+      p.gw_inline_wait = (gw->world == 1) ? 1 : 0;
     }
     p.attn_raw = attn_out ? wsf(c.attn_raw) : nullptr;
     p.g = wsf(c.g);
@@ -368,14 +393,25 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
     p.barrier = reinterpret_cast<unsigned long long*>(ws + c.ctrl) + ((plan.cluster * plan.nclusters) & 255);
     // PDL trigger: by default as soon as a CTA starts consuming (measured best: the next launch's clusters take
     // the free CTA slots as they appear); reserved[0] > 0 = that many tiles before the end, < 0 = at the end
-    p.trigger_lead = (tuning && tuning->reserved[0] != 0) ? (tuning->reserved[0] < 0 ? 0 : tuning->reserved[0]) : 1 << 20;
+    p.trigger_lead = (tuning && tuning->pdl_trigger_lead != 0) ? (tuning->pdl_trigger_lead < 0 ? 0 : tuning->pdl_trigger_lead) : 1 << 20;
     p.ts = (tuning && tuning->debug_timestamps) ? reinterpret_cast<unsigned long long*>(ws + c.ts) : nullptr;
     p.B = B; p.HW = HW; p.C = C; p.K = K; p.R = R; p.F = F;
     p.inv_scale = 1.0f / (float(HW) * float(F));
     // small batches: the cluster-local kernel (no grid barrier, g never leaves shared memory)
     bool launched = false;
     int grid = fused_grid(plan);
-    if (use_split(d, tuning)) {
+    if (gw == nullptr && use_flow(d, tuning)) {
+      p.gpart = wsf(c.gpart);
+      p.gstat = wsf(c.gstat);
+      p.cpart = wsf(c.cpart);
+      p.gsum = wsf(c.gsum);
+      p.fl_img = reinterpret_cast<unsigned long long*>(ws + c.fl_img);
+      p.fl_arr = reinterpret_cast<unsigned long long*>(ws + c.fl_arr);
+      p.fl_ctr = reinterpret_cast<unsigned long long*>(ws + kFlowCtrOff);
+      APA_CUDA(flow_launch(p, mode, tuning, stream, &grid));
+      launched = true;
+    }
+    if (!launched && use_split(d, tuning)) {
       p.gpart = wsf(c.gpart);
       p.gstat = wsf(c.gstat);
       int g1 = 0, g2 = 0;

@@ -9,6 +9,9 @@ namespace apa {
 #ifndef APA_SPIN_TIMEOUT_CYCLES
 #define APA_SPIN_TIMEOUT_CYCLES (6000000000ll)  // ~3 s at 2 GHz: trap instead of hanging the GPU
 #endif
+#ifndef APA_PEER_TIMEOUT_CYCLES
+#define APA_PEER_TIMEOUT_CYCLES (120000000000ll)  // ~60 s: a straggling RANK (first-step skew, data stall) is not a bug
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -185,6 +188,34 @@ __device__ __forceinline__ void peer_gather_finish(int world, int rank, unsigned
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags[rank] + r) : "memory");
       if (v >= step) break;
       if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
+    } while (true);
+  }
+}
+
+// Protocol v2 (flow form).  flags[q] is rank q's flag array of 2 * world words: word r = the last step whose
+// logits rank r has completely stored into q's gathered ring; word world + r = the last step rank r has
+// STARTED after everything before it in r's stream completed (= r has consumed every older gathered buffer).
+__device__ __forceinline__ void peer_gather_publish(int world, int rank, unsigned long long* const* flags,
+                                                    unsigned long long step) {
+  for (int q = 0; q < world; ++q)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[q] + rank), "l"(step) : "memory");
+}
+__device__ __forceinline__ void peer_gather_publish_started(int world, int rank, unsigned long long* const* flags,
+                                                            unsigned long long step) {
+  for (int q = 0; q < world; ++q)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[q] + world + rank), "l"(step) : "memory");
+}
+// one thread: spin until word `first + r` of my flag array is >= target for every rank r
+__device__ __forceinline__ void peer_gather_wait_all(int world, const unsigned long long* mine, int first,
+                                                     unsigned long long target) {
+  const long long t0 = clock64();
+  for (int r = 0; r < world; ++r) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + first + r) : "memory");
+      if (v >= target) break;
+      __nanosleep(100);
+      if (clock64() - t0 > APA_PEER_TIMEOUT_CYCLES) __trap();
     } while (true);
   }
 }

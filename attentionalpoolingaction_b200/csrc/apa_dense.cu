@@ -248,12 +248,16 @@ cudaError_t peer_gather_wait_launch(int world, int rank, unsigned long long* con
   return err;
 }
 
+bool dense_force_simt() {
+  static const bool force_simt = (getenv("APA_DENSE_SIMT") != nullptr);
+  return force_simt;
+}
+
 cudaError_t dense_gemm(const float* X, int ldx, int xs, const float* W, int ldw, const float* bias,
                        float* Y, int ldy, int col_stride, int col_off, int M, int N, int Kd, int relu,
                        cudaStream_t stream) {
   if (M <= 0 || N <= 0) return cudaSuccess;
-  static const bool force_simt = (getenv("APA_DENSE_SIMT") != nullptr);  // A/B switch for tests and profiling
-  if (!force_simt && dense_gemm_tc_eligible(M, N, Kd))
+  if (!dense_force_simt() && dense_gemm_tc_eligible(M, N, Kd))
     return dense_gemm_tc(X, ldx, xs, W, ldw, bias, Y, ldy, col_stride, col_off, M, N, Kd, relu, stream);
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, 1);
   dense_gemm_kernel<<<grid, 256, 0, stream>>>(X, ldx, xs, W, ldw, bias, Y, ldy, col_stride, col_off, M, N, Kd,
@@ -289,8 +293,7 @@ cudaError_t dense_pool(const float* A, const float* T, float* logits, int B, int
 }
 
 cudaError_t gram_launch(int B, int HW, int C, const float* X, float* G, cudaStream_t stream) {
-  static const bool force_simt = (getenv("APA_DENSE_SIMT") != nullptr);
-  if (!force_simt && C >= 64 && HW >= 16) return gram_tc(B, HW, C, X, G, stream);
+  if (!dense_force_simt() && C >= 64 && HW >= 16) return gram_tc(B, HW, C, X, G, stream);
   dim3 grid((C + TN - 1) / TN, (C + TM - 1) / TM, B);
   gram_kernel<<<grid, 256, 0, stream>>>(X, G, HW, C);
   return cudaGetLastError();

@@ -47,6 +47,18 @@ struct FusedParams {
   float* gpart;                       // workspace [B, lp, R, C]: per-row-slice partial g
   float* gstat;                       // workspace [B, lp, 8]: (s_r[4], running max) per row slice
   int lp;                             // row slices per image
+  // flow form (apa_pool_flow.cu)
+  unsigned long long* fl_ctr;         // control counters: [0] ticket [1] stream-done [2] slices-done
+  unsigned long long* fl_img;         // [B] per-image arrival counters (STREAM CTAs holding rows of the image)
+  unsigned long long* fl_arr;         // [video tiles * class slices] arrival counters of the CONTRACT units
+  float* gsum;                        // workspace [B][4]: attention mass per rank of the completed image
+  float* cpart;                       // workspace [tiles * class slices][8][32 videos][32 classes] partial logits
+  int fl_G, fl_NS;                    // STREAM CTAs, class slices
+  int inputs_stable;                  // X / weights may be read before the previous kernel in the stream completed
+  // fused all-gather, protocol v2 (flow form): explicit step, ring of gathered buffers
+  unsigned long long gw_step;         // this call's step (1, 2, ...)
+  size_t gw_slot_off;                 // float offset of this step's buffer inside every peer's gathered allocation
+  int gw_depth;                       // buffers in the ring
 };
 
 struct FusedPlan {
@@ -85,7 +97,19 @@ size_t split_stream_smem(int C);
 cudaError_t split_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream,
                          int* stream_grid, int* contract_grid);
 
+// ---- flow form (apa_pool_flow.cu): one launch, ticketed STREAM CTAs + CONTRACT CTAs
+constexpr int kFlowStreamCtas = 148;   // one STREAM CTA per SM of a B200
+bool flow_eligible(int B, int HW, int C, int K, int R, int F);
+int flow_stream_ctas(int B, int HW, const ApaTuning* tuning);
+int flow_class_slices(int K);
+size_t flow_gpart_slots(int B);                 // partial-g slots the workspace holds
+size_t flow_slices(int B, int K, int F);        // (video tile, class slice) pairs = arrival counters
+size_t flow_cpart_floats(int B, int K, int F);  // partial-logit floats the workspace holds
+size_t flow_smem(int C);
+cudaError_t flow_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out);
+
 // ---- dense path (apa_dense.cu)
+bool dense_force_simt();  // APA_DENSE_SIMT=1 in the environment (read once): A/B switch for tests and profiling
 // Y[m, col_off + n*col_stride] (row stride ldy) = act(sum_k X[m*ldx + k*xs] W[k,n] + bias[n])
 cudaError_t dense_gemm(const float* X, int ldx, int xs, const float* W, int ldw, const float* bias,
                        float* Y, int ldy, int col_stride, int col_off, int M, int N, int Kd, int relu,

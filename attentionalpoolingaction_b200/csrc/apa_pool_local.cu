@@ -545,8 +545,8 @@ bool local_eligible(int B, int HW, int C, int K, int R, int F) {
 }
 
 int local_shape(int B, int C, int R, int K, const ApaTuning* tuning) {
-  // reserved[1]: 4 / 5 / 6 force shape 0 / 1 / 2 (when the problem allows it); otherwise the widest that fits
-  const int force = tuning ? tuning->reserved[1] : 0;
+  // form 4 / 5 / 6 forces shape 0 / 1 / 2 (when the problem allows it); otherwise the widest that fits
+  const int force = tuning ? tuning->form : 0;
   if (R != 1 || force == 4) return 0;
   if (force == 5) return 1;
   if (B % 8 == 0 && (force == 6 || shape_smem(C, R, K, 2) <= kThreeSlotSmem)) return 2;

@@ -20,7 +20,7 @@ ROOT_PATH = os.path.dirname(cur_path)
 LIB_NAME = "libapa_attn_pool.so"
 LIB_PATH = os.path.join(ROOT_PATH, LIB_NAME)
 
-APA_ABI_VERSION = 1
+APA_ABI_VERSION = 2
 APA_MAX_RANK = 4
 APA_FLAG_SINGLE_LAYER_ATT = 1 << 0
 APA_FLAG_SOFTMAX_ATT = 1 << 1
@@ -92,8 +92,21 @@ class ApaTuning(ctypes.Structure):
         ("no_cooperative", ctypes.c_int32),
         ("no_pdl", ctypes.c_int32),
         ("debug_timestamps", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 2),
+        ("form", ctypes.c_int32),
+        ("pdl_trigger_lead", ctypes.c_int32),
+        ("inputs_stable", ctypes.c_int32),
+        ("gather_wait_lag", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 6),
     ]
+
+
+# ApaTuning.form (include/apa.h APA_FORM_*)
+APA_FORM_AUTO = 0
+APA_FORM_GRID_BARRIER = 1
+APA_FORM_LOCAL0, APA_FORM_LOCAL1, APA_FORM_LOCAL2 = 4, 5, 6
+APA_FORM_PIPELINE = 7
+APA_FORM_NO_PIPELINE = 8
+APA_FORM_FLOW = 9
 
 
 APA_MAX_PEERS = 8
@@ -203,10 +216,13 @@ def make_desc(batch, hw, channels, num_classes, frames=1, rank=1, flags=APA_FLAG
     return d
 
 
-def make_tuning(cluster_size=0, fused=-1, max_ctas=0, no_cooperative=0, no_pdl=0, debug_timestamps=0):
+def make_tuning(cluster_size=0, fused=-1, max_ctas=0, no_cooperative=0, no_pdl=0, debug_timestamps=0,
+                form=APA_FORM_AUTO, pdl_trigger_lead=0, inputs_stable=0, gather_wait_lag=0):
     t = ApaTuning()
     t.cluster_size, t.fused, t.max_ctas = int(cluster_size), int(fused), int(max_ctas)
     t.no_cooperative, t.no_pdl, t.debug_timestamps = int(no_cooperative), int(no_pdl), int(debug_timestamps)
+    t.form, t.pdl_trigger_lead = int(form), int(pdl_trigger_lead)
+    t.inputs_stable, t.gather_wait_lag = int(inputs_stable), int(gather_wait_lag)
     return t
 
 
@@ -226,7 +242,8 @@ def attn_pool_plan(desc, tuning=None, want_attn=False, want_topdown=False, want_
     if st != APA_OK:
         raise ApaError(st, "apa_attn_pool_plan")
     # cluster_local: 0 grid-barrier kernel, 1 cluster-local kernel, 2 STREAM + CONTRACT pipeline (then
-    # cluster_size = row slices per image, grid = STREAM grid, contract_grid = CONTRACT grid)
+    # cluster_size = row slices per image, grid = STREAM grid, contract_grid = CONTRACT grid), 3 flow form
+    # (grid = STREAM + CONTRACT CTAs of the one launch, contract_grid = its CONTRACT CTAs)
     keys = ("path", "cluster_size", "grid", "fused", "launches", "smem_bytes", "cluster_local", "contract_grid")
     return OrderedDict(zip(keys, list(out)[:8]))
 

@@ -242,8 +242,8 @@ def main():
     params = orc.make_params(K, C, flags=fl, seed=42)
     bits, rnk = ops.flags_from_cfg_net(fl)
     tuning = ops.make_tuning(args.cluster, args.fused, no_pdl=int(args.no_pdl), no_cooperative=int(args.no_coop))
-    tuning.reserved[0] = args.trigger_lead
-    tuning.reserved[1] = 1 if args.general else (7 if args.split else (0 if args.shape < 0 else 4 + args.shape))
+    tuning.pdl_trigger_lead = args.trigger_lead
+    tuning.form = 1 if args.general else (7 if args.split else (0 if args.shape < 0 else 4 + args.shape))
     nstreams = max(1, min(4, args.streams))
     # one op (= one workspace) per in-flight batch: consecutive steps are independent batches, so two
     # of them overlap on the GPU (one streams X from HBM while the other is in its latency-bound tail)

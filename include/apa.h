@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define APA_ABI_VERSION 1
+#define APA_ABI_VERSION 2
 #define APA_MAX_RANK 4
 
 /* cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION_* flags (src/config.py:182-209). */
@@ -101,19 +101,39 @@ typedef struct ApaWeights {
   const float* pose_logits_b;
 } ApaWeights;
 
+/* Which kernel form runs the single-map (M == 1) head.  AUTO picks by shape; the others exist for A/B
+ * measurements and tests (every form computes the same function).                                       */
+enum {
+  APA_FORM_AUTO         = 0,
+  APA_FORM_GRID_BARRIER = 1, /* one kernel, p-CTA clusters per image, one grid barrier (apa_pool_fused.cu)   */
+  APA_FORM_LOCAL0       = 4, /* 16-CTA cluster-local kernel, shapes 0/1/2 (apa_pool_local.cu)                */
+  APA_FORM_LOCAL1       = 5,
+  APA_FORM_LOCAL2       = 6,
+  APA_FORM_PIPELINE     = 7, /* STREAM kernel + cluster CONTRACT kernel (apa_pool_split.cu)                  */
+  APA_FORM_NO_PIPELINE  = 8,
+  APA_FORM_FLOW         = 9  /* one launch: ticketed STREAM CTAs + CONTRACT CTAs (apa_pool_flow.cu)          */
+};
+
 /* Launch/tuning knobs; pass NULL for defaults. Does not change results beyond fp32 rounding. */
 typedef struct ApaTuning {
-  int32_t cluster_size; /* CTAs per image in the streaming kernel: 0 = auto, else 1,2,4,8,16         */
-  int32_t fused;        /* 1 = one kernel with a grid barrier, 0 = two kernels, -1 = auto             */
-  int32_t max_ctas;     /* 0 = all SMs                                                                */
-  int32_t no_cooperative; /* 1 = never use the cooperative-launch attribute for the fused kernel      */
-  int32_t no_pdl;       /* 1 = do not launch the fused kernel as a programmatic dependent of the      */
-                        /*     previous kernel in the stream (back-to-back calls then do not overlap) */
-  int32_t debug_timestamps; /* 1 = fused kernel writes a per-CTA clock64 timeline at workspace+2048    */
-  int32_t reserved[2];  /* [0] PDL trigger lead in tiles (0 = default, <0 = at the end of the stream).      */
-                        /* [1] form of the single-map head, for A/B tests: 0 auto, 1 grid-barrier kernel,   */
-                        /*     2 inline peer wait (gather), 4/5/6 cluster-local shapes 0/1/2,               */
-                        /*     7 two-kernel STREAM + CONTRACT pipeline (cluster_size = row slices / image)  */
+  int32_t cluster_size; /* CTAs per image in the grid-barrier kernel / row slices in the pipeline: 0 = auto  */
+  int32_t fused;        /* grid-barrier kernel: 1 = one kernel, 0 = two kernels, -1 = auto                    */
+  int32_t max_ctas;     /* 0 = all SMs (flow form: number of STREAM CTAs)                                     */
+  int32_t no_cooperative; /* 1 = never use the cooperative-launch attribute for the grid-barrier kernel       */
+  int32_t no_pdl;       /* 1 = do not launch as a programmatic dependent of the previous kernel in the stream */
+                        /*     (back-to-back calls on one stream then do not overlap)                         */
+  int32_t debug_timestamps; /* 1 = kernels write a per-CTA clock64 timeline into the workspace               */
+  int32_t form;         /* APA_FORM_*                                                                         */
+  int32_t pdl_trigger_lead; /* cluster-local / pipeline forms: trigger the next launch this many tiles before */
+                        /*     a CTA's last tile (0 = at once, < 0 = at the end of the stream)                */
+  int32_t inputs_stable; /* 1 = the caller guarantees X and the weights were completely written before the    */
+                        /*     PREVIOUS kernel in `stream` was launched, so the head may read them before that */
+                        /*     kernel has finished (lets back-to-back calls on one stream overlap through      */
+                        /*     programmatic dependent launch).  0 (default) = wait for the previous kernel.    */
+  int32_t gather_wait_lag; /* apa_attn_pool_fwd_gather: after the call the gathered buffer of step             */
+                        /*     (step - lag) is complete in stream order; 0 = this step (strict), < 0 = do not  */
+                        /*     wait at all (call apa_peer_gather_wait before consuming)                        */
+  int32_t reserved[6];  /* must be 0                                                                          */
 } ApaTuning;
 
 /* Library/ABI version (APA_ABI_VERSION of the build). */

@@ -37,7 +37,7 @@ def main():
         row = []
         for fname, code in FORMS:
             tun = ops.make_tuning()
-            tun.reserved[1] = code
+            tun.form = code
             op = ops.AttnPoolOp(P, K, HW, channels=C, frames=F, rank=rank, flags=bits, tuning=tun, device=dev)
             plan = ops.attn_pool_plan(op.desc(B), tun)
             kind = {0: "grid-barrier", 1: "local", 2: "pipeline"}[plan["cluster_local"]]

@@ -18,8 +18,8 @@ def main():
     params = orc.make_params(K, C, flags=fl, seed=42)
     bits, rank = ops.flags_from_cfg_net(fl)
     tun = ops.make_tuning(cluster, fused, debug_timestamps=1, no_pdl=pieces, max_ctas=(int(sys.argv[6]) if len(sys.argv) > 6 else 0))
-    tun.reserved[0] = int(sys.argv[7]) if len(sys.argv) > 7 else 0
-    tun.reserved[1] = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+    tun.pdl_trigger_lead = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+    tun.form = int(sys.argv[8]) if len(sys.argv) > 8 else 0
     op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, rank=rank, flags=bits, tuning=tun)
     xs = [torch.relu(torch.randn((B, HW, C), device="cuda")) for _ in range(8)]
     for x in xs:

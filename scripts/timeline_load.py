@@ -22,8 +22,8 @@ def main():
     params = orc.make_params(K, C, flags=fl, seed=42)
     bits, rank = ops.flags_from_cfg_net(fl)
     tun = ops.make_tuning(debug_timestamps=1)
-    tun.reserved[0] = lead
-    tun.reserved[1] = 7 if shape == 7 else 4 + shape
+    tun.pdl_trigger_lead = lead
+    tun.form = 7 if shape == 7 else 4 + shape
     P = {k: torch.from_numpy(v) for k, v in params.items()}
     opl = [ops.AttnPoolOp(P, K, HW, rank=rank, flags=bits, tuning=tun) for _ in range(NOPS)]
     xs = [torch.relu(torch.randn((B, HW, C), device="cuda")) for _ in range(8)]

@@ -277,6 +277,21 @@ int main() {
   run<2, 4, 3, 2>(bufs, 128, 4, 0, 1, 1, L, "pair, 16 KB x 4, 3/SM");
   run<2, 4, 3, 2>(bufs, 148, 0, 1, 3, 1, L, "pair, 16 KB x 4, 3/SM, balanced, 3 lanes");
   run<2, 3, 3, 1>(bufs, 128, 4, 0, 3, 1, L, "16 KB x 3, 3/SM, 3 lanes");
+  // --- lanes without PDL, 4 lanes, 2 CTAs of a launch per SM
+  run<3, 3, 3, 1>(bufs, 148, 0, 1, 4, 1, L, "balanced 148, 4 lanes");
+  run<3, 3, 3, 1>(bufs, 148, 0, 1, 4, 0, L, "balanced 148, 4 lanes, no PDL");
+  run<3, 3, 3, 1>(bufs, 148, 0, 1, 2, 1, L, "balanced 148, 2 lanes");
+  run<3, 3, 3, 1>(bufs, 296, 0, 1, 2, 1, L, "balanced 296, 2 lanes");
+  run<3, 3, 3, 1>(bufs, 296, 0, 1, 4, 1, L, "balanced 296, 4 lanes");
+  run<4, 3, 2, 1>(bufs, 148, 0, 1, 4, 1, L, "32 KB x 3, 2/SM, balanced, 4 lanes");
+  run<4, 3, 2, 1>(bufs, 296, 0, 1, 2, 1, L, "32 KB x 3, 2/SM, balanced 296, 2 lanes");
+  run<3, 4, 2, 1>(bufs, 148, 0, 1, 1, 1, L, "24 KB x 4, 2/SM, balanced");
+  run<3, 4, 2, 1>(bufs, 148, 0, 1, 2, 1, L, "24 KB x 4, 2/SM, balanced, 2 lanes");
+  run<3, 4, 2, 1>(bufs, 148, 0, 1, 4, 1, L, "24 KB x 4, 2/SM, balanced, 4 lanes");
+  run<2, 6, 2, 1>(bufs, 148, 0, 1, 2, 1, L, "16 KB x 6, 2/SM, balanced, 2 lanes");
+  run<2, 6, 2, 1>(bufs, 148, 0, 1, 4, 1, L, "16 KB x 6, 2/SM, balanced, 4 lanes");
+  run<2, 4, 3, 1>(bufs, 148, 0, 1, 4, 1, L, "16 KB x 4, 3/SM, balanced, 4 lanes");
+  run<2, 4, 3, 1>(bufs, 296, 0, 1, 4, 1, L, "16 KB x 4, 3/SM, balanced 296, 4 lanes");
   cudaError_t err = cudaDeviceSynchronize();
   printf("done: %s\n", cudaGetErrorString(err));
   return err != cudaSuccess;

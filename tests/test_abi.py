@@ -108,7 +108,7 @@ def test_plan_without_device(B, frames, K, expect_cluster):
     assert pipe["cluster_size"] == 1 and pipe["grid"] == 320 and pipe["contract_grid"] == 16 * 11
     assert pipe["smem_bytes"] <= 76800
     t = ops.make_tuning()
-    t.reserved[1] = 1      # the grid-barrier kernel stays selectable
+    t.form = 1      # the grid-barrier kernel stays selectable
     assert ops.attn_pool_plan(ops.make_desc(320, 196, 2048, 600, frames=10), t)["cluster_local"] == 0
 
 
@@ -136,7 +136,7 @@ def test_dispatch_policy_without_device(kw, expect):
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     kw = dict(kw)
     t = ops.make_tuning()
-    t.reserved[1] = kw.pop("code", 0)
+    t.form = kw.pop("code", 0)
     d = ops.make_desc(kw.get("B"), 196, kw.get("C", 2048), kw.get("K", 393), frames=kw.get("F", 1), rank=kw.get("rank", 1))
     p = ops.attn_pool_plan(d, t)
     assert (p["cluster_local"], p["cluster_size"], p["grid"], p["launches"], p["smem_bytes"]) == expect

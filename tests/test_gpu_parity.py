@@ -69,7 +69,7 @@ def test_fused_path_parity(case):
     orc.assert_parity(got, ref, TOL)
     if F > 1:   # the default for several frames per video is the pipeline: cover the grid-barrier kernel too
         t = ops.make_tuning()
-        t.reserved[1] = 1
+        t.form = 1
         got, _, ref, _ = _run(B, HW, C, K, flags, F=F, tuning=t)
         orc.assert_parity(got, ref, TOL)
 
@@ -113,14 +113,14 @@ def test_cluster_local_kernel(case):
     orc.assert_parity(got, ref, TOL)
     # the general (grid-barrier) kernel on the same inputs agrees to fp32 rounding
     t = ops.make_tuning()
-    t.reserved[1] = 1
+    t.form = 1
     got2, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
     orc.assert_parity(got2, ref, TOL)
     assert np.abs(got - got2).max() <= 1e-5 * max(1e-30, np.abs(ref).max())
     # both ring shapes of the cluster-local kernel (4-row x 3-stage: 2 CTAs/SM, 3-row x 2-stage: 3 CTAs/SM)
     for force in (4, 5, 6):
         t = ops.make_tuning()
-        t.reserved[1] = force
+        t.form = force
         got3, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
         orc.assert_parity(got3, ref, TOL)
         got4, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
@@ -130,7 +130,7 @@ def test_cluster_local_kernel(case):
 def _split_tuning(lp=0, no_pdl=0):
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     t = ops.make_tuning(lp, -1, no_pdl=no_pdl)
-    t.reserved[1] = 7     # force the two-kernel STREAM + CONTRACT pipeline
+    t.form = 7     # force the two-kernel STREAM + CONTRACT pipeline
     return t
 
 
@@ -221,7 +221,7 @@ def test_fused_gather_single_rank(B, general):
     fl, params, X = _setup(B, 196, 2048, 393, SINGLE, seed=17)
     bits, rank = ops.flags_from_cfg_net(fl)
     t = ops.make_tuning()
-    t.reserved[1] = general
+    t.form = general
     op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 393, 196, rank=rank, flags=bits,
                         tuning=t, device="cuda:0")
     pg = apa_dist.PeerGather(B, 393, torch.device("cuda:0"))

@@ -285,7 +285,8 @@ int apa_attn_pool_fwd_gather(const ApaDesc* d, const float* X, const ApaWeights*
                              void* workspace, size_t workspace_bytes, const ApaTuning* tuning, void* stream_) {
   if (gw == nullptr) return APA_ERR_NULL;
   if (gw->world < 1 || gw->world > APA_MAX_PEERS || gw->rank < 0 || gw->rank >= gw->world) return APA_ERR_SHAPE;
-  if (gw->done_counter == nullptr) return APA_ERR_NULL;
+  if (gw->depth < 1 || gw->depth > 4 || gw->reserved0 != 0) return APA_ERR_SHAPE;
+  if (gw->counters == nullptr) return APA_ERR_NULL;
   for (int q = 0; q < gw->world; ++q)
     if (gw->peer_logits[q] == nullptr || gw->peer_flags[q] == nullptr) return APA_ERR_NULL;
   int st = check_desc(d);
@@ -381,10 +382,8 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
         p.gw_logits[q] = gw->peer_logits[q];
         p.gw_flags[q] = gw->peer_flags[q];
       }
-      p.gw_done = gw->done_counter;
-      // world > 1: the waiting for the peers' flags is done by a 1-warp kernel queued behind this launch, so
-      // no CTA of the head kernel sits on an SM (and a cluster slot) while NVLink round trips complete
-      p.gw_inline_wait = (gw->world == 1) ? 1 : 0;
+      p.gw_done = gw->counters;
+      p.gw_depth = gw->depth;
     }
     p.attn_raw = attn_out ? wsf(c.attn_raw) : nullptr;
     p.g = wsf(c.g);
@@ -400,7 +399,10 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
     // small batches: the cluster-local kernel (no grid barrier, g never leaves shared memory)
     bool launched = false;
     int grid = fused_grid(plan);
-    if (gw == nullptr && use_flow(d, tuning)) {
+    // the fused all-gather prefers the flow form (its flow control lives in the kernel) unless another form is forced
+    const bool flow_gather = gw != nullptr && (tuning == nullptr || tuning->form == APA_FORM_AUTO) &&
+                             flow_eligible(B, HW, C, K, R, F);
+    if (flow_gather || use_flow(d, tuning)) {
       p.gpart = wsf(c.gpart);
       p.gstat = wsf(c.gstat);
       p.cpart = wsf(c.cpart);
@@ -411,6 +413,7 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
       APA_CUDA(flow_launch(p, mode, tuning, stream, &grid));
       launched = true;
     }
+    if (!launched && gw != nullptr) APA_CUDA(peer_gather_begin_launch(gw, stream));  // flow control for the other forms
     if (!launched && use_split(d, tuning)) {
       p.gpart = wsf(c.gpart);
       p.gstat = wsf(c.gstat);
@@ -425,9 +428,11 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
       else { (void)cudaGetLastError(); grid = fused_grid(plan); }  // e.g. 16-CTA clusters not launchable here
     }
     if (!launched) APA_CUDA(fused_launch(p, plan, stream));
-    if (gw != nullptr && !p.gw_inline_wait)
-      APA_CUDA(peer_gather_wait_launch(gw->world, gw->rank, gw->peer_flags, gw->done_counter, unsigned(grid),
-                                       !(tuning && tuning->no_pdl), stream));
+    if (gw != nullptr) {
+      // completeness: by default this call's step; lag >= 1 pipelines the consumer behind the producers
+      const int lag = tuning ? tuning->gather_wait_lag : 0;
+      if (lag >= 0) APA_CUDA(peer_gather_wait_launch(gw, lag, !(tuning && tuning->no_pdl), stream));
+    }
     if (attn_out)
       APA_CUDA(attn_finalize_m1(p.attn_raw, w->attn_w, w->attn_b, p.smx, attn_out, B, HW, R, mode, stream));
     return APA_OK;
@@ -470,6 +475,18 @@ int apa_attn_pool_fwd_host(const ApaDesc* d, const float* X_host, const ApaWeigh
   if (st != APA_OK) return st;
   APA_CUDA(cudaMemcpyAsync(logits_host, logits_staging, lbytes, cudaMemcpyDeviceToHost, stream));
   APA_CUDA(cudaStreamSynchronize(stream));
+  return APA_OK;
+}
+
+int apa_peer_gather_wait(const ApaPeerGather* gw, int32_t lag, void* stream) {
+  if (gw == nullptr || gw->counters == nullptr) return APA_ERR_NULL;
+  if (lag < 0) return APA_ERR_SHAPE;
+  if (gw->world < 1 || gw->world > APA_MAX_PEERS || gw->rank < 0 || gw->rank >= gw->world) return APA_ERR_SHAPE;
+  for (int q = 0; q < gw->world; ++q)
+    if (gw->peer_flags[q] == nullptr) return APA_ERR_NULL;
+  int st = check_device();
+  if (st != APA_OK) return st;
+  APA_CUDA(peer_gather_wait_launch(gw, lag, false, static_cast<cudaStream_t>(stream)));
   return APA_OK;
 }
 

@@ -168,33 +168,9 @@ __device__ __forceinline__ void griddep_launch_dependents() {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- fused all-gather (peer stores)
-// Called by ONE thread per CTA after that CTA's logits stores (and a CTA-level barrier).  The last CTA of the
-// launch to get here publishes step flags to every peer and waits for every peer's flag of the same step.
-__device__ __forceinline__ void peer_gather_finish(int world, int rank, unsigned long long* const* flags,
-                                                   unsigned long long* done, unsigned int nblocks,
-                                                   bool wait_for_peers) {
-  __threadfence_system();  // this CTA's peer stores are globally visible before it is counted
-  unsigned long long prev;
-  asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], 1;" : "=l"(prev) : "l"(done) : "memory");
-  if ((prev + 1) % nblocks != 0) return;
-  const unsigned long long step = (prev + 1) / nblocks;
-  for (int q = 0; q < world; ++q)
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[q] + rank), "l"(step) : "memory");
-  if (!wait_for_peers) return;  // a 1-warp kernel right behind this launch does the waiting (peer_gather_wait_kernel)
-  const long long t0 = clock64();
-  for (int r = 0; r < world; ++r) {
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags[rank] + r) : "memory");
-      if (v >= step) break;
-      if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
-    } while (true);
-  }
-}
-
-// Protocol v2 (flow form).  flags[q] is rank q's flag array of 2 * world words: word r = the last step whose
-// logits rank r has completely stored into q's gathered ring; word world + r = the last step rank r has
-// STARTED after everything before it in r's stream completed (= r has consumed every older gathered buffer).
+// flags[q] is rank q's flag array of 2 * world words: word r = the last step whose logits rank r has completely
+// stored into q's gathered ring; word world + r = the last step rank r has STARTED after everything before it in
+// r's stream completed (= r has consumed every gathered buffer it had to, see include/apa.h).
 __device__ __forceinline__ void peer_gather_publish(int world, int rank, unsigned long long* const* flags,
                                                     unsigned long long step) {
   for (int q = 0; q < world; ++q)
@@ -218,6 +194,34 @@ __device__ __forceinline__ void peer_gather_wait_all(int world, const unsigned l
       if (clock64() - t0 > APA_PEER_TIMEOUT_CYCLES) __trap();
     } while (true);
   }
+}
+
+// The step of the gather call a kernel belongs to: calls completed so far + 1.  Only valid after the kernel's
+// griddepcontrol.wait (the previous call, which bumps the count at its very end, has then completed).
+__device__ __forceinline__ unsigned long long peer_gather_step(const unsigned long long* counters) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counters + 1) : "memory");
+  return v + 1;
+}
+// The launch's very last act (one thread, after every logits store of the launch is ordered before it).
+__device__ __forceinline__ void peer_gather_complete(int world, int rank, unsigned long long* const* flags,
+                                                     unsigned long long* counters, unsigned long long step) {
+  peer_gather_publish(world, rank, flags, step);
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(counters + 1), "l"(step) : "memory");
+}
+// Older forms (grid-barrier / cluster-local / pipeline): called by ONE thread per CTA after that CTA's logits
+// stores (and a CTA-level barrier).  counters[0] only ever grows and every launch leaves it at a multiple of 2^20,
+// so the grid may change between calls; the last CTA of the launch to get here completes the step.
+__device__ __forceinline__ void peer_gather_finish(int world, int rank, unsigned long long* const* flags,
+                                                   unsigned long long* counters, unsigned int nblocks,
+                                                   unsigned long long step) {
+  if (world > 1) __threadfence_system();  // this CTA's peer stores are globally visible before it is counted
+  unsigned long long prev;
+  asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], 1;" : "=l"(prev) : "l"(counters) : "memory");
+  if ((prev & ((1ull << 20) - 1)) != (unsigned long long)(nblocks - 1)) return;
+  const unsigned long long pad = (1ull << 20) - nblocks;
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(counters), "l"(pad) : "memory");
+  peer_gather_complete(world, rank, flags, counters, step);
 }
 
 // ----------------------------------------------------------------------------- misc

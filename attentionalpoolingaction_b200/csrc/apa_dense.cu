@@ -195,41 +195,49 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
     }
 }
 
-// Waits (one thread) until the step flags of all `world` ranks have reached this rank's own step, i.e. until
-// every peer's block of the gathered logits has landed here.  Launched as a programmatic dependent of the
-// gather kernel: triggers its own dependents at once (the next head launch may start streaming), then waits
-// for the gather kernel to finish before reading the step counter.
-struct PeerWaitParams {
+// ---- 1-warp kernels of the fused all-gather protocol (apa_common.cuh, include/apa.h)
+struct PeerParams {
   unsigned long long* flags[APA_MAX_PEERS];
-  unsigned long long* done;
-  unsigned int nblocks;
-  int world, rank;
+  unsigned long long* counters;
+  int world, rank, depth, lag;
 };
-__global__ void peer_gather_wait_kernel(const PeerWaitParams w) {
+// Waits (one thread) until the data flags of all `world` ranks in MY flag array have reached (latest step - lag).
+// Launched as a programmatic dependent of the head kernel: triggers its own dependents at once (the next head
+// launch may start streaming), then waits for the head kernel to finish (stream order) before reading the count.
+__global__ void peer_gather_wait_kernel(const PeerParams w) {
   griddep_launch_dependents();
   griddep_wait();
   if (threadIdx.x != 0) return;
-  unsigned long long d;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(d) : "l"(w.done) : "memory");
-  const unsigned long long step = d / w.nblocks;
-  const long long t0 = clock64();
-  for (int r = 0; r < w.world; ++r) {
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.flags[w.rank] + r) : "memory");
-      if (v >= step) break;
-      if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
-    } while (true);
-  }
+  const unsigned long long latest = peer_gather_step(w.counters) - 1;   // calls completed on this rank
+  if (latest > (unsigned long long)w.lag) peer_gather_wait_all(w.world, w.flags[w.rank], 0, latest - w.lag);
+}
+// Everything before this kernel in the stream has completed: tell every peer that this rank has started `step`
+// (it no longer reads the buffers it had to consume before this call), then wait until this step's ring buffer
+// is free on every peer.
+__global__ void peer_gather_begin_kernel(const PeerParams w) {
+  if (threadIdx.x != 0) return;
+  const unsigned long long step = peer_gather_step(w.counters);
+  peer_gather_publish_started(w.world, w.rank, w.flags, step);
+  if (step >= (unsigned long long)w.depth) peer_gather_wait_all(w.world, w.flags[w.rank], w.world, step - w.depth + 1);
+}
+
+PeerParams peer_params(const ApaPeerGather* gw, int lag) {
+  PeerParams w;
+  for (int q = 0; q < APA_MAX_PEERS; ++q) w.flags[q] = q < gw->world ? gw->peer_flags[q] : nullptr;
+  w.counters = gw->counters;
+  w.world = gw->world; w.rank = gw->rank; w.depth = gw->depth; w.lag = lag;
+  return w;
 }
 
 }  // namespace
 
-cudaError_t peer_gather_wait_launch(int world, int rank, unsigned long long* const* flags, unsigned long long* done,
-                                    unsigned int nblocks, bool pdl, cudaStream_t stream) {
-  PeerWaitParams w;
-  for (int q = 0; q < APA_MAX_PEERS; ++q) w.flags[q] = q < world ? flags[q] : nullptr;
-  w.done = done; w.nblocks = nblocks; w.world = world; w.rank = rank;
+cudaError_t peer_gather_begin_launch(const ApaPeerGather* gw, cudaStream_t stream) {
+  peer_gather_begin_kernel<<<1, 32, 0, stream>>>(peer_params(gw, 0));
+  return cudaGetLastError();
+}
+
+cudaError_t peer_gather_wait_launch(const ApaPeerGather* gw, int lag, bool pdl, cudaStream_t stream) {
+  const PeerParams w = peer_params(gw, lag);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(1, 1, 1);
   cfg.blockDim = dim3(32, 1, 1);

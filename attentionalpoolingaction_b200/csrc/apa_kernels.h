@@ -42,7 +42,6 @@ struct FusedParams {
   float* gw_logits[APA_MAX_PEERS];
   unsigned long long* gw_flags[APA_MAX_PEERS];
   unsigned long long* gw_done;
-  int gw_inline_wait;                 // 1: the last CTA itself waits for the peers' step flags
   // two-kernel pipeline (apa_pool_split.cu)
   float* gpart;                       // workspace [B, lp, R, C]: per-row-slice partial g
   float* gstat;                       // workspace [B, lp, 8]: (s_r[4], running max) per row slice
@@ -55,10 +54,7 @@ struct FusedParams {
   float* cpart;                       // workspace [tiles * class slices][8][32 videos][32 classes] partial logits
   int fl_G, fl_NS;                    // STREAM CTAs, class slices
   int inputs_stable;                  // X / weights may be read before the previous kernel in the stream completed
-  // fused all-gather, protocol v2 (flow form): explicit step, ring of gathered buffers
-  unsigned long long gw_step;         // this call's step (1, 2, ...)
-  size_t gw_slot_off;                 // float offset of this step's buffer inside every peer's gathered allocation
-  int gw_depth;                       // buffers in the ring
+  int gw_depth;                       // buffers in every rank's gathered ring (call `step` lands in step % depth)
 };
 
 struct FusedPlan {
@@ -133,9 +129,12 @@ cudaError_t dense_relu(float* A, size_t n, cudaStream_t stream);
 // logits[v,k] = 1/(HW F) sum_f sum_hw sum_r A[b,hw,m(k),r] T[b,hw,k,r]
 cudaError_t dense_pool(const float* A, const float* T, float* logits, int B, int HW, int K, int M,
                        int R, int F, cudaStream_t stream);
-// 1-warp kernel queued right behind a gather launch: waits until every peer's flag reached this rank's step
-cudaError_t peer_gather_wait_launch(int world, int rank, unsigned long long* const* flags, unsigned long long* done,
-                                    unsigned int nblocks, bool pdl, cudaStream_t stream);
+// 1-warp kernels of the fused all-gather (include/apa.h ApaPeerGather):
+//   begin  (forms without in-kernel flow control) publishes "rank started `step`" to every peer and waits until every
+//          peer has started step - depth + 1, i.e. until this step's ring buffer may be overwritten everywhere
+//   wait   waits until every rank's data flag in MY flag array has reached `target`
+cudaError_t peer_gather_begin_launch(const ApaPeerGather* gw, cudaStream_t stream);
+cudaError_t peer_gather_wait_launch(const ApaPeerGather* gw, int lag, bool pdl, cudaStream_t stream);
 cudaError_t gram_launch(int B, int HW, int C, const float* X, float* G, cudaStream_t stream);
 
 }  // namespace apa

@@ -296,6 +296,9 @@ apa_flow_kernel(const FusedParams p) {
         if (tid == 0 && p.ts != nullptr && t < 320) p.ts[size_t(t) * 64 + 2] = clock64();
         griddep_wait();
         waited = true;
+        // everything before this call in the stream is complete: this rank no longer reads older gathered buffers
+        if (t == 0 && tid == 0 && p.gw_world > 0)
+          peer_gather_publish_started(p.gw_world, p.gw_rank, p.gw_flags, peer_gather_step(p.gw_done));
       }
       int e_lo, e_hi;                                  // STREAM CTAs holding rows of image b
       flow_image_ctas(N, G, HW, b, &e_lo, &e_hi);
@@ -573,6 +576,17 @@ apa_flow_kernel(const FusedParams p) {
       for (int c = 1; c < kNJ; ++c) { sum[0] += pv[c].x; sum[1] += pv[c].y; sum[2] += pv[c].z; sum[3] += pv[c].w; }
       const int vi = (tid * 4) / kKW, kk0 = (tid * 4) % kKW;
       const int v = v0 + vi;
+      size_t gw_off = 0;
+      if (p.gw_world > 0) {  // this step's ring buffer must be free on every peer (they started step - depth + 1)
+        if (tid == 0) {
+          const unsigned long long step = peer_gather_step(p.gw_done);
+          if (p.gw_world > 1 && step >= (unsigned long long)p.gw_depth)
+            peer_gather_wait_all(p.gw_world, p.gw_flags[p.gw_rank], p.gw_world, step - p.gw_depth + 1);
+          *tick_s = step;
+        }
+        named_bar_sync(1, kConsumerThreads);
+        gw_off = size_t(*tick_s % (unsigned long long)p.gw_depth) * size_t(p.gw_world) * Bv * K;
+      }
       if (v < Bv) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
@@ -582,7 +596,7 @@ apa_flow_kernel(const FusedParams p) {
             for (int j = 0; j < R; ++j) val = fmaf(__ldg(p.td_b[j] + k), sS[vi * 4 + j], val);
             val *= p.inv_scale;
             if (p.gw_world > 0) {
-              const size_t off = p.gw_slot_off + (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
+              const size_t off = gw_off + (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
               for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
             } else {
               p.logits[size_t(v) * K + k] = val;
@@ -599,7 +613,7 @@ apa_flow_kernel(const FusedParams p) {
           // the launch's last logits are stored: pad the two per-launch counters to the next multiple
           (void)atom_add_relaxed(ctr + 2, kStride - nslices);
           (void)atom_add_acq_rel(ctr + 1, kStride - (unsigned long long)G);
-          if (p.gw_world > 0) peer_gather_publish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_step);
+          if (p.gw_world > 0) peer_gather_complete(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, *tick_s);
         }
       }
     }

@@ -467,7 +467,7 @@ apa_pool_local_kernel(const FusedParams p) {
         }
         const float val = sum * p.inv_scale;
         if (p.gw_world > 0) {
-          const size_t off = (size_t(p.gw_rank) * p.B + size_t(g * LI + i)) * K + k;
+          const size_t off = (peer_gather_step(p.gw_done) % p.gw_depth) * size_t(p.gw_world) * p.B * p.K + (size_t(p.gw_rank) * p.B + size_t(g * LI + i)) * K + k;
           for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
         } else {
           p.logits[size_t(g * LI + i) * K + k] = val;
@@ -480,7 +480,7 @@ apa_pool_local_kernel(const FusedParams p) {
     }
   }
   named_bar_sync(1, kConsumerThreads);  // this CTA's logits stores precede the gather bookkeeping below
-  if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x, p.gw_inline_wait != 0);
+  if (p.gw_world > 0 && tid == 0) peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x, peer_gather_step(p.gw_done));
   if (tid == 0) {
     lts_mark(p.ts, 5);
     if (p.ts) p.ts[size_t(blockIdx.x) * 64 + 63] = lglobaltimer_ns();

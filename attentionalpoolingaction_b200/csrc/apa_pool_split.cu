@@ -454,7 +454,7 @@ apa_contract_kernel(const FusedParams p) {
         for (int j = 0; j < R; ++j) sum = fmaf(__ldg(p.td_b[j] + k), sS[vi * 4 + j], sum);
         const float val = sum * p.inv_scale;
         if (p.gw_world > 0) {
-          const size_t off = (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
+          const size_t off = (peer_gather_step(p.gw_done) % p.gw_depth) * size_t(p.gw_world) * Bv * p.K + (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
           for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
         } else {
           p.logits[size_t(v) * K + k] = val;
@@ -465,7 +465,7 @@ apa_contract_kernel(const FusedParams p) {
   }
   __syncthreads();  // this CTA's logits stores precede the gather bookkeeping below
   if (p.gw_world > 0 && tid == 0)
-    peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x, p.gw_inline_wait != 0);
+    peer_gather_finish(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, gridDim.x, peer_gather_step(p.gw_done));
   if (tid == 0) {
     sts_mark(p.ts, ts_row, 5);
     if (p.ts && ts_row < 320) p.ts[size_t(ts_row) * 64 + 63] = sglobaltimer_ns();

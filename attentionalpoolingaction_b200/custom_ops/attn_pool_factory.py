@@ -47,6 +47,7 @@ ABI_SYMBOLS = (
     "apa_attn_pool_fwd",
     "apa_attn_pool_fwd_host",
     "apa_attn_pool_fwd_gather",
+    "apa_peer_gather_wait",
     "apa_gram_fwd",
     "apa_attn_pool_plan",
 )
@@ -116,9 +117,11 @@ class ApaPeerGather(ctypes.Structure):
     _fields_ = [
         ("world", ctypes.c_int32),
         ("rank", ctypes.c_int32),
+        ("depth", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
         ("peer_logits", ctypes.c_void_p * APA_MAX_PEERS),
         ("peer_flags", ctypes.c_void_p * APA_MAX_PEERS),
-        ("done_counter", ctypes.c_void_p),
+        ("counters", ctypes.c_void_p),
     ]
 
 
@@ -158,6 +161,8 @@ def _load():
     lib.apa_attn_pool_fwd_gather.argtypes = [c.POINTER(ApaDesc), c.c_void_p, c.POINTER(ApaWeights),
                                              c.POINTER(ApaPeerGather), c.c_void_p, c.c_size_t,
                                              c.POINTER(ApaTuning), c.c_void_p]
+    lib.apa_peer_gather_wait.restype = c.c_int
+    lib.apa_peer_gather_wait.argtypes = [c.POINTER(ApaPeerGather), c.c_int32, c.c_void_p]
     lib.apa_gram_fwd.restype = c.c_int
     lib.apa_gram_fwd.argtypes = [c.c_int32, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.apa_attn_pool_plan.restype = c.c_int
@@ -378,8 +383,13 @@ class AttnPoolOp(object):
 
     def forward_gather(self, X, gather):
         """Batch-sharded multi-GPU call: this rank's logits are stored straight into every peer's gathered
-        buffer by the kernel (`gather` is an ApaPeerGather, see attentionalpoolingaction_b200.dist.PeerGather)."""
+        ring by the kernel.  `gather` is a dist.PeerGather (its host-side mirror of the device step counter is
+        advanced here; returns the step of this call) or a filled-in ApaPeerGather."""
         torch = self._torch
+        step = None
+        if hasattr(gather, "next_step"):
+            step = gather.next_step()
+            gather = gather.struct
         if X.dim() == 4:
             X = X.reshape(X.shape[0], X.shape[1] * X.shape[2], X.shape[3])
         X = X.contiguous()
@@ -391,6 +401,7 @@ class AttnPoolOp(object):
                                            ctypes.c_void_p(stream))
         if st != APA_OK:
             raise ApaError(st, "apa_attn_pool_fwd_gather")
+        return step
 
     def forward_host(self, X_host, logits_host=None):
         """Plugin-style call with HOST buffers (pinned for speed): H2D copy, head, D2H copy, sync."""
@@ -423,6 +434,13 @@ class AttnPoolOp(object):
         return logits_host
 
 
+def peer_gather_wait(gather_struct, lag, stream):
+    """Enqueue a wait on `stream` until every rank's block of call (latest - lag) has landed in this rank's ring."""
+    st = _lib.apa_peer_gather_wait(ctypes.byref(gather_struct), int(lag), ctypes.c_void_p(stream))
+    if st != APA_OK:
+        raise ApaError(st, "apa_peer_gather_wait")
+
+
 def attn_pool(X, params, num_classes, flags=APA_FLAG_SINGLE_LAYER_ATT, rank=1, frames=1, **kwargs):
     """Functional form, like the reference's `pose_to_heatmap(*args, **kwargs)` wrappers: builds the op
     for this call's shapes and runs it.  Prefer AttnPoolOp for repeated calls."""
@@ -433,14 +451,16 @@ def attn_pool(X, params, num_classes, flags=APA_FLAG_SINGLE_LAYER_ATT, rank=1, f
     return op(X, **want)
 
 
-def gram(X):
+def gram(X, out=None):
     """Full second-order pooling G[b] = X[b]^T X[b] (paper; not in the reference code)."""
     import torch
     if X.dim() == 4:
         X = X.reshape(X.shape[0], X.shape[1] * X.shape[2], X.shape[3])
     X = X.contiguous()
     B, HW, C = X.shape
-    G = torch.empty((B, C, C), dtype=torch.float32, device=X.device)
+    G = out if out is not None else torch.empty((B, C, C), dtype=torch.float32, device=X.device)
+    if tuple(G.shape) != (B, C, C) or G.dtype != torch.float32 or not G.is_contiguous():
+        raise ValueError("out must be a contiguous float32 [B, C, C] tensor")
     st = _lib.apa_gram_fwd(B, HW, C, _ptr(X), _ptr(G),
                            ctypes.c_void_p(torch.cuda.current_stream(X.device).cuda_stream))
     if st != APA_OK:

@@ -74,15 +74,28 @@ class ShardedHead(object):
 
 
 class PeerGather(object):
-    """The all-gather of the logits fused into the kernel: a symmetric [world * b, K] buffer on every rank;
-    each rank's kernel stores its block into every peer's buffer over NVLink and signals a step flag
-    (include/apa.h: ApaPeerGather).  Built on torch.distributed symmetric memory for the peer mappings only.
-    `world == 1` (no process group) degenerates to a local buffer, which is how single-GPU tests cover it."""
+    """The all-gather of the logits fused into the kernel: a symmetric ring of `depth` gathered buffers
+    [depth, world * b, K] on every rank; each rank's kernel stores its block of call `step` into buffer
+    step % depth on every peer over NVLink and signals flags (include/apa.h: ApaPeerGather).  Built on
+    torch.distributed symmetric memory for the peer mappings only.  `world == 1` (no process group) degenerates
+    to a local ring, which is how single-GPU tests cover it.
 
-    def __init__(self, videos_per_rank, num_classes, device, group=None):
+        step = op.forward_gather(X, pg)      # with ApaTuning.gather_wait_lag = L the buffer of step - L is
+        pg.buffer(step - L)                  #   complete in stream order after the call
+        pg.wait(0); pg.buffer(step)          # or wait explicitly for the newest one
+    The step is counted on the device (CUDA-graph replays keep counting); `pg.step` mirrors it on the host for
+    eager calls, `pg.sync_step()` re-reads it after graph replays.
+    """
+
+    def __init__(self, videos_per_rank, num_classes, device, group=None, depth=1):
         import torch
         from .custom_ops import attn_pool_factory as ops
         self.rank, self.world = 0, 1
+        self.depth = int(depth)
+        if not (1 <= self.depth <= 4):
+            raise ValueError("depth must be in 1..4")
+        self.step = 0
+        self.rows = int(videos_per_rank)
         self._keep = []
         use_dist = False
         try:
@@ -98,12 +111,13 @@ class PeerGather(object):
             self.rank, self.world = dist.get_rank(grp), dist.get_world_size(grp)
             if self.world > ops.APA_MAX_PEERS:
                 raise ValueError("at most %d ranks" % ops.APA_MAX_PEERS)
-            self.out = symm_mem.empty((self.world * videos_per_rank, num_classes), dtype=torch.float32, device=device)
+            self.ring = symm_mem.empty((self.depth, self.world * videos_per_rank, num_classes), dtype=torch.float32,
+                                       device=device)
             self.flags = symm_mem.empty((64,), dtype=torch.int64, device=device)
-            self.out.zero_()
+            self.ring.zero_()
             self.flags.zero_()
             torch.cuda.synchronize(device)
-            h_out = symm_mem.rendezvous(self.out, grp)
+            h_out = symm_mem.rendezvous(self.ring, grp)
             h_flags = symm_mem.rendezvous(self.flags, grp)
             self._keep += [h_out, h_flags]
             for q in range(self.world):
@@ -111,11 +125,38 @@ class PeerGather(object):
                 g.peer_flags[q] = int(h_flags.buffer_ptrs[q])
             dist.barrier(grp)
         else:
-            self.out = torch.zeros((videos_per_rank, num_classes), dtype=torch.float32, device=device)
+            self.ring = torch.zeros((self.depth, videos_per_rank, num_classes), dtype=torch.float32, device=device)
             self.flags = torch.zeros((64,), dtype=torch.int64, device=device)
-            g.peer_logits[0] = self.out.data_ptr()
+            g.peer_logits[0] = self.ring.data_ptr()
             g.peer_flags[0] = self.flags.data_ptr()
         self.done = torch.zeros((8,), dtype=torch.int64, device=device)
-        g.world, g.rank = self.world, self.rank
-        g.done_counter = self.done.data_ptr()
+        g.world, g.rank, g.depth = self.world, self.rank, self.depth
+        g.counters = self.done.data_ptr()
         self.struct = g
+        self.device = device
+
+    def next_step(self):
+        self.step += 1
+        return self.step
+
+    def sync_step(self):
+        """Re-read the device-side count of completed calls (after CUDA-graph replays); synchronises."""
+        self.step = int(self.done[1].item())
+        return self.step
+
+    def buffer(self, step):
+        """The gathered [world * b, K] logits of call `step` (valid once that step is complete, see class doc)."""
+        return self.ring[int(step) % self.depth]
+
+    @property
+    def out(self):
+        """The gathered logits of the most recent call."""
+        return self.buffer(self.step)
+
+    def wait(self, lag=0, stream=None):
+        """Enqueue a wait until the gathered buffer of call (latest - lag) is complete on this rank."""
+        import torch
+        from .custom_ops import attn_pool_factory as ops
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        ops.peer_gather_wait(self.struct, lag, stream)

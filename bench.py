@@ -1,28 +1,34 @@
 #!/usr/bin/env python
 """bench.py — images/s through the attentional-pooling head on synthetic conv5 features.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A *step* is one pass of the hot path over one batch: BASELINE.json configs[1] — rank-1
-attentional pooling, 32 feature maps of 14x14x2048 fp32 per GPU, K=393 — ONE kernel launch; at N>1
-the single all-gather of the [32,393] logits is fused into that kernel (NVLink peer stores + step
-flags, `--collective nccl` for a NCCL all_gather instead).  Consecutive steps are independent batches:
-four are kept in flight (`--streams 4`, each lane with its own workspace) and back-to-back launches on
-a lane overlap through programmatic dependent launch.  Weak scaling: every rank owns 32 images per step.  Prints ONE JSON line on rank 0 (contract in the task statement):
+A *step* is one pass of the hot path over one batch per GPU (weak scaling: every rank owns the same batch).
+`--config` indexes BASELINE.json `configs` (default 1, the configuration the metric is quoted on):
+  1  rank-1 attn pool, 14x14x2048, K=393, batch 32 per GPU                     HBM-bound   (one kernel launch)
+  2  config-003 flags + RANK=2 (chained attention), batch 128 per GPU          tensor-bound (pose GEMM on tcgen05)
+  3  HICO K=600, 10-crop: 32 videos x 10 crop maps = 320 maps per GPU          HBM-bound
+  4  full second-order X^T X, 28x28x2048, 64 images per GPU, outputs local     tensor-bound
+At N>1 the single all-gather of the logits is fused into the head kernel (NVLink peer stores into a ring of
+gathered buffers + step flags; the consumer is pipelined `--gather-lag` steps behind, `--collective nccl` for a NCCL
+all_gather per step instead).  Consecutive steps are independent batches: `--streams` of them are kept in flight
+(each lane its own workspace) and back-to-back launches on a lane overlap through programmatic dependent launch
+(the inputs are resident in HBM before the timed region, ApaTuning.inputs_stable).  Prints ONE JSON line on rank 0:
   value        whole-job images/s with X resident in HBM (CUDA events, max over ranks)
-  e2e          same metric through the C-ABI host-buffer entry (apa_attn_pool_fwd_host): pinned
-               host X -> device, head, logits -> host, inside the timed region
-  roofline     fused kernel alone: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
-  cpu_baseline the oracle's PyTorch-CPU fp32 direct-form port timed on this box's host cores
-L2 hygiene: the inputs rotate over a ring of X buffers larger than 2x L2, so every step reads
-X from HBM.  `--impl reference` times the CPU port (TF-1.1 itself cannot be installed).
+  e2e          same metric through the C-ABI host-buffer entry (apa_attn_pool_fwd_host): pinned host X -> device,
+               head, logits -> host, inside the timed region (PCIe-bound: e2e.roofline compares it with a bare copy)
+  roofline     the head kernel alone: algorithmic bytes (or flops) / CUDA-event duration vs MEASURED_PEAKS.json
+  latency_us   one cold launch alone (config 1: batch 32 and batch 1), see `latency_us.method`
+  cpu_baseline the oracle's PyTorch-CPU fp32 direct-form port timed on this box's host cores (rank 0, N=1 only)
+L2 hygiene: the inputs rotate over a ring of X buffers larger than 2x L2, so every step reads X from HBM.
+`--impl reference` times the CPU port with the same thread sweep (TF-1.1 itself cannot be installed).
 """
 from __future__ import annotations
 
 import argparse
-import math
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -33,22 +39,44 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-B_PER_GPU, HW, C, K = 32, 196, 2048, 393
-FLAGS = {"SINGLE_LAYER_ATT": True}
-X_BYTES = B_PER_GPU * HW * C * 4
-W_BYTES = (C + 1) * (K + 1) * 4
-OUT_BYTES = B_PER_GPU * K * 4
-ALGO_BYTES = X_BYTES + W_BYTES + OUT_BYTES  # 54.66 MB per launch
+HW14, HW28, C = 196, 784, 2048
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "imgs/sec attn-pool 14x14x2048->393 logits"
+
+# BASELINE.json configs[i] -> workload.  B = feature maps per GPU per step, F = maps (frames / crops) per image.
+CONFIGS = {
+    1: dict(name="configs[1]: rank-1 attn pool, synthetic 14x14x2048 feats, K=393, batch=32 per GPU",
+            kind="head", B=32, F=1, HW=HW14, K=393, flags={"SINGLE_LAYER_ATT": True}, bound="hbm"),
+    2: dict(name="configs[2]: rank-P=2 pose-regularized attn (003 config), batch=128 per GPU",
+            kind="head", B=128, F=1, HW=HW14, K=393, flags={"RANK": 2}, bound="tensor"),
+    3: dict(name="configs[3]: HICO K=600 attn pool, 10-crop, 32 images x 10 crop maps = 320 maps per GPU "
+                 "(256 images on 8 GPUs)",
+            kind="head", B=320, F=10, HW=HW14, K=600, flags={"SINGLE_LAYER_ATT": True}, bound="hbm"),
+    4: dict(name="configs[4]: full-rank bilinear X^T X (2048^2), synthetic 28x28x2048, 64 images per GPU "
+                 "(512 on 8 GPUs), outputs stay local",
+            kind="gram", B=64, F=1, HW=HW28, K=0, flags={}, bound="tensor"),
+}
 
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic(cfg):
+    """(bytes, flops) per step per GPU of the configuration."""
+    B, F, HW, K = cfg["B"], cfg["F"], cfg["HW"], cfg["K"]
+    if cfg["kind"] == "gram":
+        return B * HW * C * 4 + B * C * C * 4, 2.0 * HW * C * C * B
+    x = B * HW * C * 4
+    if cfg["flags"].get("SINGLE_LAYER_ATT"):
+        return x + (C + 1) * (K + 1) * 4 + (B // F) * K * 4, 2.0 * HW * C * (K + 1) * B
+    R = int(cfg["flags"].get("RANK", 1))
+    return x + (C + 1) * 768 * 4 + R * (C + 1) * K * 4 + (B // F) * K * 4, 2.0 * HW * C * 768 * B
 
 
 class ClockSampler(object):
@@ -81,7 +109,7 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        sm, mx, power, reasons = [], [], [], set()
         try:
             with open(self.path) as f:
                 for line in f:
@@ -91,6 +119,7 @@ class ClockSampler(object):
                     try:
                         sm.append(float(p[1]))
                         mx.append(float(p[2]))
+                        power.append(float(p[3]))
                     except ValueError:
                         continue
                     for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
@@ -101,90 +130,105 @@ class ClockSampler(object):
         except Exception:
             pass
         if sm:
-            out["sm_mhz"] = statistics.median(sm)
+            # "under load" = the samples taken while the GPU drew real power (the CPU legs idle it)
+            hot = [s for s, w in zip(sm, power) if w >= 0.5 * max(power)] or sm
+            out["sm_mhz"] = statistics.median(hot)
             out["sm_max_mhz"] = max(mx)
             out["samples"] = len(sm)
+            out["power_w_max"] = max(power)
         out["reasons"] = sorted(reasons)
         return out
 
 
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_step_fn(cfg, images):
+    """One call = the reference graph (PyTorch-CPU fp32 direct-form port, oracle (ii)) on `images` images."""
+    import torch
+    from oracle import attn_pool_oracle as orc
+    if cfg["kind"] == "gram":
+        X = torch.from_numpy(orc.make_features(images, cfg["HW"], C, seed=42))
+        return lambda: torch.matmul(X.transpose(1, 2), X)
+    fl = dict(orc.DEFAULT_FLAGS, **cfg["flags"])
+    params = {k: torch.from_numpy(v) for k, v in orc.make_params(cfg["K"], C, flags=fl, seed=42).items()}
+    X = torch.from_numpy(orc.make_features(images * cfg["F"], cfg["HW"], C, seed=42))   # built ONCE
+    return lambda: orc.attn_pool_head_torch_cpu(X, params, fl, cfg["K"], frames_per_video=cfg["F"])
+
+
 def _best_thread_count(fn):
-    """The CPU arm gets its best shot: sweep the intra-op thread count (all cores is often NOT the fastest
-    for this memory-bound graph on a many-core host) and keep the fastest; leaves torch set to it."""
+    """The CPU arm gets its best shot: sweep the intra-op thread count (all cores is often NOT the fastest for
+    this memory-bound graph on a many-core host), 3 timed calls per candidate; leaves torch set to the fastest."""
     import torch
     ncpu = os.cpu_count() or 1
-    cands = sorted(set(c for c in (8, 16, 32, 64, ncpu) if c <= ncpu))
+    cands = sorted(set(c for c in (8, 16, 32, 64, 96, ncpu) if c <= ncpu))
     best, best_t = ncpu, float("inf")
     with torch.no_grad():
         for c in cands:
             torch.set_num_threads(c)
             fn()
             t0 = time.perf_counter()
-            fn()
-            dt = time.perf_counter() - t0
+            for _ in range(3):
+                fn()
+            dt = (time.perf_counter() - t0) / 3
             if dt < best_t:
                 best, best_t = c, dt
     torch.set_num_threads(best)
-    return best
+    return best, best_t
 
 
-def cpu_port_rate(seconds, images_per_call=B_PER_GPU):
-    """images/s of the op-for-op PyTorch-CPU fp32 direct-form port (oracle (ii)), all host threads."""
+def cpu_sample_images(cfg):
+    """Images per CPU call: the whole per-GPU batch for config 1, a bounded slice of it for the heavy ones."""
+    return {1: 32, 2: 16, 3: 4, 4: 2}.get(cfg["id"], cfg["B"] // cfg["F"])
+
+
+def cpu_port_rate(cfg, seconds):
+    """images/s of the CPU port at its best thread count: calls repeated for >= `seconds`."""
     import torch
-    from oracle import attn_pool_oracle as orc
-    fl = dict(orc.DEFAULT_FLAGS, **FLAGS)
-    params = {k: torch.from_numpy(v) for k, v in orc.make_params(K, C, flags=fl, seed=42).items()}
-    X = torch.from_numpy(orc.make_features(images_per_call, HW, C, seed=42))
-    cores = _best_thread_count(lambda: orc.attn_pool_head_torch_cpu(X, params, fl, K))
+    n_img = cpu_sample_images(cfg)
+    fn = _cpu_step_fn(cfg, n_img)
+    cores, _ = _best_thread_count(fn)
     with torch.no_grad():
-        orc.attn_pool_head_torch_cpu(X, params, fl, K)  # warm-up
+        fn()
         n, t0 = 0, time.perf_counter()
         while True:
-            orc.attn_pool_head_torch_cpu(X, params, fl, K)
+            fn()
             n += 1
             dt = time.perf_counter() - t0
             if dt >= seconds:
                 break
-    return n * images_per_call / dt, cores, n, dt
+    return n * n_img / dt, cores, n, dt, n_img
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path for this head.  TF 1.1 / Python 2.7 cannot be
-    installed here (no network, no wheel), so this times the oracle's op-for-op PyTorch-CPU port."""
+def run_reference(args, cfg, rank):
+    """--impl reference: the reference's CPU path for this head.  TF 1.1 / Python 2.7 cannot be installed here
+    (no network, no wheel), so this times the oracle's op-for-op PyTorch-CPU port: same thread sweep and the same
+    pre-built inputs as the GPU arm's cpu_baseline; the K steps are repeated until >= 5 s have been timed."""
     if rank != 0:
         return
     import torch
-    from oracle import attn_pool_oracle as orc
-    fl = dict(orc.DEFAULT_FLAGS, **FLAGS)
-    params = {k: torch.from_numpy(v) for k, v in orc.make_params(K, C, flags=fl, seed=42).items()}
-    # bound the whole run to ~2 minutes: shrink the per-step sample if K is large
-    probe = torch.from_numpy(orc.make_features(4, HW, C, seed=42))
-    cores = _best_thread_count(lambda: orc.attn_pool_head_torch_cpu(
-        torch.from_numpy(orc.make_features(B_PER_GPU, HW, C, seed=42)), params, fl, K))
-    with torch.no_grad():
-        orc.attn_pool_head_torch_cpu(probe, params, fl, K)
-        t0 = time.perf_counter()
-        orc.attn_pool_head_torch_cpu(probe, params, fl, K)
-        t_img = (time.perf_counter() - t0) / 4
-    budget = 120.0
-    n_img = int(max(1, min(B_PER_GPU, budget / (max(1, args.steps + args.warmup) * t_img))))
-    X = torch.from_numpy(orc.make_features(n_img, HW, C, seed=42))
+    n_img = cpu_sample_images(cfg)
+    fn = _cpu_step_fn(cfg, n_img)
+    cores, _ = _best_thread_count(fn)
     with torch.no_grad():
         for _ in range(args.warmup):
-            orc.attn_pool_head_torch_cpu(X, params, fl, K)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            orc.attn_pool_head_torch_cpu(X, params, fl, K)
-        dt = time.perf_counter() - t0
-    value = args.steps * n_img / dt
-    sample = "%d images/step (of the %d-image batch), %d steps, PyTorch-CPU fp32 direct form" % (
-        n_img, B_PER_GPU, args.steps)
+            fn()
+        blocks, t0 = 0, time.perf_counter()
+        while True:
+            for _ in range(args.steps):
+                fn()
+            blocks += 1
+            dt = time.perf_counter() - t0
+            if dt >= 5.0 or blocks >= 200:
+                break
+    nsteps = blocks * args.steps
+    value = nsteps * n_img / dt
+    sample = ("%d images per step (of the %d-image batch), %d x %d steps in %.1f s, PyTorch-CPU fp32 direct form, "
+              "%d threads (best of a sweep)" % (n_img, cfg["B"] // cfg["F"], blocks, args.steps, dt, cores))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / nsteps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: rank-1 attn pool, synthetic 14x14x2048 feats, K=393, batch=32",
-                   "note": "TF-1.1 CPU path is not installable here; oracle port timed instead"},
+        "config": {"workload": cfg["name"],
+                   "note": "TF-1.1 CPU path is not installable here; the oracle's PyTorch-CPU port is timed instead"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -192,107 +236,157 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ host placement
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and so the pinned staging buffers it is about to allocate, first-touch) to the CPU cores
+    of the NUMA node the GPU hangs off: the H2D copy of the e2e leg then does not cross the socket interconnect."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local_rank)
+        pci = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % pci) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cluster", type=int, default=0, help="force CTAs per image (0 = auto)")
-    ap.add_argument("--fused", type=int, default=-1, help="1 fused kernel, 0 two kernels, -1 auto")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
+    ap.add_argument("--form", type=int, default=0, help="ApaTuning.form (0 = library default)")
+    ap.add_argument("--max-ctas", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="independent batches in flight (1..4)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch")
-    ap.add_argument("--trigger-lead", type=int, default=0, help="PDL trigger lead in tiles (0 = library default, -1 = none)")
-    ap.add_argument("--no-coop", action="store_true", help="never use the cooperative launch attribute")
+    ap.add_argument("--inputs-stable", type=int, default=1,
+                    help="ApaTuning.inputs_stable: the bench's inputs are resident before the timed region")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: all-gather fused into the kernel as NVLink peer stores, or a NCCL all_gather per step")
-    ap.add_argument("--general", action="store_true", help="force the grid-barrier kernel (not the cluster-local one)")
-    ap.add_argument("--split", action="store_true", help="force the two-kernel STREAM + CONTRACT pipeline")
-    ap.add_argument("--shape", type=int, default=-1, choices=[-1, 0, 1, 2],
-                    help="cluster-local kernel shape (-1 = library default; 0: 4 img/cluster, 2 CTAs/SM; "
-                         "1: 4 img/cluster, 3 CTAs/SM; 2: 8 img/cluster, 3 CTAs/SM)")
+    ap.add_argument("--gather-depth", type=int, default=3, help="gathered buffers in the ring (fused all-gather)")
+    ap.add_argument("--gather-lag", type=int, default=2,
+                    help="steps the consumer of the gathered logits runs behind the producers (0 = strict)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    cfg = dict(CONFIGS[args.config], id=args.config)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank)
         return
 
     import torch
     import torch.distributed as dist
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     from attentionalpoolingaction_b200 import dist as apa_dist
-    from oracle import attn_pool_oracle as orc  # inputs generator + cpu_baseline leg only
+    from oracle import attn_pool_oracle as orc  # inputs generator, parity spot-check and the cpu_baseline leg only
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    placement = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d" % (args.gpus, world)
 
-    fl = dict(orc.DEFAULT_FLAGS, **FLAGS)
-    params = orc.make_params(K, C, flags=fl, seed=42)
-    bits, rnk = ops.flags_from_cfg_net(fl)
-    tuning = ops.make_tuning(args.cluster, args.fused, no_pdl=int(args.no_pdl), no_cooperative=int(args.no_coop))
-    tuning.pdl_trigger_lead = args.trigger_lead
-    tuning.form = 1 if args.general else (7 if args.split else (0 if args.shape < 0 else 4 + args.shape))
+    B, F, HW, K = cfg["B"], cfg["F"], cfg["HW"], cfg["K"]
+    Bv = B // F
+    x_bytes = B * HW * C * 4
+    algo_bytes, algo_flops = algorithmic(cfg)
+    hbm_peak, bf16_peak, peak_src = _peaks()
     nstreams = max(1, min(4, args.streams))
-    # one op (= one workspace) per in-flight batch: consecutive steps are independent batches, so two
-    # of them overlap on the GPU (one streams X from HBM while the other is in its latency-bound tail)
-    opl = [ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, rank=rnk,
-                          flags=bits, tuning=tuning, device=dev) for _ in range(nstreams)]
-    op = opl[0]
-    plan = ops.attn_pool_plan(op.desc(B_PER_GPU), tuning)
+    is_gram = cfg["kind"] == "gram"
+    lag = max(0, min(args.gather_lag, args.gather_depth - 1))
 
     # ring of inputs > 2x L2 so that every step streams X from HBM
-    nbuf = max(2, -(-2 * L2_BYTES // X_BYTES) + 1)
+    nbuf = max(2, -(-2 * L2_BYTES // x_bytes) + 1)
     g = torch.Generator(device=dev).manual_seed(42 + rank)
-    ring = [torch.relu(torch.randn((B_PER_GPU, HW, C), device=dev, generator=g)) for _ in range(nbuf)]
-    logits_l = [torch.empty((B_PER_GPU, K), device=dev) for _ in range(nstreams)]
-    logits = logits_l[0]
-    gathered_l = [torch.empty((world * B_PER_GPU, K), device=dev) if world > 1 else None for _ in range(nstreams)]
-    collective = "none"
-    peer_l = None
-    if world > 1:
-        collective = args.collective
-        if collective == "peer":
-            try:
-                peer_l = [apa_dist.PeerGather(B_PER_GPU, K, dev) for _ in range(nstreams)]
-            except Exception as e:  # symmetric memory not available on this box: NCCL all_gather
-                sys.stderr.write("peer gather unavailable (%s); using NCCL all_gather\n" % e)
-                collective = "nccl"
+    ring = [torch.relu(torch.randn((B, HW, C), device=dev, generator=g)) for _ in range(nbuf)]
 
-    def step(i, with_collective=True):
-        j = i % nstreams
-        if world > 1 and with_collective and collective == "peer":
-            opl[j].forward_gather(ring[i % nbuf], peer_l[j].struct)   # kernel stores into every peer's buffer
-            return
-        opl[j](ring[i % nbuf], logits=logits_l[j])
-        if world > 1 and with_collective:
-            apa_dist.all_gather_logits(logits_l[j], gathered_l[j])
+    plan, parity, collective, peer_l, op = {}, None, "none", None, None
+    if is_gram:
+        gout = [torch.empty((B, C, C), device=dev) for _ in range(min(2, nstreams))]   # 1 GB each
 
-    # parity spot-check of what is being timed (first buffer, rank-local) -- outside timed regions
-    step(0)
-    torch.cuda.synchronize()
-    ref, _ = orc.attn_pool_head(ring[0][:4].cpu().numpy(), params, fl, K, want_pose=False)
-    mine = (peer_l[0].out[rank * B_PER_GPU:rank * B_PER_GPU + 4] if (world > 1 and collective == "peer")
-            else logits[:4])
-    parity = orc.rel_err(mine.cpu().numpy(), ref)
+        def step(i, with_collective=True):
+            ops.gram(ring[i % nbuf], out=gout[i % len(gout)])
+        step(0)
+        torch.cuda.synchronize()
+        ref = orc.gram(ring[0][:1].cpu().numpy())
+        parity = orc.rel_err(gout[0][:1].cpu().numpy(), ref)
+        launches_per_step = 1
+    else:
+        fl = dict(orc.DEFAULT_FLAGS, **cfg["flags"])
+        params = orc.make_params(K, C, flags=fl, seed=42)
+        bits, rnk = ops.flags_from_cfg_net(fl)
+        tuning = ops.make_tuning(no_pdl=int(args.no_pdl), form=args.form, max_ctas=args.max_ctas,
+                                 inputs_stable=args.inputs_stable, gather_wait_lag=lag)
+        P = {k: torch.from_numpy(v) for k, v in params.items()}
+        # one op (= one workspace) per in-flight batch: consecutive steps are independent batches
+        opl = [ops.AttnPoolOp(P, K, HW, channels=C, frames=F, rank=rnk, flags=bits, tuning=tuning, device=dev)
+               for _ in range(nstreams)]
+        op = opl[0]
+        plan = dict(ops.attn_pool_plan(op.desc(B), tuning))
+        launches_per_step = int(plan["launches"])
+        logits_l = [torch.empty((Bv, K), device=dev) for _ in range(nstreams)]
+        gathered_l = [torch.empty((world * Bv, K), device=dev) if world > 1 else None for _ in range(nstreams)]
+        if world > 1:
+            collective = args.collective
+            if collective == "peer":
+                try:
+                    peer_l = [apa_dist.PeerGather(Bv, K, dev, depth=args.gather_depth) for _ in range(nstreams)]
+                except Exception as e:  # symmetric memory not available on this box: NCCL all_gather
+                    sys.stderr.write("peer gather unavailable (%s); using NCCL all_gather\n" % e)
+                    collective = "nccl"
+
+        def step(i, with_collective=True):
+            j = i % nstreams
+            if world > 1 and with_collective and collective == "peer":
+                opl[j].forward_gather(ring[i % nbuf], peer_l[j])   # kernel stores into every peer's ring
+                return
+            opl[j](ring[i % nbuf], logits=logits_l[j])
+            if world > 1 and with_collective:
+                apa_dist.all_gather_logits(logits_l[j], gathered_l[j])
+
+        # parity spot-check of what is being timed (first buffer, rank-local) -- outside timed regions
+        step(0)
+        if peer_l is not None:
+            peer_l[0].wait(0)
+        torch.cuda.synchronize()
+        nchk = min(4, Bv)
+        ref, _ = orc.attn_pool_head(ring[0][:nchk * F].cpu().numpy(), params, fl, K, frames_per_video=F,
+                                    want_pose=False)
+        mine = (peer_l[0].buffer(1)[rank * Bv:rank * Bv + nchk] if peer_l is not None else logits_l[0][:nchk])
+        parity = orc.rel_err(mine.cpu().numpy(), ref)
     assert parity <= 1e-4, "bench parity check failed: %.3e" % parity
 
     side = torch.cuda.Stream(device=dev)
     lanes = [side] + [torch.cuda.Stream(device=dev) for _ in range(nstreams - 1)]
+    graphs_alive = []
 
     def enqueue(cnt, with_collective):
-        """`cnt` steps on the current stream, step i on lane i % nstreams (fork/join around the extra lane)."""
+        """`cnt` steps on the current stream, step i on lane i % nstreams (fork/join around the extra lanes)."""
         cur = torch.cuda.current_stream(dev)
         for ln in lanes[1:]:
             ln.wait_stream(cur)
@@ -300,6 +394,10 @@ def main():
             ln = cur if i % nstreams == 0 else lanes[i % nstreams]
             with torch.cuda.stream(ln):
                 step(i, with_collective)
+        if peer_l is not None and with_collective and lag > 0:   # the last steps' gathered buffers are complete too
+            for j, ln in enumerate([cur] + lanes[1:]):
+                with torch.cuda.stream(ln):
+                    peer_l[j].wait(0)
         for ln in lanes[1:]:
             cur.wait_stream(ln)
 
@@ -320,6 +418,7 @@ def main():
                         enqueue(cnt, with_collective)
                     graphs.append(gr)
             torch.cuda.synchronize()
+            graphs_alive.extend(graphs)
             g_full = graphs[0] if full else None
             g_rem = graphs[-1] if rem else None
 
@@ -328,8 +427,8 @@ def main():
                     g_full.replay()
                 if g_rem is not None:
                     g_rem.replay()
-            return run, "cuda-graph(%d steps/replay, %d batches in flight)" % (ring_steps, nstreams)
-        except Exception as e:  # capture refused (e.g. cooperative launch): plain stream launches
+            return run, "cuda-graph(%d steps/replay, %d batches in flight)" % (min(nsteps, ring_steps), nstreams)
+        except Exception as e:  # capture refused: plain stream launches
             sys.stderr.write("graph capture failed (%s); using stream launches\n" % e)
             torch.cuda.synchronize()
             return (lambda: enqueue(nsteps, with_collective)), "stream"
@@ -361,86 +460,168 @@ def main():
     torch.cuda.synchronize()
     ms_total = timed(run_k)                       # <- the K timed steps
     ms_per_step = ms_total / args.steps
-    value = world * B_PER_GPU * args.steps / (ms_total * 1e-3)
+    value = world * Bv * args.steps / (ms_total * 1e-3)
 
-    # roofline: the fused kernel alone (no collective), long enough for clock sampling (~1 s)
-    n_roof = int(min(200000, max(2000, 1.0e3 / max(ms_per_step, 1e-3))))
+    # roofline: the head alone (no collective), long enough for clock sampling (~1 s)
+    n_roof = int(min(200000, max(200, 1.0e3 / max(ms_per_step, 1e-3))))
     run_r, _ = make_runner(n_roof, False)
     run_r()
     torch.cuda.synchronize()
     ms_roof = timed(run_r) / n_roof
-    peak, peak_src = _peaks()
-    achieved = ALGO_BYTES / (ms_roof * 1e-3) / 1e9
+    if cfg["bound"] == "hbm":
+        achieved, peak, unit = algo_bytes / (ms_roof * 1e-3) / 1e9, hbm_peak, "GB/s"
+        peak_note = peak_src + ": hbm_gbs (a read+write copy; a read-mostly stream can exceed it slightly)"
+    else:
+        # fp32 results need the error-compensated 3xTF32 split: 3 tensor-core MMAs per algorithmic MMA, and the TF32
+        # pipe runs at half the (measured) bf16 rate -> peak = bf16 / 2 / 3 of fp32-equivalent flops
+        achieved, peak, unit = algo_flops / (ms_roof * 1e-3) / 1e12, bf16_peak / 6.0, "TFLOP/s"
+        peak_note = peak_src + ": bf16_tflops / 2 (TF32 rate) / 3 (3xTF32 split for fp32-level results)"
+
+    # latency: ONE launch alone on an idle GPU, X cold (this config's batch, and one image)
+    latency = None
+    if not is_gram and not args.no_latency and rank == 0:
+        latency = {"method": "CUDA events around one graph-launched call after a device sync, X not in L2, "
+                             "median of 15; includes the graph launch itself"}
+        for tag, b in (("b%d" % Bv, B), ("b1", F)):
+            lg = torch.empty((b // F, K), device=dev)
+            xs1 = [r[:b] for r in ring]
+            with torch.cuda.stream(side):
+                op(xs1[0], logits=lg)
+                torch.cuda.synchronize()
+                grs = []
+                for x1 in xs1[:4]:
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr, stream=side):
+                        op(x1, logits=lg)
+                    grs.append(gr)
+                lat = []
+                for i in range(15):
+                    torch.cuda.synchronize()
+                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    grs[i % len(grs)].replay()
+                    b_.record()
+                    torch.cuda.synchronize()
+                    lat.append(a.elapsed_time(b_) * 1e3)
+            latency[tag] = statistics.median(lat)
+            graphs_alive.extend(grs)
 
     # e2e: host buffers through apa_attn_pool_fwd_host (H2D + kernel + D2H + sync per step)
-    xh = [torch.relu(torch.randn((B_PER_GPU, HW, C), generator=torch.Generator().manual_seed(rank))).pin_memory()
-          for _ in range(2)]
-    lh = torch.empty((B_PER_GPU, K)).pin_memory()
-    for i in range(3):
-        op.forward_host(xh[i % 2], lh)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(args.e2e_steps):
-        op.forward_host(xh[i % 2], lh)
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_value = world * B_PER_GPU * args.e2e_steps / t_e2e
+    if not is_gram:
+        xh = [torch.relu(torch.randn((B, HW, C), generator=torch.Generator().manual_seed(rank))).pin_memory()
+              for _ in range(2)]
+        lh = torch.empty((Bv, K)).pin_memory()
+        for i in range(3):
+            op.forward_host(xh[i % 2], lh)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            op.forward_host(xh[i % 2], lh)
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        # the bound of this leg: the same pinned buffer copied host -> device with nothing else (PCIe)
+        stage = torch.empty_like(ring[0])
+        stage.copy_(xh[0], non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(10):
+            stage.copy_(xh[i % 2], non_blocking=True)
+        torch.cuda.synchronize()
+        copy_gbs = 10 * x_bytes / (time.perf_counter() - t0) / 1e9
+        del stage
+        e2e_gbs = x_bytes * args.e2e_steps / t_e2e / 1e9
+        e2e = {"value": world * Bv * args.e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": x_bytes,
+               "d2h_bytes_per_step": Bv * K * 4, "steps": args.e2e_steps,
+               "roofline": {"bound": "pcie h2d", "achieved": e2e_gbs, "peak": copy_gbs, "unit": "GB/s per GPU",
+                            "frac": e2e_gbs / copy_gbs,
+                            "peak_source": "the same pinned buffer copied host->device alone, measured in this run"},
+               "api": "apa_attn_pool_fwd_host (pinned host X -> HBM, head, logits -> host, sync)",
+               "host_placement": placement}
+    else:
+        # the Gram has no host-buffer entry point: its e2e is the device call plus the copies done by torch
+        xh = ring[0].cpu().pin_memory()
+        gh = torch.empty((B, C, C)).pin_memory()
+        nst = max(2, args.e2e_steps // 10)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(nst):
+            ring[0].copy_(xh, non_blocking=True)
+            ops.gram(ring[0], out=gout[0])
+            gh.copy_(gout[0], non_blocking=True)
+            torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        e2e = {"value": world * Bv * nst / t_e2e, "unit": "images/s", "h2d_bytes_per_step": x_bytes,
+               "d2h_bytes_per_step": B * C * C * 4, "steps": nst,
+               "api": "pinned host X -> HBM, apa_gram_fwd, G -> pinned host (copies by torch), sync",
+               "host_placement": placement}
 
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        cpu_v, cores, ncalls, cpu_dt = cpu_port_rate(args.cpu_seconds)
+        cpu_v, cores, ncalls, cpu_dt, cpu_img = cpu_port_rate(cfg, args.cpu_seconds)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.config == 1:
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
+        kernel = {0: "apa_pool_fused_kernel", 1: "apa_pool_local_kernel", 2: "apa_stream_kernel + apa_contract_kernel",
+                  3: "apa_flow_kernel"}.get(plan.get("cluster_local"), "gemm_tf32x3_kernel (gram)")
+        if cfg["bound"] == "tensor" and not is_gram:
+            kernel = "gemm_tf32x3_kernel (pose pre-logits 2048->768) + " + kernel
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "configs[1]: rank-1 attn pool, synthetic 14x14x2048 feats, K=393, batch=32 per GPU",
-                "per_gpu_batch": B_PER_GPU, "global_batch": world * B_PER_GPU,
-                "parallelism": ("batch-sharded x%d, one all-gather of logits per step (%s)" % (
-                                    world, "fused into the kernel: NVLink peer stores + step flags"
-                                    if collective == "peer" else "NCCL all_gather_into_tensor")) if world > 1
-                               else "single GPU",
+                "workload": cfg["name"],
+                "per_gpu_batch": Bv, "global_batch": world * Bv, "feature_maps_per_gpu": B,
+                "parallelism": ("batch-sharded x%d, %s" % (
+                    world, "outputs stay local (no collective)" if is_gram else
+                    ("one all-gather of logits per step fused into the kernel: NVLink peer stores into a ring of %d "
+                     "gathered buffers + step flags, consumer %d steps behind" % (args.gather_depth, lag)
+                     if collective == "peer" else "one NCCL all_gather_into_tensor of logits per step")))
+                    if world > 1 else "single GPU",
                 "l2": "inputs rotate over %d buffers x %.1f MB (%.0f MB > 2x 126 MB L2): every step reads HBM"
-                      % (nbuf, X_BYTES / 1e6, nbuf * X_BYTES / 1e6),
-                "launch": launch_mode, "plan": dict(plan), "batches_in_flight": nstreams, "parity_rel_err_vs_fp64_oracle": parity,
+                      % (nbuf, x_bytes / 1e6, nbuf * x_bytes / 1e6),
+                "launch": launch_mode, "plan": plan, "batches_in_flight": nstreams,
+                "inputs_stable": args.inputs_stable, "parity_rel_err_vs_fp64_oracle": parity,
                 "clock_sampling": "nvidia-smi every 100 ms across warm-up, the K timed steps, the "
-                                  "roofline loop (%d launches) and the e2e loop" % n_roof,
+                                  "roofline loop (%d steps), the latency and e2e loops" % n_roof,
             },
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": X_BYTES,
-                    "d2h_bytes_per_step": OUT_BYTES, "steps": args.e2e_steps,
-                    "api": "apa_attn_pool_fwd_host (pinned host X -> HBM, head, logits -> host, sync)"},
-            "gpu_launches": args.steps * int(plan["launches"]),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "apa_pool_local_kernel" if plan.get("cluster_local") else "apa_pool_fused_kernel", "us_per_launch": ms_roof * 1e3,
-                         "duration": "CUDA-event time of the loop / launches (%d independent launches in flight)"
+            "e2e": e2e,
+            "gpu_launches": args.steps * launches_per_step,
+            "roofline": {"bound": cfg["bound"], "achieved": achieved, "peak": peak, "unit": unit,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_note,
+                         "kernel": kernel, "us_per_step": ms_roof * 1e3,
+                         "duration": "CUDA-event time of the loop / steps (%d independent batches in flight)"
                                      % nstreams,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES, "launches_timed": n_roof},
+                         "algorithmic_bytes_per_step": algo_bytes, "algorithmic_flops_per_step": algo_flops,
+                         "steps_timed": n_roof},
+            "latency_us": latency,
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "%d calls x %d images in %.1f s, PyTorch-CPU fp32 direct form"
-                                       % (ncalls, B_PER_GPU, cpu_dt)},
+                                       % (ncalls, cpu_img, cpu_dt)},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+
+    # orderly teardown (the driver's native-load record is written at interpreter exit): drop the captured graphs
+    # and everything that holds device memory before the process group goes away
+    torch.cuda.synchronize()
+    graphs_alive.clear()
+    run_w = run_k = run_r = None
+    peer_l = None
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
     sys.stdout.flush()
     sys.stderr.flush()
-    # Captured CUDA graphs hold NCCL kernels; tearing the communicator down under them can hang.  Everything
-    # is printed and synchronised: leave without running destructors.
-    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -176,18 +176,30 @@ int apa_attn_pool_fwd_host(const ApaDesc* desc, const float* X_host, const ApaWe
                            void* stream);
 
 /* The single collective of the multi-GPU path, fused into the kernel: instead of writing `logits`, every rank
- * stores its [batch/frames, K] block straight into the gathered buffer of every peer (NVLink peer stores from
- * the kernel's last step) at row offset rank * batch/frames, then publishes a per-rank step flag; the kernel
- * returns only once the flags of all ranks for this step have arrived, so stream completion on a rank means
- * its gathered buffer is complete.  peer_* are device pointers valid on THIS GPU (symmetric memory / IPC
- * mappings); flags and done_counter are zeroed once by the caller; every rank must issue the same calls. */
+ * stores its [batch/frames, K] block straight into a gathered buffer on every peer (NVLink peer stores from
+ * the kernel's last step) at row offset rank * batch/frames, then publishes a per-rank step flag.  The gathered
+ * buffers form a ring of `depth` buffers on every rank: call number `step` (1, 2, 3, ... counted on the device in
+ * counters[1], so CUDA-graph replays keep counting; the same on every rank) lands in buffer step % depth.
+ *   completeness  After the call, in stream order, buffer (step - lag) % depth holds the blocks of ALL ranks for
+ *                 step - lag, where lag = ApaTuning.gather_wait_lag (0 by default: this step, every call then
+ *                 waits for the slowest rank; lag >= 1 pipelines the consumer behind the producers; lag < 0:
+ *                 nothing is waited for -- call apa_peer_gather_wait before consuming).
+ *   buffer reuse  The caller must have consumed buffer step % depth (the result of call step - depth) in stream
+ *                 order before it enqueues call step - depth + 1 on that rank; a rank only overwrites a peer's
+ *                 buffer once that peer has started call step - depth + 1, so with depth >= 2 a fast rank
+ *                 runs up to depth - 1 calls ahead of a slow one without waiting.
+ * peer_* are device pointers valid on THIS GPU (symmetric memory / IPC mappings); each flag array has 2 * world
+ * words and is zeroed once by the caller, like `counters`; every rank must issue the same calls.  A rank that
+ * never arrives makes the waiting kernels trap after ~60 s (APA_PEER_TIMEOUT_CYCLES) instead of hanging. */
 #define APA_MAX_PEERS 8
 typedef struct ApaPeerGather {
   int32_t world;                                     /* 1..APA_MAX_PEERS                                   */
   int32_t rank;                                      /* this rank                                          */
-  float* peer_logits[APA_MAX_PEERS];                 /* peer q's gathered buffer [world * batch/frames, K]  */
-  unsigned long long* peer_flags[APA_MAX_PEERS];     /* peer q's flag array [world]                         */
-  unsigned long long* done_counter;                  /* local                                              */
+  int32_t depth;                                     /* gathered buffers in the ring, 1..4                 */
+  int32_t reserved0;                                 /* must be 0                                          */
+  float* peer_logits[APA_MAX_PEERS];                 /* peer q's ring [depth][world * batch/frames][K]      */
+  unsigned long long* peer_flags[APA_MAX_PEERS];     /* peer q's flag array [2 * world]                     */
+  unsigned long long* counters;                      /* 2 local words: [0] scratch, [1] calls completed     */
 } ApaPeerGather;
 
 /* apa_attn_pool_fwd for the batch-sharded multi-GPU path (single-map head only): logits go to the peers'
@@ -196,6 +208,11 @@ typedef struct ApaPeerGather {
 int apa_attn_pool_fwd_gather(const ApaDesc* desc, const float* X, const ApaWeights* weights,
                              const ApaPeerGather* gather, void* workspace, size_t workspace_bytes,
                              const ApaTuning* tuning, void* stream);
+
+/* Enqueue on `stream` a wait until the blocks of every rank for call (latest - lag) have landed in this rank's
+ * ring, `latest` being the last gather call enqueued on `stream` before this one (one thread polling this rank's
+ * own flag array; returns at once when they already have).                                              */
+int apa_peer_gather_wait(const ApaPeerGather* gather, int32_t lag, void* stream);
 
 /* Full second-order pooling G[b] = X[b]^T X[b]  ([batch, C, C], symmetric).  Not present in the
  * reference code; defined from the paper's second-order pooling equation (BASELINE config 5). */

@@ -21,7 +21,7 @@ for it in range(6):
     X = torch.relu(torch.randn((B, HW, C), device=dev, generator=torch.Generator(device=dev).manual_seed(100 * it + rank)))
     local = op(X)[0].clone()
     ref = apa_dist.all_gather_logits(local)
-    op.forward_gather(X, pg.struct)
+    op.forward_gather(X, pg)
     torch.cuda.synchronize()
     same = torch.equal(pg.out, ref)
     ok = ok and same

@@ -38,6 +38,11 @@ CASES = [
     ("fused_c1024_single", 3, (2, 3), 1024, 5, 3, 1, S),
     ("fused_c1024_softmax", 2, (2, 3), 1024, 5, 3, 1, dict(S, SOFTMAX_ATT=True)),
     ("fused_c1024_rank2_relu_frames", 4, (2, 2), 1024, 5, 3, 2, dict(S, RANK=2, RELU_ATT=True)),
+    # C = 2048, the shapes every form of the single-map head accepts (the headline kernels see a fixture directly;
+    # tests/test_gpu_golden.py runs these through each form)
+    ("c2048_b8_single", 8, (3, 3), 2048, 5, 3, 1, S),
+    ("c2048_b8_softmax", 8, (3, 3), 2048, 5, 3, 1, dict(S, SOFTMAX_ATT=True)),
+    ("c2048_frames2_rank2_relu", 8, (3, 3), 2048, 5, 3, 2, dict(S, RANK=2, RELU_ATT=True)),
 ]
 ERROR_CASES = [("softmax_rank2_build_error", dict(S, SOFTMAX_ATT=True, RANK=2))]
 

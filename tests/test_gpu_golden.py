@@ -44,6 +44,40 @@ def test_cuda_head_matches_reference_graph_fixture(name):
     orc.assert_parity(logits2.cpu().numpy(), z["logits"], TOL, name + " logits (no end-points)")
 
 
+FORM_CASES = sorted(k for k in CASES if k.startswith("c2048_"))
+
+
+@pytest.mark.parametrize("name", FORM_CASES)
+def test_every_form_of_the_head_sees_a_reference_fixture(name):
+    """C = 2048 fixtures from the reference graph through EVERY form of the single-map head (ApaTuning.form), with
+    the plan asserted: the headline kernels are pinned by a reference-generated vector directly, not transitively."""
+    import torch
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc
+    meta = INDEX[name]
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    variables = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("var:")}
+    X = torch.from_numpy(z["X"]).cuda()
+    H, W = meta["hw"]
+    bits, rank = ops.flags_from_cfg_net(meta["flags"])
+    forms = [(ops.APA_FORM_FLOW, 3), (ops.APA_FORM_GRID_BARRIER, 0), (ops.APA_FORM_PIPELINE, 2)]
+    if meta["frames"] == 1:
+        forms.append((ops.APA_FORM_LOCAL0, 1))
+    seen = set()
+    for form, kind in forms:
+        t = ops.make_tuning(form=form)
+        op = ops.AttnPoolOp(variables, meta["num_classes"], H * W, channels=meta["channels"], frames=meta["frames"],
+                            rank=rank, flags=bits, num_pose_keypoints=meta["num_pose_keypoints"], tuning=t,
+                            device="cuda:0")
+        plan = ops.attn_pool_plan(op.desc(X.shape[0]), t)
+        assert plan["path"] == 0 and plan["cluster_local"] == kind, (form, dict(plan))
+        seen.add(plan["cluster_local"])
+        logits, _ = op(X)
+        torch.cuda.synchronize()
+        orc.assert_parity(logits.cpu().numpy(), z["logits"], TOL, "%s form %d" % (name, form))
+    assert len(seen) == len(forms)
+
+
 def test_reference_build_error_is_an_abi_error():
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     meta = INDEX["softmax_rank2_build_error"]

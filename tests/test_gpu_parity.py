@@ -227,11 +227,12 @@ def test_fused_gather_single_rank(B, general):
     pg = apa_dist.PeerGather(B, 393, torch.device("cuda:0"))
     Xd = torch.from_numpy(X).cuda()
     for _ in range(5):
-        op.forward_gather(Xd, pg.struct)
+        op.forward_gather(Xd, pg)
     torch.cuda.synchronize()
     ref, _ = orc.attn_pool_head(X, params, fl, 393, want_pose=False)
     orc.assert_parity(pg.out.cpu().numpy(), ref, TOL)
-    assert int(pg.flags[0].item()) == 5        # one step flag per launch
+    assert int(pg.flags[0].item()) == 5        # one data flag per launch
+    assert pg.sync_step() == 5                 # counted on the device
 
 
 def test_two_batches_in_flight():

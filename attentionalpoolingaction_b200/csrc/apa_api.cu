@@ -26,7 +26,7 @@ constexpr size_t kFlowCtrOff = 2048;        // [2048, 4096): the flow form's tic
 constexpr size_t kTsBytes = 320 * 64 * 8;  // debug timeline: up to 320 CTAs x 64 stamps
 
 struct Carve {
-  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, cpart, gsum, fl_img, fl_arr, total;
+  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, cpart, gsum, fl_arr, total;
   int path;  // 0 fused single-map, 1 dense
 };
 
@@ -61,7 +61,6 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
         if (flow_gpart_slots(d->batch) > slots) slots = flow_gpart_slots(d->batch);
         c.cpart = take(flow_cpart_floats(d->batch, d->num_classes, d->frames));
         c.gsum = take(B * 4);
-        c.fl_img = take(B * 2);  // u64 per image
         c.fl_arr = take(flow_slices(d->batch, d->num_classes, d->frames) * 2);
       }
       c.gpart = take(slots * R * C);
@@ -235,12 +234,12 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
     bool two = !fp.fused;
     if (use_flow(desc, tuning)) {
       plan[1] = 0;
-      plan[2] = flow_stream_ctas(desc->batch, desc->hw, tuning) + 8 * flow_class_slices(desc->num_classes);
-      plan[3] = 1;
+      plan[2] = flow_stream_ctas(desc->batch, desc->hw, tuning);   // STREAM grid
+      plan[3] = 0;
       plan[5] = int32_t(flow_smem(desc->channels));
-      plan[6] = 3;                                   // flow form: STREAM + CONTRACT CTAs in one launch
-      plan[7] = 8 * flow_class_slices(desc->num_classes);
-      two = false;
+      plan[6] = 3;                                   // flow form: row-balanced STREAM + small CONTRACT
+      plan[7] = flow_contract_grid(desc->num_classes);
+      two = true;
     } else if (use_split(desc, tuning)) {
       const int lp = split_lp(desc->batch, desc->hw, tuning);
       const int units = desc->batch * lp, cap = 148 * (desc->rank == 1 ? 3 : 1);
@@ -253,6 +252,7 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
       two = true;
     }
     launches += two ? 2 : 1;
+    if (plan[6] == 3) launches += 1;               // flow form: STREAM, REDUCE, CONTRACT
     if (want_attn) launches += 1;
   } else {
     const int R = desc->rank;
@@ -407,10 +407,10 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
       p.gstat = wsf(c.gstat);
       p.cpart = wsf(c.cpart);
       p.gsum = wsf(c.gsum);
-      p.fl_img = reinterpret_cast<unsigned long long*>(ws + c.fl_img);
       p.fl_arr = reinterpret_cast<unsigned long long*>(ws + c.fl_arr);
       p.fl_ctr = reinterpret_cast<unsigned long long*>(ws + kFlowCtrOff);
-      APA_CUDA(flow_launch(p, mode, tuning, stream, &grid));
+      int g1 = 0;
+      APA_CUDA(flow_launch(p, mode, tuning, stream, &g1, &grid));
       launched = true;
     }
     if (!launched && gw != nullptr) APA_CUDA(peer_gather_begin_launch(gw, stream));  // flow control for the other forms

@@ -47,11 +47,10 @@ struct FusedParams {
   float* gstat;                       // workspace [B, lp, 8]: (s_r[4], running max) per row slice
   int lp;                             // row slices per image
   // flow form (apa_pool_flow.cu)
-  unsigned long long* fl_ctr;         // control counters: [0] ticket [1] stream-done [2] slices-done
-  unsigned long long* fl_img;         // [B] per-image arrival counters (STREAM CTAs holding rows of the image)
+  unsigned long long* fl_ctr;         // control counters: [2] slices-done (fused all-gather)
   unsigned long long* fl_arr;         // [video tiles * class slices] arrival counters of the CONTRACT units
-  float* gsum;                        // workspace [B][4]: attention mass per rank of the completed image
-  float* cpart;                       // workspace [tiles * class slices][8][32 videos][32 classes] partial logits
+  float* gsum;                        // workspace [B][4]: attention mass per rank of the reduced image
+  float* cpart;                       // workspace [tiles * class slices][16][32 videos][32 classes] partial logits
   int fl_G, fl_NS;                    // STREAM CTAs, class slices
   int inputs_stable;                  // X / weights may be read before the previous kernel in the stream completed
   int gw_depth;                       // buffers in every rank's gathered ring (call `step` lands in step % depth)
@@ -93,7 +92,7 @@ size_t split_stream_smem(int C);
 cudaError_t split_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream,
                          int* stream_grid, int* contract_grid);
 
-// ---- flow form (apa_pool_flow.cu): one launch, ticketed STREAM CTAs + CONTRACT CTAs
+// ---- flow form (apa_pool_flow.cu): row-balanced STREAM kernel + small CONTRACT kernel parked in griddepcontrol.wait
 constexpr int kFlowStreamCtas = 148;   // one STREAM CTA per SM of a B200
 bool flow_eligible(int B, int HW, int C, int K, int R, int F);
 int flow_stream_ctas(int B, int HW, const ApaTuning* tuning);
@@ -102,7 +101,9 @@ size_t flow_gpart_slots(int B);                 // partial-g slots the workspace
 size_t flow_slices(int B, int K, int F);        // (video tile, class slice) pairs = arrival counters
 size_t flow_cpart_floats(int B, int K, int F);  // partial-logit floats the workspace holds
 size_t flow_smem(int C);
-cudaError_t flow_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out);
+int flow_contract_grid(int K);
+cudaError_t flow_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream,
+                        int* stream_grid, int* contract_grid);
 
 // ---- dense path (apa_dense.cu)
 bool dense_force_simt();  // APA_DENSE_SIMT=1 in the environment (read once): A/B switch for tests and profiling

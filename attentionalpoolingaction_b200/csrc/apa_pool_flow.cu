@@ -1,34 +1,32 @@
-// apa_pool_flow.cu — the single-map head as ONE launch of two kinds of CTA that never hold each other up.
-// Same math as the other forms (reference sites nets_factory.py:259-328, :350-352, :354-374):
+// apa_pool_flow.cu — the single-map head as a STREAM kernel that does nothing but stream, followed by two small
+// kernels that wait in hardware.  Same math as the other forms (reference sites nets_factory.py:259-328,
+// :350-352, :354-374):
 //     g_r[b] = sum_hw A_r[b,hw] X[b,hw,:]      s_r[b] = sum_hw A_r[b,hw]
 //     logits[v] = sum_frames sum_r (g_r . B_r + d_r s_r) / (HW F)
 //
-//   blocks [0, G)       STREAM CTAs.  The launch's B*HW rows are cut into G equal runs that cross image
-//                       boundaries (G = 148: every SM streams the same byte count).  A producer lane feeds
-//                       3-row x C tiles (24 KB, cp.async.bulk) through a 3-stage mbarrier ring, 8 consumer warps
-//                       form a[row] and accumulate g in registers.  At every image boundary the CTA stores its
-//                       PARTIAL g (8 KB per rank) + (attention mass, running max) and counts itself in that
-//                       image's arrival counter; the CTA that completes an image adds the image's partials in
-//                       fixed order (softmax: max/sum merge) into g[b].  An image that lies inside one run is
-//                       written to g[b] directly.  At the end the CTA counts itself in `stream-done` and exits.
-//                       74 KB / 72 registers: three CTAs per SM.
-//   blocks [G, G + U)   CONTRACT CTAs, U = 8 channel slices x ceil(K/32) class slices.  A unit loads its
-//                       [C/8 x 32] block of B_r into shared memory, spins (one thread, nanosleep) until
-//                       `stream-done` reaches G, loads g of its channels for 32 videos (summing frames), contracts
-//                       (4 x 4 register tiles, 4 channel quarters), and writes its partial [32 x 32] block.  The 8th
-//                       unit to arrive for a class slice adds the 8 partials in fixed order (bit-reproducible),
-//                       bias, scale, and stores the logits (or the peer stores of the fused all-gather).
-// A CONTRACT CTA waits only for STREAM CTAs of its own launch, which have lower block indices (CTAs are
-// dispatched in index order, so they are resident or done) and which themselves wait for nothing but the
-// previous launch; every spin has a trap timeout.  All counters live in the workspace and only ever grow: each
-// launch leaves each of them at the next multiple of 2^20, so CUDA-graph replays and changing shapes need no host
-// state and no reset (CONTRACT CTAs learn the launch index from a ticket counter).
-//
-// Programmatic dependent launch: every CTA triggers at once, so launch n+1's STREAM CTAs take the free CTA
-// slots while launch n is still streaming / contracting; a STREAM CTA executes griddepcontrol.wait before its
-// first global write (launch n has then completed, so neither the workspace nor the counters are ever shared by
-// two launches).  Reading X before that wait is only legal when X was complete before the previous kernel in
-// the stream started: ApaTuning.inputs_stable (default 0 = wait first).
+//   STREAM    G CTAs (G = 148: one per SM, and its 129 KB of shared memory keep it the only STREAM CTA on its
+//             SM).  The launch's B*HW rows are cut into G equal runs that cross image boundaries, so every SM
+//             streams the same byte count whatever the batch.  A producer lane feeds 3-row x C tiles (24 KB,
+//             cp.async.bulk) through a 4-stage mbarrier ring; two groups of 4 consumer warps take alternate tiles
+//             (two dot -> reduce -> accumulate chains in flight), form a[row] and accumulate g in registers.  A
+//             group's PARTIAL g of an image (8 KB per rank) and (attention mass, running max) go to slot
+//             2 (CTA + image) + group of the workspace: partials of non-final images wait in shared memory, the
+//             CTA executes griddepcontrol.wait once, after its last tile, then stores.  No flags, atomics, fences.
+//   REDUCE    one 128-thread CTA per (image, 512 channels): adds the image's partials in run order (softmax:
+//             max/sum merge) into g[b], the attention mass into gsum[b].
+//   CONTRACT  16 channel slices x ceil(K/32) class slices, 128 threads, 34 KB.  A unit loads its [C/16 x 32] block
+//             of B_r into shared memory, executes griddepcontrol.wait, loads g of its channels for 32 videos (frames
+//             summed), contracts (4 x 4 register tiles, two channel halves), and writes its partial [32 x 32]
+//             block.  The 16th unit to arrive for a class slice adds the 16 partials in fixed order
+//             (bit-reproducible), bias, scale, and stores the logits (or the peer stores of the fused all-gather).
+// All three are programmatic dependents that trigger at once: STREAM(n) -> REDUCE(n) -> CONTRACT(n) -> STREAM(n+1).
+// REDUCE(n) and CONTRACT(n) are small enough to be resident (parked in griddepcontrol.wait, a hardware wait) beside
+// STREAM(n) on every SM, so STREAM(n+1)'s CTA takes an SM the moment STREAM(n)'s CTA leaves it and HBM idles only
+// for the first-tile latency between calls, on one stream as on four.  STREAM(n+1) executes griddepcontrol.wait
+// before its first global write (CONTRACT(n), and so everything before it, has then completed).  Reading X before
+// that wait is only legal when X was complete before the previous kernel in the stream started:
+// ApaTuning.inputs_stable (default 0 = wait first).  The only counters are the CONTRACT units' arrival counters
+// (each launch adds exactly 16 to each) and a slices-done counter that every launch leaves at a multiple of 2^20.
 #include "apa_common.cuh"
 #include "apa_kernels.h"
 
@@ -39,11 +37,13 @@ namespace apa {
 namespace {
 
 constexpr int kFTR = 3;        // rows per X tile
-constexpr int kFStages = 3;    // ring depth
-constexpr int kNJ = 8;         // channel slices of the contraction
+constexpr int kFStages = 4;    // ring depth: 96 KB in flight per SM; with the staging area no second STREAM CTA fits beside it
+constexpr int kNJ = 16;        // channel slices of the contraction
 constexpr int kKW = 32;        // classes per contract unit
-constexpr int kGPad = 4;       // gs[video][C/8 + 4]: consecutive videos start 4 banks apart
-constexpr unsigned long long kStride = 1ull << 20;  // every launch leaves every counter at a multiple of this
+constexpr int kGPad = 4;       // gs[video][C/16 + 4]: consecutive videos start 4 banks apart
+constexpr int kCThreads = 128; // CONTRACT block
+constexpr int kRThreads = 128; // REDUCE block: 128 float4 columns = 512 channels
+constexpr unsigned long long kStride = 1ull << 20;
 
 __device__ __forceinline__ float fdot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
@@ -64,11 +64,6 @@ __device__ __forceinline__ unsigned long long atom_add_acq_rel(unsigned long lon
   asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], %2;" : "=l"(prev) : "l"(p), "l"(v) : "memory");
   return prev;
 }
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long fglobaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -77,7 +72,7 @@ __device__ __forceinline__ unsigned long long fglobaltimer_ns() {
 
 // rows [flow_row_lo(t), flow_row_lo(t + 1)) of the flattened [B * HW] row space belong to STREAM CTA t
 __device__ __forceinline__ int flow_row_lo(long long N, int G, int t) { return int(N * t / G); }
-// the STREAM CTAs that hold rows of image b are [lo, hi]
+// the STREAM CTAs that hold rows of image b are [lo, hi]; CTA e keeps its partial of image b in slot e + b
 __device__ __forceinline__ void flow_image_ctas(long long N, int G, int HW, int b, int* lo, int* hi) {
   const long long x0 = (long long)b * HW, x1 = x0 + HW - 1;
   long long a = ((x0 + 1) * G - 1) / N, c = ((x1 + 1) * G - 1) / N;
@@ -85,386 +80,405 @@ __device__ __forceinline__ void flow_image_ctas(long long N, int G, int HW, int 
   *hi = int(c < G - 1 ? c : G - 1);
 }
 
-__host__ __device__ constexpr size_t flow_main_bytes(int C) {
-  const size_t ring = size_t(kFStages) * kFTR * C * 4;
-  const size_t contract = size_t(C / kNJ) * kKW * 4 + size_t(kVideoTile) * (C / kNJ + kGPad) * 4 + kVideoTile * 4 * 4;
-  return ((ring > contract ? ring : contract) + 127) / 128 * 128;
+constexpr int kNG = 2;                        // consumer groups: two tiles are in work at any time
+constexpr int kWPG = kConsumerWarps / kNG;    // warps per group (4): a warp covers C / 4 channels of a row
+constexpr size_t kStageBytes = 32 * 1024;     // partials of a CTA's non-final image segments wait here
+__host__ __device__ inline size_t stream_smem_bytes(int C) {
+  return size_t(kFStages) * kFTR * C * 4 + kStageBytes + 512 + 512 + 16 * 8;
 }
-__host__ __device__ inline size_t flow_smem_bytes(int C) { return flow_main_bytes(C) + 2 * 32 * 4 + 16 * 8 + 64; }
 
+// ================================================================================================ STREAM
 template <int Q, int RMAX, int MODE>
-__global__ void __launch_bounds__(kFusedThreads, (RMAX == 1) ? 3 : 1)
-apa_flow_kernel(const FusedParams p) {
-  constexpr int C = Q * 1024, TR = kFTR, CH = C / kNJ;
+__global__ void __launch_bounds__(kFusedThreads, 1) __maxnreg__((RMAX == 1) ? 128 : 216)
+apa_flow_stream_kernel(const FusedParams p) {
+  constexpr int C = Q * 1024, TR = kFTR, QT = Q * kNG;   // QT float4s of a row per thread
   constexpr size_t kTileBytes = size_t(TR) * C * 4;
-  constexpr size_t kMainBytes = flow_main_bytes(C);
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* partS = reinterpret_cast<float*>(smem + kMainBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kMainBytes + 256);
-  uint64_t* empty_bar = full_bar + 4;
-  unsigned long long* tick_s = reinterpret_cast<unsigned long long*>(full_bar + 8);
-  int* flag_s = reinterpret_cast<int*>(full_bar + 10);
-  const int R = p.R, G = p.fl_G, K = p.K, F = p.F, HW = p.HW;
+  float* stg = reinterpret_cast<float*>(smem + kFStages * kTileBytes);              // [seg][R][group][C]
+  float* stgstat = reinterpret_cast<float*>(smem + kFStages * kTileBytes + kStageBytes);   // [seg][group][8]
+  float* partS = stgstat + 128;                                                      // [group][2][16]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(partS + 128);
+  uint64_t* empty_bar = full_bar + 8;
+  static_assert(kFStages <= 8, "barrier arrays");
+  const int R = p.R, G = p.fl_G, HW = p.HW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long N = (long long)p.B * HW;
-  unsigned long long* ctr = p.fl_ctr;  // [0] ticket (CONTRACT CTAs)  [1] stream-done  [2] slices-done
   const int t = blockIdx.x;
 
-  griddep_launch_dependents();  // the next launch may take free CTA slots from now on
-  if (!p.inputs_stable || p.attn_in != nullptr || p.attn_raw != nullptr) griddep_wait();
+  griddep_launch_dependents();  // REDUCE / CONTRACT of this call, then the next call's STREAM, may be scheduled
+  const bool wait_first = !p.inputs_stable || p.attn_in != nullptr || p.attn_raw != nullptr;
+  if (wait_first) griddep_wait();
 
-  if (t < G) {
-    // ========================================================================================= STREAM
-    const int row_lo = flow_row_lo(N, G, t), row_hi = flow_row_lo(N, G, t + 1);
-    const int b_first = row_lo / HW, b_last = (row_hi - 1) / HW;
-    if (tid == 0) {
-      for (int i = 0; i < kFStages; ++i) {
-        mbar_init(&full_bar[i], 1);
-        mbar_init(&empty_bar[i], kConsumerWarps);
-      }
-      fence_mbar_init();
+  const int row_lo = flow_row_lo(N, G, t), row_hi = flow_row_lo(N, G, t + 1);
+  const int b_first = row_lo / HW, b_last = (row_hi - 1) / HW;
+  if (tid == 0) {
+    for (int i = 0; i < kFStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kWPG);
     }
-    __syncthreads();
-    if (warp == kConsumerWarps) {
-      if (lane == 0) {
-        const uint64_t pol_x = l2_policy_evict_first();
-        uint32_t stage = 0, phase = 0;
-        for (int b = b_first; b <= b_last; ++b) {
-          const int lo = max(row_lo, b * HW), hi = min(row_hi, (b + 1) * HW);
-          const int nrows = hi - lo, ntiles = (nrows + TR - 1) / TR;
-          const float* xb = p.X + size_t(lo) * C;
-          for (int tt = 0; tt < ntiles; ++tt) {
-            const int rows = min(TR, nrows - tt * TR);
-            const uint32_t bytes = uint32_t(rows) * C * 4u;
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            bulk_g2s(smem + stage * kTileBytes, xb + size_t(tt) * TR * C, bytes, &full_bar[stage], pol_x);
-            if (++stage == kFStages) { stage = 0; phase ^= 1u; }
-          }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // =========================================================================== producer warp
+  if (warp == kConsumerWarps) {
+    if (lane == 0) {
+      const uint64_t pol_x = l2_policy_evict_first();
+      uint32_t stage = 0, phase = 0;
+      for (int b = b_first; b <= b_last; ++b) {
+        const int lo = max(row_lo, b * HW), hi = min(row_hi, (b + 1) * HW);
+        const int nrows = hi - lo, ntiles = (nrows + TR - 1) / TR;
+        const float* xb = p.X + size_t(lo) * C;
+        for (int tt = 0; tt < ntiles; ++tt) {
+          const int rows = min(TR, nrows - tt * TR);
+          const uint32_t bytes = uint32_t(rows) * C * 4u;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          bulk_g2s(smem + stage * kTileBytes, xb + size_t(tt) * TR * C, bytes, &full_bar[stage], pol_x);
+          if (++stage == kFStages) { stage = 0; phase ^= 1u; }
         }
-      }
-      return;
-    }
-    if (tid == 0 && p.ts != nullptr && t < 320) {
-      p.ts[size_t(t) * 64 + 0] = clock64();
-      p.ts[size_t(t) * 64 + 62] = fglobaltimer_ns();
-      unsigned int smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      p.ts[size_t(t) * 64 + 61] = smid;
-    }
-    const int col0 = warp * (C / kConsumerWarps) + lane * 4;  // + qq*128
-    float4 wv[Q];
-    float c0 = 0.f;
-    const float c_in = (p.attn_in != nullptr && p.attn_in_bias) ? __ldg(p.attn_b[0]) : 0.f;
-    if (p.attn_in == nullptr) {
-#pragma unroll
-      for (int qq = 0; qq < Q; ++qq) wv[qq] = __ldg(reinterpret_cast<const float4*>(p.attn_w[0] + col0 + qq * 128));
-      c0 = __ldg(p.attn_b[0]);
-    }
-    float cw[RMAX], cb[RMAX];
-#pragma unroll
-    for (int j = 0; j < RMAX; ++j) {
-      cw[j] = (j >= 1 && j < R) ? __ldg(p.attn_w[j]) : 0.f;
-      cb[j] = (j >= 1 && j < R) ? __ldg(p.attn_b[j]) : 0.f;
-    }
-    uint32_t stage = 0, phase = 0, flip = 0;
-    bool waited = false;
-    for (int b = b_first; b <= b_last; ++b) {
-      int gi = max(row_lo, b * HW);                       // running global row index of this image segment
-      int remaining = min(row_hi, (b + 1) * HW) - gi;     // rows left in it
-      float f[RMAX][Q * 4];
-      float s[RMAX];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < RMAX; ++j) {
-        s[j] = 0.f;
-#pragma unroll
-        for (int i = 0; i < Q * 4; ++i) f[j][i] = 0.f;
-      }
-      for (; remaining > 0; remaining -= TR, gi += TR, flip ^= 32u) {
-        const int rows = min(TR, remaining);
-        const bool full = (rows == TR);
-        const float* st = reinterpret_cast<const float*>(smem + stage * kTileBytes) + col0;
-        mbar_wait(&full_bar[stage], phase);
-        float4 x[TR][Q];
-        if (full) {
-#pragma unroll
-          for (int r = 0; r < TR; ++r)
-#pragma unroll
-            for (int qq = 0; qq < Q; ++qq) x[r][qq] = *reinterpret_cast<const float4*>(st + r * C + qq * 128);
-        } else {
-#pragma unroll
-          for (int r = 0; r < TR; ++r)
-#pragma unroll
-            for (int qq = 0; qq < Q; ++qq)
-              x[r][qq] = (r < rows) ? *reinterpret_cast<const float4*>(st + r * C + qq * 128)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float a[TR];
-        if (p.attn_in == nullptr) {
-          float pd[TR];
-#pragma unroll
-          for (int r = 0; r < TR; ++r) {
-            pd[r] = fdot4(x[r][0], wv[0]);
-#pragma unroll
-            for (int qq = 1; qq < Q; ++qq) pd[r] += fdot4(x[r][qq], wv[qq]);
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[stage]);
-          // 3 row sums per warp with one transposing butterfly: after it, lane 8r holds row r's warp sum
-          const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
-          float k0 = hi16 ? pd[2] : pd[0], s0 = hi16 ? pd[0] : pd[2];
-          float k1 = hi16 ? 0.f : pd[1], s1 = hi16 ? pd[1] : 0.f;
-          k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-          k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          float kk = hi8 ? k1 : k0;
-          const float ss = hi8 ? k0 : k1;
-          kk += __shfl_xor_sync(0xffffffffu, ss, 8);
-          kk += __shfl_xor_sync(0xffffffffu, kk, 4);
-          kk += __shfl_xor_sync(0xffffffffu, kk, 2);
-          kk += __shfl_xor_sync(0xffffffffu, kk, 1);
-          float* part = partS + flip;
-          if ((lane & 7) == 0) part[(lane >> 3) * 8 + warp] = kk;
-          named_bar_sync(1, kConsumerThreads);
-          float v = part[lane];
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-#pragma unroll
-          for (int r = 0; r < TR; ++r) a[r] = c0 + __shfl_sync(0xffffffffu, v, 8 * r);
-        } else {
-#pragma unroll
-          for (int r = 0; r < TR; ++r) {
-            float v = 0.f;
-            if (r < rows) {
-              v = c_in;
-              for (int pp = 0; pp < p.attn_in_parts; ++pp)
-                v += ldg_cg_f(p.attn_in + size_t(pp) * p.B * HW + size_t(gi + r));
-            }
-            a[r] = v;
-          }
-        }
-        if (p.attn_raw != nullptr && tid == 0) {
-#pragma unroll
-          for (int r = 0; r < TR; ++r)
-            if (r < rows) p.attn_raw[size_t(gi + r)] = a[r];
-        }
-        float valid[TR];
-#pragma unroll
-        for (int r = 0; r < TR; ++r) valid[r] = (full || r < rows) ? 1.f : 0.f;
-        if (MODE == MODE_SOFTMAX) {
-          float tmax = -INFINITY;
-#pragma unroll
-          for (int r = 0; r < TR; ++r) tmax = fmaxf(tmax, valid[r] != 0.f ? a[r] : -INFINITY);
-          const float mnew = fmaxf(mx, tmax);
-          const float sc = (mnew == -INFINITY) ? 1.f : expf(mx - mnew);
-          mx = mnew;
-          s[0] *= sc;
-#pragma unroll
-          for (int i = 0; i < Q * 4; ++i) f[0][i] *= sc;
-#pragma unroll
-          for (int r = 0; r < TR; ++r) {
-            const float e = valid[r] != 0.f ? expf(a[r] - mx) : 0.f;
-            s[0] += e;
-#pragma unroll
-            for (int qq = 0; qq < Q; ++qq) faxpy4(&f[0][qq * 4], e, x[r][qq]);
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < TR; ++r) {
-            float ar = a[r];
-#pragma unroll
-            for (int j = 0; j < RMAX; ++j) {
-              if (j < R) {
-                if (j >= 1) ar = fmaf(cw[j], ar, cb[j]);
-                const float A = ((MODE == MODE_RELU) ? fmaxf(ar, 0.f) : ar) * valid[r];
-                s[j] += A;
-#pragma unroll
-                for (int qq = 0; qq < Q; ++qq) faxpy4(&f[j][qq * 4], A, x[r][qq]);
-              }
-            }
-          }
-        }
-        if (p.attn_in != nullptr) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[stage]);
-        }
-        if (++stage == kFStages) { stage = 0; phase ^= 1u; }
-      }
-      // the previous launch (whose CONTRACT CTAs read this workspace) must have completely finished
-      if (!waited) {
-        if (tid == 0 && p.ts != nullptr && t < 320) p.ts[size_t(t) * 64 + 2] = clock64();
-        griddep_wait();
-        waited = true;
-        // everything before this call in the stream is complete: this rank no longer reads older gathered buffers
-        if (t == 0 && tid == 0 && p.gw_world > 0)
-          peer_gather_publish_started(p.gw_world, p.gw_rank, p.gw_flags, peer_gather_step(p.gw_done));
-      }
-      int e_lo, e_hi;                                  // STREAM CTAs holding rows of image b
-      flow_image_ctas(N, G, HW, b, &e_lo, &e_hi);
-      const bool whole = (e_lo == e_hi);               // the image lies inside this CTA's run: g[b] directly
-      if (whole && MODE == MODE_SOFTMAX) {
-        const float inv = 1.f / s[0];
-#pragma unroll
-        for (int i = 0; i < Q * 4; ++i) f[0][i] *= inv;
-      }
-      {
-        float* base_g = whole ? p.g + size_t(b) * R * C : p.gpart + size_t(t + b) * R * C;
-#pragma unroll
-        for (int j = 0; j < RMAX; ++j)
-          if (j < R) {
-            float* dst = base_g + size_t(j) * C + col0;
-#pragma unroll
-            for (int qq = 0; qq < Q; ++qq)
-              *reinterpret_cast<float4*>(dst + qq * 128) =
-                  make_float4(f[j][qq * 4 + 0], f[j][qq * 4 + 1], f[j][qq * 4 + 2], f[j][qq * 4 + 3]);
-          }
-      }
-      if (tid == 0) {
-        if (whole) {
-#pragma unroll
-          for (int j = 0; j < RMAX; ++j) p.gsum[size_t(b) * 4 + j] = (MODE == MODE_SOFTMAX) ? 1.f : s[j];
-          if (MODE == MODE_SOFTMAX && p.smx != nullptr) { p.smx[2 * b] = mx; p.smx[2 * b + 1] = s[0]; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < RMAX; ++j) p.gstat[size_t(t + b) * 8 + j] = s[j];
-          p.gstat[size_t(t + b) * 8 + 4] = mx;
-        }
-      }
-      if (!whole) {
-        // count this CTA in image b; the CTA that completes the image reduces its partials into g[b]
-        named_bar_sync(1, kConsumerThreads);
-        if (tid == 0) {
-          const unsigned long long cnt = (unsigned long long)(e_hi - e_lo + 1);
-          const unsigned long long prev = atom_add_acq_rel(p.fl_img + b, 1ull);
-          const bool last = ((prev & (kStride - 1)) == cnt - 1);
-          if (last) (void)atom_add_relaxed(p.fl_img + b, kStride - cnt);
-          *flag_s = last ? 1 : 0;
-        }
-        named_bar_sync(1, kConsumerThreads);
-        if (*flag_s) {
-          float M = 0.f, S = 1.f;
-          if (MODE == MODE_SOFTMAX) {
-            M = -INFINITY;
-            for (int e = e_lo; e <= e_hi; ++e) M = fmaxf(M, __ldcg(p.gstat + size_t(e + b) * 8 + 4));
-            S = 0.f;
-            for (int e = e_lo; e <= e_hi; ++e)
-              S += expf(__ldcg(p.gstat + size_t(e + b) * 8 + 4) - M) * __ldcg(p.gstat + size_t(e + b) * 8);
-          }
-#pragma unroll
-          for (int j = 0; j < RMAX; ++j)
-            if (j < R) {
-              float4 acc4[Q];
-#pragma unroll
-              for (int qq = 0; qq < Q; ++qq) acc4[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
-              const float* gp = p.gpart + (size_t(e_lo + b) * R + j) * C + col0;
-              const int nsl = e_hi - e_lo + 1;
-              for (int e0 = 0; e0 < nsl; e0 += 4) {
-                float4 gv[4][Q];
-                float sc[4];
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  const bool ok = (e0 + q4 < nsl);
-#pragma unroll
-                  for (int qq = 0; qq < Q; ++qq)
-                    gv[q4][qq] = ok ? __ldcg(reinterpret_cast<const float4*>(gp + size_t(e0 + q4) * R * C + qq * 128))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                  sc[q4] = 1.f;
-                  if (MODE == MODE_SOFTMAX && ok)
-                    sc[q4] = expf(__ldcg(p.gstat + size_t(e_lo + b + e0 + q4) * 8 + 4) - M) / S;
-                }
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-#pragma unroll
-                  for (int qq = 0; qq < Q; ++qq) {
-                    acc4[qq].x = fmaf(sc[q4], gv[q4][qq].x, acc4[qq].x);
-                    acc4[qq].y = fmaf(sc[q4], gv[q4][qq].y, acc4[qq].y);
-                    acc4[qq].z = fmaf(sc[q4], gv[q4][qq].z, acc4[qq].z);
-                    acc4[qq].w = fmaf(sc[q4], gv[q4][qq].w, acc4[qq].w);
-                  }
-              }
-              float* dst = p.g + (size_t(b) * R + j) * C + col0;
-#pragma unroll
-              for (int qq = 0; qq < Q; ++qq) *reinterpret_cast<float4*>(dst + qq * 128) = acc4[qq];
-            }
-          if (tid < RMAX) {
-            float mass = 1.f;
-            if (MODE != MODE_SOFTMAX) {
-              mass = 0.f;
-              if (tid < R)
-                for (int e = e_lo; e <= e_hi; ++e) mass += __ldcg(p.gstat + size_t(e + b) * 8 + tid);
-            }
-            p.gsum[size_t(b) * 4 + tid] = mass;
-          }
-          if (MODE == MODE_SOFTMAX && p.smx != nullptr && tid == 0) { p.smx[2 * b] = M; p.smx[2 * b + 1] = S; }
-        }
-      }
-    }
-    named_bar_sync(1, kConsumerThreads);  // every consumer's stores (partials, completed images) are issued
-    if (tid == 0) {
-      (void)atom_add_acq_rel(ctr + 1, 1ull);  // release: they are visible to whoever sees the count
-      if (p.ts != nullptr && t < 320) {
-        p.ts[size_t(t) * 64 + 5] = clock64();
-        p.ts[size_t(t) * 64 + 63] = fglobaltimer_ns();
       }
     }
     return;
   }
-
-  // =========================================================================================== CONTRACT
-  if (warp == kConsumerWarps) return;  // 256 threads do the contraction
-  const int NS = p.fl_NS, U = kNJ * NS;
-  if (tid == 0) {  // ticket: which launch this is (base) and which unit I am
-    const unsigned long long prev = atom_add_relaxed(ctr + 0, 1ull);
-    if ((prev & (kStride - 1)) == (unsigned long long)(U - 1))  // last ticket: pad to the next multiple
-      (void)atom_add_relaxed(ctr + 0, kStride - (unsigned long long)U);
-    *tick_s = prev;
+  if (tid == 0 && p.ts != nullptr && t < 160) {
+    p.ts[size_t(t) * 64 + 0] = clock64();
+    p.ts[size_t(t) * 64 + 62] = fglobaltimer_ns();
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.ts[size_t(t) * 64 + 61] = smid;
   }
-  named_bar_sync(1, kConsumerThreads);
-  const unsigned long long base = *tick_s & ~(kStride - 1);   // = launch index * 2^20
-  const int u = int(*tick_s & (kStride - 1));                 // unit: channel slice cj (fastest), class slice sl
+
+  // =========================================================================== consumers: two groups of 4 warps;
+  // group g takes the CTA's tiles g, g + 2, ... and keeps its own partial sums (slot 2 (CTA + image) + g)
+  const int grp = warp / kWPG, wig = warp % kWPG, gtid = tid - grp * (kWPG * 32);
+  const int col0 = wig * (C / kWPG) + lane * 4;  // + qq*128
+  float4 wv[QT];
+  float c0 = 0.f;
+  const float c_in = (p.attn_in != nullptr && p.attn_in_bias) ? __ldg(p.attn_b[0]) : 0.f;
+  if (p.attn_in == nullptr) {
+#pragma unroll
+    for (int qq = 0; qq < QT; ++qq) wv[qq] = __ldg(reinterpret_cast<const float4*>(p.attn_w[0] + col0 + qq * 128));
+    c0 = __ldg(p.attn_b[0]);
+  }
+  float cw[RMAX], cb[RMAX];
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) {
+    cw[j] = (j >= 1 && j < R) ? __ldg(p.attn_w[j]) : 0.f;
+    cb[j] = (j >= 1 && j < R) ? __ldg(p.attn_b[j]) : 0.f;
+  }
+  float* part0 = partS + grp * 32;
+  const int stage_cap = int(kStageBytes / (size_t(R) * kNG * C * 4));   // image segments that fit the staging area
+  uint32_t tile0 = 0, flip = 0;       // index (within the CTA) of the current segment's first tile
+  int staged = 0;
+  bool waited = wait_first;
+  for (int b = b_first; b <= b_last; ++b) {
+    const int seg_lo = max(row_lo, b * HW);
+    const int nrows = min(row_hi, (b + 1) * HW) - seg_lo;
+    const uint32_t ntiles = uint32_t(nrows + TR - 1) / TR;
+    float f[RMAX][QT * 4];
+    float s[RMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      s[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < QT * 4; ++i) f[j][i] = 0.f;
+    }
+    // my first tile of this segment: the smallest i >= tile0 with i % 2 == grp
+    for (uint32_t i = tile0 + ((tile0 ^ uint32_t(grp)) & 1u); i < tile0 + ntiles; i += kNG, flip ^= 16u) {
+      const uint32_t stage = i % kFStages, phase = (i / kFStages) & 1u;
+      const int off = int(i - tile0) * TR;
+      const int rows = min(TR, nrows - off);
+      const int gi = seg_lo + off;
+      const bool full = (rows == TR);
+      const float* st = reinterpret_cast<const float*>(smem + stage * kTileBytes) + col0;
+      mbar_wait(&full_bar[stage], phase);
+      float4 x[TR][QT];
+      if (full) {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+          for (int qq = 0; qq < QT; ++qq) x[r][qq] = *reinterpret_cast<const float4*>(st + r * C + qq * 128);
+      } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+          for (int qq = 0; qq < QT; ++qq)
+            x[r][qq] = (r < rows) ? *reinterpret_cast<const float4*>(st + r * C + qq * 128)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float a[TR];
+      if (p.attn_in == nullptr) {
+        float pd[TR];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          pd[r] = fdot4(x[r][0], wv[0]);
+#pragma unroll
+          for (int qq = 1; qq < QT; ++qq) pd[r] += fdot4(x[r][qq], wv[qq]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        // 3 row sums per warp with one transposing butterfly: after it, lane 8r holds row r's warp sum
+        const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+        float k0 = hi16 ? pd[2] : pd[0], s0 = hi16 ? pd[0] : pd[2];
+        float k1 = hi16 ? 0.f : pd[1], s1 = hi16 ? pd[1] : 0.f;
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        float kk = hi8 ? k1 : k0;
+        const float ss = hi8 ? k0 : k1;
+        kk += __shfl_xor_sync(0xffffffffu, ss, 8);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+        float* part = part0 + flip;
+        if ((lane & 7) == 0) part[(lane >> 3) * kWPG + wig] = kk;      // [row][warp of the group]
+        if (grp == 0) named_bar_sync(1, kWPG * 32);
+        else named_bar_sync(2, kWPG * 32);
+        float v = (lane < TR * kWPG) ? part[lane] : 0.f;
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+#pragma unroll
+        for (int r = 0; r < TR; ++r) a[r] = c0 + __shfl_sync(0xffffffffu, v, kWPG * r);
+      } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          float v = 0.f;
+          if (r < rows) {
+            v = c_in;
+            for (int pp = 0; pp < p.attn_in_parts; ++pp)
+              v += ldg_cg_f(p.attn_in + size_t(pp) * p.B * HW + size_t(gi + r));
+          }
+          a[r] = v;
+        }
+      }
+      if (p.attn_raw != nullptr && gtid == 0) {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+          if (r < rows) p.attn_raw[size_t(gi + r)] = a[r];
+      }
+      float valid[TR];
+#pragma unroll
+      for (int r = 0; r < TR; ++r) valid[r] = (full || r < rows) ? 1.f : 0.f;
+      if (MODE == MODE_SOFTMAX) {
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < TR; ++r) tmax = fmaxf(tmax, valid[r] != 0.f ? a[r] : -INFINITY);
+        const float mnew = fmaxf(mx, tmax);
+        const float sc = (mnew == -INFINITY) ? 1.f : expf(mx - mnew);
+        mx = mnew;
+        s[0] *= sc;
+#pragma unroll
+        for (int i = 0; i < QT * 4; ++i) f[0][i] *= sc;
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          const float e = valid[r] != 0.f ? expf(a[r] - mx) : 0.f;
+          s[0] += e;
+#pragma unroll
+          for (int qq = 0; qq < QT; ++qq) faxpy4(&f[0][qq * 4], e, x[r][qq]);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          float ar = a[r];
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) {
+            if (j < R) {
+              if (j >= 1) ar = fmaf(cw[j], ar, cb[j]);
+              const float A = ((MODE == MODE_RELU) ? fmaxf(ar, 0.f) : ar) * valid[r];
+              s[j] += A;
+#pragma unroll
+              for (int qq = 0; qq < QT; ++qq) faxpy4(&f[j][qq * 4], A, x[r][qq]);
+            }
+          }
+        }
+      }
+      if (p.attn_in != nullptr) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      }
+    }
+    tile0 += ntiles;
+    // ---- this group's partial of image b.  Non-final segments wait in shared memory (the CTA must not stall in
+    //      the middle of its stream); the last one stays in registers; everything is flushed after the wait below.
+    const bool last_seg = (b == b_last);
+    if (!last_seg && !waited && staged < stage_cap) {
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j)
+        if (j < R) {
+          float* dst = stg + ((size_t(staged) * R + j) * kNG + grp) * C + col0;
+#pragma unroll
+          for (int qq = 0; qq < QT; ++qq)
+            *reinterpret_cast<float4*>(dst + qq * 128) =
+                make_float4(f[j][qq * 4 + 0], f[j][qq * 4 + 1], f[j][qq * 4 + 2], f[j][qq * 4 + 3]);
+        }
+      if (gtid == 0) {
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) stgstat[(staged * kNG + grp) * 8 + j] = s[j];
+        stgstat[(staged * kNG + grp) * 8 + 4] = mx;
+      }
+      ++staged;
+      continue;
+    }
+    // the previous CONTRACT launch (which reads the workspace through REDUCE's output... and REDUCE itself) must
+    // have completely finished before the first global write of this launch
+    if (!waited) {
+      if (tid == 0 && p.ts != nullptr && t < 160) p.ts[size_t(t) * 64 + 2] = clock64();
+      griddep_wait();
+      waited = true;
+    }
+    for (int k = 0; k < staged; ++k) {   // flush what waited in shared memory (my own values: no barrier needed)
+      const int slot = 2 * (t + b_first + k) + grp;
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j)
+        if (j < R) {
+          const float* src = stg + ((size_t(k) * R + j) * kNG + grp) * C + col0;
+          float* dst = p.gpart + (size_t(slot) * R + j) * C + col0;
+#pragma unroll
+          for (int qq = 0; qq < QT; ++qq)
+            *reinterpret_cast<float4*>(dst + qq * 128) = *reinterpret_cast<const float4*>(src + qq * 128);
+        }
+      if (gtid == 0) {
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) p.gstat[size_t(slot) * 8 + j] = stgstat[(k * kNG + grp) * 8 + j];
+        p.gstat[size_t(slot) * 8 + 4] = stgstat[(k * kNG + grp) * 8 + 4];
+      }
+    }
+    staged = 0;
+    const int slot = 2 * (t + b) + grp;
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j)
+      if (j < R) {
+        float* dst = p.gpart + (size_t(slot) * R + j) * C + col0;
+#pragma unroll
+        for (int qq = 0; qq < QT; ++qq)
+          *reinterpret_cast<float4*>(dst + qq * 128) =
+              make_float4(f[j][qq * 4 + 0], f[j][qq * 4 + 1], f[j][qq * 4 + 2], f[j][qq * 4 + 3]);
+      }
+    if (gtid == 0) {
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) p.gstat[size_t(slot) * 8 + j] = s[j];
+      p.gstat[size_t(slot) * 8 + 4] = mx;
+    }
+  }
+  if (tid == 0) {
+    // everything before this call in the stream is complete: this rank no longer reads older gathered buffers
+    if (t == 0 && p.gw_world > 0)
+      peer_gather_publish_started(p.gw_world, p.gw_rank, p.gw_flags, peer_gather_step(p.gw_done));
+    if (p.ts != nullptr && t < 160) {
+      p.ts[size_t(t) * 64 + 5] = clock64();
+      p.ts[size_t(t) * 64 + 63] = fglobaltimer_ns();
+    }
+  }
+}
+
+// ================================================================================================ REDUCE
+template <bool SOFTMAX>
+__global__ void __launch_bounds__(kRThreads, 8)
+apa_flow_reduce_kernel(const FusedParams p) {
+  __shared__ float scl[320];   // per partial of this image: softmax scale exp(m_e - M) / S (1 otherwise)
+  const int R = p.R, G = p.fl_G, HW = p.HW, C = p.C;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int c = (blockIdx.y * kRThreads + tid) * 4;
+  const long long N = (long long)p.B * HW;
+  griddep_launch_dependents();
+  griddep_wait();   // STREAM of this call has finished and its partial g / stats are visible
+  int lo, hi;
+  flow_image_ctas(N, G, HW, b, &lo, &hi);
+  const int n = kNG * (hi - lo + 1), s0 = kNG * (lo + b);   // partials of image b (runs x consumer groups), first slot
+  if (SOFTMAX) {
+    float M = -INFINITY;
+    for (int e = 0; e < n; ++e) M = fmaxf(M, __ldcg(p.gstat + size_t(s0 + e) * 8 + 4));
+    float S = 0.f;
+    for (int e = 0; e < n; ++e) S += expf(__ldcg(p.gstat + size_t(s0 + e) * 8 + 4) - M) * __ldcg(p.gstat + size_t(s0 + e) * 8);
+    for (int e = tid; e < n; e += kRThreads) scl[e] = expf(__ldcg(p.gstat + size_t(s0 + e) * 8 + 4) - M) / S;
+    if (tid == 0 && blockIdx.y == 0) {
+      p.gsum[size_t(b) * 4] = 1.f;
+      if (p.smx != nullptr) { p.smx[2 * b] = M; p.smx[2 * b + 1] = S; }
+    }
+    __syncthreads();
+  } else if (tid < 4 && blockIdx.y == 0) {
+    float mass = 0.f;
+    if (tid < R)
+      for (int e = 0; e < n; ++e) mass += __ldcg(p.gstat + size_t(s0 + e) * 8 + tid);
+    p.gsum[size_t(b) * 4 + tid] = mass;
+  }
+  if (c < C) {
+    for (int j = 0; j < R; ++j) {
+      const float* gp = p.gpart + (size_t(s0) * R + j) * C + c;
+      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e0 = 0; e0 < n; e0 += 8) {   // eight loads in flight, added in run order
+        float4 gv[8];
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8)
+          gv[q8] = (e0 + q8 < n) ? __ldcg(reinterpret_cast<const float4*>(gp + size_t(e0 + q8) * R * C))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) {
+          const float sc = (SOFTMAX && e0 + q8 < n) ? scl[e0 + q8] : 1.f;
+          a4.x = fmaf(sc, gv[q8].x, a4.x);
+          a4.y = fmaf(sc, gv[q8].y, a4.y);
+          a4.z = fmaf(sc, gv[q8].z, a4.z);
+          a4.w = fmaf(sc, gv[q8].w, a4.w);
+        }
+      }
+      *reinterpret_cast<float4*>(p.g + (size_t(b) * R + j) * C + c) = a4;
+    }
+  }
+}
+
+// ================================================================================================ CONTRACT
+__host__ __device__ inline size_t contract_smem_bytes(int C) {
+  const int CH = C / kNJ;
+  return size_t(CH) * kKW * 4 + size_t(kVideoTile) * (CH + kGPad) * 4 + kVideoTile * 4 * 4 + 64;
+}
+
+template <int Q>
+__global__ void __launch_bounds__(kCThreads, 6)
+apa_flow_contract_kernel(const FusedParams p) {
+  constexpr int C = Q * 1024, CH = C / kNJ, GS = CH + kGPad;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* Ws = reinterpret_cast<float*>(smem);       // [CH][kKW]   block of B_r
+  float* gs = Ws + CH * kKW;                        // [32 videos][GS]; later red[2][32][kKW]
+  float* sS = gs + kVideoTile * GS;                 // [32 videos][4] attention mass per rank
+  unsigned long long* step_s = reinterpret_cast<unsigned long long*>(sS + kVideoTile * 4);
+  int* flag_s = reinterpret_cast<int*>(step_s + 1);
+  const int R = p.R, K = p.K, F = p.F, NS = p.fl_NS;
+  const int tid = threadIdx.x;
+  const int u = blockIdx.x;            // unit: channel slice cj (fastest), class slice sl
   const int cj = u % kNJ, sl = u / kNJ;
   const int k_lo = int((long long)K * sl / NS), k_hi = int((long long)K * (sl + 1) / NS);
   const int width = k_hi - k_lo;       // <= kKW
   const int c_base = cj * CH;
   const int Bv = p.B / F;
   const int ntile = (Bv + kVideoTile - 1) / kVideoTile;
-  constexpr int GS = CH + kGPad;
-  float* Ws = reinterpret_cast<float*>(smem);       // [CH][kKW]
-  float* gs = Ws + CH * kKW;                        // [32 videos][GS]; later red[4][32][kKW]
-  float* sS = gs + kVideoTile * GS;                 // [32 videos][4] attention mass per rank
   const int ts_row = 160 + u;
+
+  griddep_launch_dependents();  // the next call's STREAM may start right away
+  if (!p.inputs_stable) griddep_wait();
   if (tid == 0 && p.ts != nullptr && ts_row < 320) {
     p.ts[size_t(ts_row) * 64 + 0] = clock64();
     p.ts[size_t(ts_row) * 64 + 62] = fglobaltimer_ns();
   }
   auto load_w = [&](int j) {
     const float* W = p.td_w[j];
-    for (int idx = tid; idx < CH * kKW; idx += kConsumerThreads) {
+    for (int idx = tid; idx < CH * kKW; idx += kCThreads) {
       const int c = idx / kKW, kk = idx - c * kKW;
       Ws[idx] = (kk < width) ? __ldg(W + size_t(c_base + c) * K + k_lo + kk) : 0.f;
     }
   };
-  load_w(0);  // does not depend on the STREAM CTAs
-  if (tid == 0) {  // wait until all G STREAM CTAs of THIS launch have published their images
-    const unsigned long long target = base + (unsigned long long)G;
-    const long long t0 = clock64();
-    while (ld_acquire(ctr + 1) < target) {
-      __nanosleep(32);
-      if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
-    }
-  }
-  named_bar_sync(1, kConsumerThreads);
+  load_w(0);        // does not depend on this call's STREAM / REDUCE
+  griddep_wait();   // REDUCE (and so STREAM) of this call has finished: g[b] and gsum[b] are visible
   if (tid == 0 && p.ts != nullptr && ts_row < 320) p.ts[size_t(ts_row) * 64 + 1] = clock64();
-  griddep_wait();  // previous launch complete (it is: this launch's STREAM CTAs waited for it) before any global write
 
-  // thread tile of the contraction: 4 videos x 4 classes, one quarter of the unit's channels
-  const int ks = warp >> 1;                    // channel quarter
+  // thread tile of the contraction: 4 videos x 4 classes, one half of the unit's channels
+  const int ks = tid >> 6;                       // channel half
   const int vr = (tid & 63) >> 3, cq = tid & 7;  // video group (4 videos), class group (4 classes)
+  constexpr int NP = kVideoTile * (CH / 4) / kCThreads;   // float4s of g per thread and rank (8, or 4 for C = 1024)
   for (int tile = 0; tile < ntile; ++tile) {
     const int v0 = tile * kVideoTile;
-    if (tile != 0) named_bar_sync(1, kConsumerThreads);  // sS / red of the previous tile fully consumed
-    if (tid < kVideoTile * 4) {  // attention mass per (video, rank): sum over frames
+    if (tile != 0) __syncthreads();  // sS / red of the previous tile fully consumed
+    if (tid < kVideoTile * 4) {      // attention mass per (video, rank): sum over frames
       const int vi = tid >> 2, j = tid & 3, v = v0 + vi;
       float mass = 0.f;
       if (v < Bv && j < R)
@@ -478,49 +492,43 @@ apa_flow_kernel(const FusedParams p) {
       for (int m = 0; m < 4; ++m) acc[i][m] = 0.f;
     for (int j = 0; j < R; ++j) {
       if (j != 0 || tile != 0) {
-        named_bar_sync(1, kConsumerThreads);  // previous operands fully consumed
-        if (R > 1) load_w(j);                 // rank 1: the block loaded before the wait stays valid (red aliases gs only)
+        __syncthreads();                      // previous operands fully consumed
+        if (R > 1) load_w(j);                 // rank 1: the block loaded before the wait stays valid
       }
-      // ---- operand g: this unit's channels of 32 videos, frames summed.  thread = (video, 4 channels), CH / 32 of them,
-      //      four loads in flight at a time
-      constexpr int NP = CH / 32;
+      // ---- operand g: this unit's channels of 32 videos, frames summed.  thread = (video, 4 channels); all NP
+      //      loads of a frame in flight together
 #pragma unroll
-      for (int h = 0; h < NP; h += 4) {
-        float4 a4[4];
-        const float* gp[4];
+      for (int h0 = 0; h0 < NP; h0 += NP) {
+        float4 a4[NP];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int idx = tid + (h + q4) * kConsumerThreads;
-          const int vi = idx / (CH / 4), c4 = idx - vi * (CH / 4);
-          a4[q4] = make_float4(0.f, 0.f, 0.f, 0.f);
-          gp[q4] = (v0 + vi < Bv) ? p.g + (size_t(v0 + vi) * F * R + j) * C + c_base + c4 * 4 : nullptr;
-        }
+        for (int h = 0; h < NP; ++h) a4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int fr = 0; fr < F; ++fr) {
-          float4 gv[4];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            gv[q4] = (gp[q4] != nullptr) ? __ldcg(reinterpret_cast<const float4*>(gp[q4] + size_t(fr) * R * C))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            a4[q4].x += gv[q4].x; a4[q4].y += gv[q4].y; a4[q4].z += gv[q4].z; a4[q4].w += gv[q4].w;
+          for (int h = 0; h < NP; ++h) {
+            const int idx = tid + (h0 + h) * kCThreads;
+            const int vi = idx / (CH / 4), c4 = idx - vi * (CH / 4);
+            if (v0 + vi < Bv) {
+              const float4 gv = __ldcg(reinterpret_cast<const float4*>(
+                  p.g + ((size_t(v0 + vi) * F + fr) * R + j) * C + c_base + c4 * 4));
+              a4[h].x += gv.x; a4[h].y += gv.y; a4[h].z += gv.z; a4[h].w += gv.w;
+            }
           }
         }
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int idx = tid + (h + q4) * kConsumerThreads;
+        for (int h = 0; h < NP; ++h) {
+          const int idx = tid + (h0 + h) * kCThreads;
           const int vi = idx / (CH / 4), c4 = idx - vi * (CH / 4);
-          *reinterpret_cast<float4*>(gs + vi * GS + c4 * 4) = a4[q4];
+          *reinterpret_cast<float4*>(gs + vi * GS + c4 * 4) = a4[h];
         }
       }
-      named_bar_sync(1, kConsumerThreads);
+      __syncthreads();
       if (tid == 0 && tile == 0 && j == 0 && p.ts != nullptr && ts_row < 320) p.ts[size_t(ts_row) * 64 + 2] = clock64();
-      // ---- contraction: acc[i][m] += g[4 vr + i][c] * W[c][4 cq + m] over this thread's channel quarter
+      // ---- contraction: acc[i][m] += g[4 vr + i][c] * W[c][4 cq + m] over this thread's channel half
       {
-        const float* g0 = gs + (vr * 4) * GS + ks * (CH / 4);
-        const float* w0 = Ws + (ks * (CH / 4)) * kKW + cq * 4;
+        const float* g0 = gs + (vr * 4) * GS + ks * (CH / 2);
+        const float* w0 = Ws + (ks * (CH / 2)) * kKW + cq * 4;
 #pragma unroll 2
-        for (int c = 0; c < CH / 4; c += 4) {
+        for (int c = 0; c < CH / 2; c += 4) {
           float4 gv[4], wv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) gv[i] = *reinterpret_cast<const float4*>(g0 + i * GS + c);
@@ -540,80 +548,88 @@ apa_flow_kernel(const FusedParams p) {
         }
       }
     }
-    // ---- the four channel quarters meet in shared memory (red aliases gs), fixed order
-    named_bar_sync(1, kConsumerThreads);
-    float* red = gs;  // [4][32 videos][kKW]
+    // ---- the two channel halves meet in shared memory (red aliases gs), fixed order
+    __syncthreads();
+    float* red = gs;  // [2][32 videos][kKW]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(red + (ks * kVideoTile + vr * 4 + i) * kKW + cq * 4) =
           make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    named_bar_sync(1, kConsumerThreads);
+    __syncthreads();
     const int cslot = tile * NS + sl;
-    {
-      float4 r0 = *reinterpret_cast<const float4*>(red + tid * 4);
+    float* cp = p.cpart + (size_t(cslot) * kNJ + cj) * (kVideoTile * kKW);
 #pragma unroll
-      for (int q4 = 1; q4 < 4; ++q4) {
-        const float4 rq = *reinterpret_cast<const float4*>(red + q4 * kVideoTile * kKW + tid * 4);
-        r0.x += rq.x; r0.y += rq.y; r0.z += rq.z; r0.w += rq.w;
-      }
-      *reinterpret_cast<float4*>(p.cpart + (size_t(cslot) * kNJ + cj) * (kVideoTile * kKW) + tid * 4) = r0;
+    for (int h = 0; h < 2; ++h) {
+      const int o = (tid + h * kCThreads) * 4;
+      float4 r0 = *reinterpret_cast<const float4*>(red + o);
+      const float4 r1 = *reinterpret_cast<const float4*>(red + kVideoTile * kKW + o);
+      r0.x += r1.x; r0.y += r1.y; r0.z += r1.z; r0.w += r1.w;
+      *reinterpret_cast<float4*>(cp + o) = r0;
     }
-    named_bar_sync(1, kConsumerThreads);
+    __syncthreads();
     if (tid == 0) {
       const unsigned long long prev = atom_add_acq_rel(p.fl_arr + cslot, 1ull);
       *flag_s = ((prev + 1) % kNJ == 0) ? 1 : 0;
       if (tile == 0 && p.ts != nullptr && ts_row < 320) p.ts[size_t(ts_row) * 64 + 3] = clock64();
     }
-    named_bar_sync(1, kConsumerThreads);
+    __syncthreads();
     if (*flag_s) {
-      // ---- 8th arrival for this (tile, class slice): fixed-order sum of the 8 partial blocks, bias, logits
-      const float* cb0 = p.cpart + size_t(cslot) * kNJ * (kVideoTile * kKW) + tid * 4;
-      float4 pv[kNJ];
-#pragma unroll
-      for (int c = 0; c < kNJ; ++c) pv[c] = __ldcg(reinterpret_cast<const float4*>(cb0 + size_t(c) * (kVideoTile * kKW)));
-      float sum[4] = {pv[0].x, pv[0].y, pv[0].z, pv[0].w};
-#pragma unroll
-      for (int c = 1; c < kNJ; ++c) { sum[0] += pv[c].x; sum[1] += pv[c].y; sum[2] += pv[c].z; sum[3] += pv[c].w; }
-      const int vi = (tid * 4) / kKW, kk0 = (tid * 4) % kKW;
-      const int v = v0 + vi;
+      // ---- 16th arrival for this (tile, class slice): fixed-order sum of the 16 partial blocks, bias, logits
       size_t gw_off = 0;
       if (p.gw_world > 0) {  // this step's ring buffer must be free on every peer (they started step - depth + 1)
         if (tid == 0) {
           const unsigned long long step = peer_gather_step(p.gw_done);
           if (p.gw_world > 1 && step >= (unsigned long long)p.gw_depth)
             peer_gather_wait_all(p.gw_world, p.gw_flags[p.gw_rank], p.gw_world, step - p.gw_depth + 1);
-          *tick_s = step;
+          *step_s = step;
         }
-        named_bar_sync(1, kConsumerThreads);
-        gw_off = size_t(*tick_s % (unsigned long long)p.gw_depth) * size_t(p.gw_world) * Bv * K;
+        __syncthreads();
+        gw_off = size_t(*step_s % (unsigned long long)p.gw_depth) * size_t(p.gw_world) * Bv * K;
       }
-      if (v < Bv) {
+      const float* cb0 = p.cpart + size_t(cslot) * kNJ * (kVideoTile * kKW);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int kk = kk0 + m, k = k_lo + kk;
-          if (kk < width) {
-            float val = sum[m];
-            for (int j = 0; j < R; ++j) val = fmaf(__ldg(p.td_b[j] + k), sS[vi * 4 + j], val);
-            val *= p.inv_scale;
-            if (p.gw_world > 0) {
-              const size_t off = gw_off + (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
-              for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
-            } else {
-              p.logits[size_t(v) * K + k] = val;
+      for (int h = 0; h < 2; ++h) {
+        const int o = (tid + h * kCThreads) * 4;
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c0 = 0; c0 < kNJ; c0 += 8) {   // eight loads in flight at a time, summed in index order
+          float4 pv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            pv[c] = __ldcg(reinterpret_cast<const float4*>(cb0 + size_t(c0 + c) * (kVideoTile * kKW) + o));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { sum[0] += pv[c].x; sum[1] += pv[c].y; sum[2] += pv[c].z; sum[3] += pv[c].w; }
+        }
+        const int vi = o / kKW, kk0 = o % kKW;
+        const int v = v0 + vi;
+        if (v < Bv) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int kk = kk0 + m, k = k_lo + kk;
+            if (kk < width) {
+              float val = sum[m];
+              for (int j = 0; j < R; ++j) val = fmaf(__ldg(p.td_b[j] + k), sS[vi * 4 + j], val);
+              val *= p.inv_scale;
+              if (p.gw_world > 0) {
+                const size_t off = gw_off + (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
+                for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
+              } else {
+                p.logits[size_t(v) * K + k] = val;
+              }
             }
           }
         }
       }
-      if (p.gw_world > 1) __threadfence_system();  // my peer stores are visible system-wide before I am counted
-      named_bar_sync(1, kConsumerThreads);
-      if (tid == 0) {
-        const unsigned long long prev2 = atom_add_acq_rel(ctr + 2, 1ull);
-        const unsigned long long nslices = (unsigned long long)ntile * NS;
-        if ((prev2 & (kStride - 1)) == nslices - 1) {
-          // the launch's last logits are stored: pad the two per-launch counters to the next multiple
-          (void)atom_add_relaxed(ctr + 2, kStride - nslices);
-          (void)atom_add_acq_rel(ctr + 1, kStride - (unsigned long long)G);
-          if (p.gw_world > 0) peer_gather_complete(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, *tick_s);
+      if (p.gw_world > 0) {
+        if (p.gw_world > 1) __threadfence_system();  // my peer stores are visible system-wide before I am counted
+        __syncthreads();
+        if (tid == 0) {
+          const unsigned long long prev2 = atom_add_acq_rel(p.fl_ctr + 2, 1ull);
+          const unsigned long long nslices = (unsigned long long)ntile * NS;
+          if ((prev2 & (kStride - 1)) == nslices - 1) {  // the launch's last logits are stored: complete the step
+            (void)atom_add_relaxed(p.fl_ctr + 2, kStride - nslices);
+            peer_gather_complete(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, *step_s);
+          }
         }
       }
     }
@@ -626,26 +642,31 @@ apa_flow_kernel(const FusedParams p) {
 
 using FKernelFn = void (*)(const FusedParams);
 
-FKernelFn flow_select(int Q, int rmax, int mode) {
+FKernelFn flow_stream_select(int Q, int rmax, int mode) {
   if (Q == 2) {
     if (rmax == 1) {
-      if (mode == MODE_PLAIN) return &apa_flow_kernel<2, 1, MODE_PLAIN>;
-      if (mode == MODE_RELU) return &apa_flow_kernel<2, 1, MODE_RELU>;
-      return &apa_flow_kernel<2, 1, MODE_SOFTMAX>;
+      if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<2, 1, MODE_PLAIN>;
+      if (mode == MODE_RELU) return &apa_flow_stream_kernel<2, 1, MODE_RELU>;
+      return &apa_flow_stream_kernel<2, 1, MODE_SOFTMAX>;
     }
-    if (mode == MODE_PLAIN) return &apa_flow_kernel<2, APA_MAX_RANK, MODE_PLAIN>;
-    if (mode == MODE_RELU) return &apa_flow_kernel<2, APA_MAX_RANK, MODE_RELU>;
+    if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<2, APA_MAX_RANK, MODE_PLAIN>;
+    if (mode == MODE_RELU) return &apa_flow_stream_kernel<2, APA_MAX_RANK, MODE_RELU>;
     return nullptr;
   }
   if (Q == 1) {
     if (rmax == 1) {
-      if (mode == MODE_PLAIN) return &apa_flow_kernel<1, 1, MODE_PLAIN>;
-      if (mode == MODE_RELU) return &apa_flow_kernel<1, 1, MODE_RELU>;
-      return &apa_flow_kernel<1, 1, MODE_SOFTMAX>;
+      if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<1, 1, MODE_PLAIN>;
+      if (mode == MODE_RELU) return &apa_flow_stream_kernel<1, 1, MODE_RELU>;
+      return &apa_flow_stream_kernel<1, 1, MODE_SOFTMAX>;
     }
-    if (mode == MODE_PLAIN) return &apa_flow_kernel<1, APA_MAX_RANK, MODE_PLAIN>;
-    if (mode == MODE_RELU) return &apa_flow_kernel<1, APA_MAX_RANK, MODE_RELU>;
+    if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<1, APA_MAX_RANK, MODE_PLAIN>;
+    if (mode == MODE_RELU) return &apa_flow_stream_kernel<1, APA_MAX_RANK, MODE_RELU>;
   }
+  return nullptr;
+}
+FKernelFn flow_contract_select(int Q) {
+  if (Q == 2) return &apa_flow_contract_kernel<2>;
+  if (Q == 1) return &apa_flow_contract_kernel<1>;
   return nullptr;
 }
 
@@ -674,6 +695,7 @@ cudaError_t flow_prepare(const void* fn, size_t smem) {
 }  // namespace
 
 int flow_class_slices(int K) { return (K + kKW - 1) / kKW; }
+int flow_contract_grid(int K) { return kNJ * flow_class_slices(K); }
 
 int flow_stream_ctas(int B, int HW, const ApaTuning* tuning) {
   long long n = (long long)B * HW;
@@ -685,43 +707,65 @@ int flow_stream_ctas(int B, int HW, const ApaTuning* tuning) {
 
 bool flow_eligible(int B, int HW, int C, int K, int R, int F) {
   if (!((C == 1024 || C == 2048) && R >= 1 && R <= APA_MAX_RANK && F >= 1 && B % F == 0 && HW >= 1)) return false;
-  const long long slices = (long long)flow_slices(B, K, F);
-  return slices < (long long)kStride / 2 && (long long)kNJ * flow_class_slices(K) < 60000;
+  return (long long)flow_slices(B, K, F) < (long long)kStride / 2 && flow_contract_grid(K) <= 65535;
 }
 
-size_t flow_gpart_slots(int B) { return size_t(kFlowStreamCtas) + size_t(B); }
+size_t flow_gpart_slots(int B) { return kNG * (size_t(kFlowStreamCtas) + size_t(B)); }
 size_t flow_slices(int B, int K, int F) {  // (video tile, class slice) pairs = arrival counters
   const int ntile = (B / F + kVideoTile - 1) / kVideoTile;
   return size_t(ntile) * flow_class_slices(K);
 }
 size_t flow_cpart_floats(int B, int K, int F) { return flow_slices(B, K, F) * kNJ * kVideoTile * kKW; }
-size_t flow_smem(int C) { return flow_smem_bytes(C); }
+size_t flow_smem(int C) { return stream_smem_bytes(C); }
 
-cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out) {
+cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuning, cudaStream_t stream,
+                        int* stream_grid, int* contract_grid) {
+  static_assert(kVideoTile * kKW == 8 * kCThreads, "two float4s of the partial block per thread");
   FusedParams p = p_in;
   const int Q = p.C / 1024, rmax = (p.R == 1) ? 1 : APA_MAX_RANK;
-  FKernelFn fn = flow_select(Q, rmax, mode);
-  if (fn == nullptr) return cudaErrorInvalidValue;
-  const size_t smem = flow_smem_bytes(p.C);
-  cudaError_t err = flow_prepare(reinterpret_cast<const void*>(fn), smem);
+  FKernelFn sfn = flow_stream_select(Q, rmax, mode), cfn = flow_contract_select(Q);
+  FKernelFn rfn = (mode == MODE_SOFTMAX) ? &apa_flow_reduce_kernel<true> : &apa_flow_reduce_kernel<false>;
+  if (sfn == nullptr || cfn == nullptr) return cudaErrorInvalidValue;
+  const size_t smem1 = stream_smem_bytes(p.C), smem2 = contract_smem_bytes(p.C);
+  cudaError_t err = flow_prepare(reinterpret_cast<const void*>(sfn), smem1);
+  if (err != cudaSuccess) return err;
+  err = flow_prepare(reinterpret_cast<const void*>(cfn), smem2);
   if (err != cudaSuccess) return err;
   p.fl_G = flow_stream_ctas(p.B, p.HW, tuning);
   p.fl_NS = flow_class_slices(p.K);
   p.inputs_stable = (tuning && tuning->inputs_stable) ? 1 : 0;
-  const int grid = p.fl_G + kNJ * p.fl_NS;
-  static_assert(kVideoTile * kKW == 4 * kConsumerThreads, "one float4 of the partial block per thread");
-  if (grid_out) *grid_out = grid;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(kFusedThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
+  const int grid2 = kNJ * p.fl_NS;
+  if (stream_grid) *stream_grid = p.fl_G;
+  if (contract_grid) *contract_grid = grid2;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
+  const int na = (tuning && tuning->no_pdl) ? 0 : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.fl_G, 1, 1);
+  cfg.blockDim = dim3(kFusedThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem1;
+  cfg.stream = stream;
   cfg.attrs = at;
-  cfg.numAttrs = (tuning && tuning->no_pdl) ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, fn, p);
+  cfg.numAttrs = na;
+  err = cudaLaunchKernelEx(&cfg, sfn, p);
+  if (err != cudaSuccess) return err;
+  cudaLaunchConfig_t cfgr = {};
+  cfgr.gridDim = dim3(p.B, (p.C / 4 + kRThreads - 1) / kRThreads, 1);
+  cfgr.blockDim = dim3(kRThreads, 1, 1);
+  cfgr.stream = stream;
+  cfgr.attrs = at;
+  cfgr.numAttrs = na;
+  err = cudaLaunchKernelEx(&cfgr, rfn, p);
+  if (err != cudaSuccess) return err;
+  cudaLaunchConfig_t cfg2 = {};
+  cfg2.gridDim = dim3(grid2, 1, 1);
+  cfg2.blockDim = dim3(kCThreads, 1, 1);
+  cfg2.dynamicSmemBytes = smem2;
+  cfg2.stream = stream;
+  cfg2.attrs = at;
+  cfg2.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg2, cfn, p);
 }
 
 }  // namespace apa

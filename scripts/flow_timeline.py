@@ -23,7 +23,7 @@ opl = [ops.AttnPoolOp(P, K, HW, rank=rank, flags=bits, tuning=tun) for _ in rang
 xs = [torch.relu(torch.randn((B, HW, C), device="cuda")) for _ in range(8)]
 outs = [torch.empty((B, K), device="cuda") for _ in range(NOPS)]
 plan = ops.attn_pool_plan(opl[0].desc(B), tun)
-G = plan["grid"] - plan["contract_grid"]
+G = plan["grid"]
 U = plan["contract_grid"]
 
 

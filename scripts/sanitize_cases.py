@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Small shapes of every kernel family, for compute-sanitizer (scripts/gpu_sanitize.sh): each form of the single-map
+head, the fused all-gather on one rank, the dense path on the tcgen05 GEMM, the Gram.  Each case is checked against
+the oracle so a sanitizer-clean run is also a correct one."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+from attentionalpoolingaction_b200 import dist as apa_dist
+from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+from oracle import attn_pool_oracle as orc
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+S = dict(SINGLE_LAYER_ATT=True)
+
+
+def head(name, B, HW, C, K, flags, F=1, form=0, gather=False, want=(False, False, False), reps=2):
+    fl = dict(orc.DEFAULT_FLAGS, **flags)
+    params = orc.make_params(K, C, 64, 5, flags=fl, seed=2)
+    X = orc.make_features(B, HW, C, seed=2)
+    ref, _ = orc.attn_pool_head(X, params, fl, K, frames_per_video=F, want_pose=False)
+    bits, rank = ops.flags_from_cfg_net(fl)
+    t = ops.make_tuning(form=form, inputs_stable=1)
+    op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, frames=F, rank=rank,
+                        flags=bits, num_pose_keypoints=5, tuning=t, device="cuda:0")
+    Xd = torch.from_numpy(X).cuda()
+    if gather:
+        pg = apa_dist.PeerGather(B // F, K, torch.device("cuda:0"), depth=2)
+        for _ in range(reps + 1):
+            op.forward_gather(Xd, pg)
+        torch.cuda.synchronize()
+        got = pg.buffer(reps + 1).cpu().numpy()
+    else:
+        for _ in range(reps):           # back-to-back launches: the PDL overlap is part of what is checked
+            got = op(Xd, want_attn=want[0], want_topdown=want[1], want_pose=want[2])[0]
+        torch.cuda.synchronize()
+        got = got.cpu().numpy()
+    err = orc.rel_err(got, ref)
+    print("%-36s rel err %.2e %s" % (name, err, "OK" if err <= 1e-4 else "MISMATCH"), flush=True)
+    assert err <= 1e-4
+
+
+if which in ("all", "flow"):
+    head("flow plain b8", 8, 49, 2048, 37, S, form=ops.APA_FORM_FLOW)
+    head("flow softmax b5 odd", 5, 25, 2048, 37, dict(S, SOFTMAX_ATT=True), form=ops.APA_FORM_FLOW)
+    head("flow rank2 relu frames2 c1024", 8, 16, 1024, 70, dict(S, RANK=2, RELU_ATT=True), F=2, form=ops.APA_FORM_FLOW)
+    head("flow gather (world 1, depth 2)", 8, 49, 2048, 37, S, form=ops.APA_FORM_FLOW, gather=True)
+    head("flow attention end point", 4, 25, 2048, 37, dict(S, SOFTMAX_ATT=True), form=ops.APA_FORM_FLOW,
+         want=(True, False, False))
+if which in ("all", "older"):
+    head("cluster-local b8", 8, 49, 2048, 37, S, form=ops.APA_FORM_LOCAL0)
+    head("cluster-local shape 2 softmax", 8, 25, 2048, 37, dict(S, SOFTMAX_ATT=True), form=ops.APA_FORM_LOCAL2)
+    head("pipeline frames2", 8, 25, 2048, 37, S, F=2, form=ops.APA_FORM_PIPELINE)
+    head("grid-barrier b5 rank2", 5, 25, 2048, 37, dict(S, RANK=2), form=ops.APA_FORM_GRID_BARRIER)
+    head("cluster-local gather (world 1)", 8, 49, 2048, 37, S, form=ops.APA_FORM_LOCAL0, gather=True)
+if which in ("all", "dense"):
+    head("config 003 (tcgen05 pose GEMM + a0)", 8, 64, 2048, 37, dict(RANK=2), form=ops.APA_FORM_FLOW)
+    head("per-class dense path", 4, 64, 2048, 40, dict(S, PER_CLASS=True))
+    head("top-down end point", 2, 64, 2048, 40, S, want=(True, True, False))
+    Xg = torch.relu(torch.randn((2, 64, 256), device="cuda"))
+    G = ops.gram(Xg)
+    torch.cuda.synchronize()
+    err = orc.rel_err(G.cpu().numpy(), orc.gram(Xg.cpu().numpy()))
+    print("%-36s rel err %.2e" % ("gram 2 x 64 x 256", err), flush=True)
+    assert err <= 1e-4
+print("SANITIZE_CASES_DONE", flush=True)

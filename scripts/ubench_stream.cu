@@ -241,57 +241,46 @@ void run(const Bufs& bufs, int grid, int lp, int balanced, int nstreams, int pdl
   for (auto& s : st) cudaStreamDestroy(s);
 }
 
-int main() {
+__global__ void fill_random(float* p, size_t n, unsigned int seed) {  // relu(pseudo-normal): like real conv5 features
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    unsigned int h = (unsigned int)(i * 2654435761u) ^ seed;
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    const float u = (h >> 8) * (1.0f / 16777216.0f) - 0.5f;
+    p[i] = u > 0.f ? 3.f * u : 0.f;
+  }
+}
+
+int main(int argc, char** argv) {
+  const bool zeros = (argc > 1 && argv[1][0] == 'z');
+  printf("input data: %s\n", zeros ? "all zeros (cudaMemset)" : "relu(pseudo-random)");
   Bufs bufs;
   const size_t xbytes = size_t(B) * HW * C * 4;
   for (int i = 0; i < 7; ++i) {  // 7 x 51 MB = 360 MB > 2x L2
     float* p;
     cudaMalloc(&p, xbytes);
-    cudaMemset(p, 0, xbytes);
+    if (zeros) cudaMemset(p, 0, xbytes);
+    else fill_random<<<1184, 256>>>(p, xbytes / 4, 17u * i + 1u);
     bufs.X.push_back(p);
   }
-  cudaMalloc(&bufs.w, C * 4); cudaMemset(bufs.w, 0, C * 4);
+  cudaMalloc(&bufs.w, C * 4);
+  if (zeros) cudaMemset(bufs.w, 0, C * 4);
+  else fill_random<<<8, 256>>>(bufs.w, C, 999u);
   cudaMalloc(&bufs.gpart, size_t(8) * 512 * C * 4);
   cudaMalloc(&bufs.smid, 4 * 1024);
   cudaMalloc(&bufs.cyc, 16 * 1024);
   const int L = 210;
-  // --- the shipped STREAM kernel's shape, sliced map, one launch at a time / PDL / lanes
   run<3, 3, 3, 1>(bufs, 128, 4, 0, 1, 0, L, "as shipped, no overlap");
   run<3, 3, 3, 1>(bufs, 128, 4, 0, 1, 1, L, "as shipped, PDL");
-  run<3, 3, 3, 1>(bufs, 128, 4, 0, 3, 1, L, "as shipped, PDL, 3 lanes");
-  // --- balanced maps: every SM the same byte count
+  run<3, 3, 3, 1>(bufs, 148, 0, 1, 1, 0, L, "balanced 148, no overlap");
   run<3, 3, 3, 1>(bufs, 148, 0, 1, 1, 1, L, "balanced 148");
+  run<3, 3, 3, 1>(bufs, 148, 0, 1, 4, 1, L, "balanced 148, 4 lanes");
   run<3, 3, 3, 1>(bufs, 296, 0, 1, 1, 1, L, "balanced 296");
-  run<3, 3, 3, 1>(bufs, 148, 0, 1, 3, 1, L, "balanced 148, 3 lanes");
-  // --- bigger rings, two per SM
-  run<4, 3, 2, 1>(bufs, 128, 4, 0, 1, 1, L, "32 KB x 3, 2/SM");
   run<4, 3, 2, 1>(bufs, 148, 0, 1, 1, 1, L, "32 KB x 3, 2/SM, balanced");
   run<4, 3, 2, 1>(bufs, 148, 0, 1, 2, 1, L, "32 KB x 3, 2/SM, balanced, 2 lanes");
   run<4, 6, 1, 1>(bufs, 148, 0, 1, 1, 1, L, "32 KB x 6, 1/SM, balanced");
-  run<4, 6, 1, 1>(bufs, 148, 0, 1, 2, 1, L, "32 KB x 6, 1/SM, balanced, 2 lanes");
-  // --- two tiles per consumer chain
-  run<3, 4, 2, 2>(bufs, 128, 4, 0, 1, 1, L, "pair, 24 KB x 4, 2/SM");
   run<3, 4, 2, 2>(bufs, 148, 0, 1, 1, 1, L, "pair, 24 KB x 4, 2/SM, balanced");
-  run<3, 4, 2, 2>(bufs, 148, 0, 1, 2, 1, L, "pair, 24 KB x 4, 2/SM, balanced, 2 lanes");
-  run<4, 4, 1, 2>(bufs, 148, 0, 1, 1, 1, L, "pair, 32 KB x 4, 1/SM, balanced");
-  run<2, 4, 3, 2>(bufs, 128, 4, 0, 1, 1, L, "pair, 16 KB x 4, 3/SM");
-  run<2, 4, 3, 2>(bufs, 148, 0, 1, 3, 1, L, "pair, 16 KB x 4, 3/SM, balanced, 3 lanes");
-  run<2, 3, 3, 1>(bufs, 128, 4, 0, 3, 1, L, "16 KB x 3, 3/SM, 3 lanes");
-  // --- lanes without PDL, 4 lanes, 2 CTAs of a launch per SM
-  run<3, 3, 3, 1>(bufs, 148, 0, 1, 4, 1, L, "balanced 148, 4 lanes");
-  run<3, 3, 3, 1>(bufs, 148, 0, 1, 4, 0, L, "balanced 148, 4 lanes, no PDL");
-  run<3, 3, 3, 1>(bufs, 148, 0, 1, 2, 1, L, "balanced 148, 2 lanes");
-  run<3, 3, 3, 1>(bufs, 296, 0, 1, 2, 1, L, "balanced 296, 2 lanes");
-  run<3, 3, 3, 1>(bufs, 296, 0, 1, 4, 1, L, "balanced 296, 4 lanes");
-  run<4, 3, 2, 1>(bufs, 148, 0, 1, 4, 1, L, "32 KB x 3, 2/SM, balanced, 4 lanes");
-  run<4, 3, 2, 1>(bufs, 296, 0, 1, 2, 1, L, "32 KB x 3, 2/SM, balanced 296, 2 lanes");
-  run<3, 4, 2, 1>(bufs, 148, 0, 1, 1, 1, L, "24 KB x 4, 2/SM, balanced");
-  run<3, 4, 2, 1>(bufs, 148, 0, 1, 2, 1, L, "24 KB x 4, 2/SM, balanced, 2 lanes");
-  run<3, 4, 2, 1>(bufs, 148, 0, 1, 4, 1, L, "24 KB x 4, 2/SM, balanced, 4 lanes");
   run<2, 6, 2, 1>(bufs, 148, 0, 1, 2, 1, L, "16 KB x 6, 2/SM, balanced, 2 lanes");
-  run<2, 6, 2, 1>(bufs, 148, 0, 1, 4, 1, L, "16 KB x 6, 2/SM, balanced, 4 lanes");
   run<2, 4, 3, 1>(bufs, 148, 0, 1, 4, 1, L, "16 KB x 4, 3/SM, balanced, 4 lanes");
-  run<2, 4, 3, 1>(bufs, 296, 0, 1, 4, 1, L, "16 KB x 4, 3/SM, balanced 296, 4 lanes");
   cudaError_t err = cudaDeviceSynchronize();
   printf("done: %s\n", cudaGetErrorString(err));
   return err != cudaSuccess;

@@ -26,7 +26,7 @@ constexpr size_t kFlowCtrOff = 2048;        // [2048, 4096): the flow form's tic
 constexpr size_t kTsBytes = 320 * 64 * 8;  // debug timeline: up to 320 CTAs x 64 stamps
 
 struct Carve {
-  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, cpart, gsum, fl_arr, total;
+  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, cpart, gsum, fl_g, fl_arr, total;
   int path;  // 0 fused single-map, 1 dense
 };
 
@@ -58,10 +58,12 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
     if (split_eligible(d->channels, d->rank)) {  // pipeline / flow forms: partial g and stats per row run
       size_t slots = B * size_t(split_lp_cap(d->batch, d->hw));
       if (flow_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) {
-        if (flow_gpart_slots(d->batch) > slots) slots = flow_gpart_slots(d->batch);
-        c.cpart = take(flow_cpart_floats(d->batch, d->num_classes, d->frames));
-        c.gsum = take(B * 4);
-        c.fl_arr = take(flow_slices(d->batch, d->num_classes, d->frames) * 2);
+        // the flow form keeps kFlowDepth copies of every per-call buffer (call L uses copy L % kFlowDepth)
+        if (kFlowDepth * flow_gpart_slots(d->batch) > slots) slots = kFlowDepth * flow_gpart_slots(d->batch);
+        c.cpart = take(kFlowDepth * flow_cpart_floats(d->batch, d->num_classes, d->frames));
+        c.gsum = take(kFlowDepth * B * 4);
+        c.fl_g = take(kFlowDepth * B * R * C);
+        c.fl_arr = take(kFlowDepth * flow_slices(d->batch, d->num_classes, d->frames) * 2);
       }
       c.gpart = take(slots * R * C);
       c.gstat = take(slots * 8);
@@ -81,8 +83,9 @@ bool use_flow(const ApaDesc* d, const ApaTuning* t) {
   const int force = t ? t->form : 0;
   if (force == APA_FORM_FLOW) return true;
   if (force != APA_FORM_AUTO) return false;
-  if (t && (t->fused >= 0 || t->cluster_size != 0)) return false;  // explicit requests for the older forms
-  return false;
+  // measured (scripts/bench_flow.py, flow_parts.py; profiles/): the flow form has the shortest single call at every
+  // shape and the highest throughput with several batches in flight; it is the default wherever it applies
+  return true;
 }
 
 bool use_split(const ApaDesc* d, const ApaTuning* t) {
@@ -252,7 +255,7 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
       two = true;
     }
     launches += two ? 2 : 1;
-    if (plan[6] == 3) launches += 1;               // flow form: STREAM, REDUCE, CONTRACT
+    if (plan[6] == 3) launches += 2;               // flow form: STREAM, REDUCE, CONTRACT, FINISH
     if (want_attn) launches += 1;
   } else {
     const int R = desc->rank;
@@ -407,9 +410,11 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
       p.gstat = wsf(c.gstat);
       p.cpart = wsf(c.cpart);
       p.gsum = wsf(c.gsum);
+      p.g = wsf(c.fl_g);
       p.fl_arr = reinterpret_cast<unsigned long long*>(ws + c.fl_arr);
       p.fl_ctr = reinterpret_cast<unsigned long long*>(ws + kFlowCtrOff);
       int g1 = 0;
+      p.trigger_lead = tuning ? tuning->pdl_trigger_lead : 0;   // flow form: 0 = at the last tiles, < 0 = at once
       APA_CUDA(flow_launch(p, mode, tuning, stream, &g1, &grid));
       launched = true;
     }

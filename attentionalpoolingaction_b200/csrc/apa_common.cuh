@@ -207,7 +207,7 @@ __device__ __forceinline__ unsigned long long peer_gather_step(const unsigned lo
 __device__ __forceinline__ void peer_gather_complete(int world, int rank, unsigned long long* const* flags,
                                                      unsigned long long* counters, unsigned long long step) {
   peer_gather_publish(world, rank, flags, step);
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(counters + 1), "l"(step) : "memory");
+  asm volatile("red.release.gpu.global.max.u64 [%0], %1;" ::"l"(counters + 1), "l"(step) : "memory");
 }
 // Older forms (grid-barrier / cluster-local / pipeline): called by ONE thread per CTA after that CTA's logits
 // stores (and a CTA-level barrier).  counters[0] only ever grows and every launch leaves it at a multiple of 2^20,

@@ -47,12 +47,15 @@ struct FusedParams {
   float* gstat;                       // workspace [B, lp, 8]: (s_r[4], running max) per row slice
   int lp;                             // row slices per image
   // flow form (apa_pool_flow.cu)
-  unsigned long long* fl_ctr;         // control counters: [2] slices-done (fused all-gather)
+  unsigned long long* fl_ctr;         // control words: STREAM / REDUCE / CONTRACT tickets, completed calls, gather steps
+  size_t fl_gpart_stride, fl_gstat_stride, fl_g_stride, fl_gsum_stride, fl_cpart_stride, fl_arr_stride;
+                                      // distance between the kFlowDepth copies of the per-call buffers
   unsigned long long* fl_arr;         // [video tiles * class slices] arrival counters of the CONTRACT units
   float* gsum;                        // workspace [B][4]: attention mass per rank of the reduced image
   float* cpart;                       // workspace [tiles * class slices][16][32 videos][32 classes] partial logits
-  int fl_G, fl_NS;                    // STREAM CTAs, class slices
+  int fl_G, fl_NS, fl_ng;             // STREAM CTAs, class slices, consumer groups (partials per CTA and image)
   int inputs_stable;                  // X / weights may be read before the previous kernel in the stream completed
+  int fl_debug_nowait;                // measurement builds of the chain without its tail: skip the completed-calls check
   int gw_depth;                       // buffers in every rank's gathered ring (call `step` lands in step % depth)
 };
 
@@ -94,6 +97,7 @@ cudaError_t split_launch(const FusedParams& p, int mode, const ApaTuning* tuning
 
 // ---- flow form (apa_pool_flow.cu): row-balanced STREAM kernel + small CONTRACT kernel parked in griddepcontrol.wait
 constexpr int kFlowStreamCtas = 148;   // one STREAM CTA per SM of a B200
+constexpr int kFlowDepth = 2;          // copies of the per-call buffers: call L uses copy L % 2
 bool flow_eligible(int B, int HW, int C, int K, int R, int F);
 int flow_stream_ctas(int B, int HW, const ApaTuning* tuning);
 int flow_class_slices(int K);

@@ -14,19 +14,23 @@
 //             CTA executes griddepcontrol.wait once, after its last tile, then stores.  No flags, atomics, fences.
 //   REDUCE    one 128-thread CTA per (image, 512 channels): adds the image's partials in run order (softmax:
 //             max/sum merge) into g[b], the attention mass into gsum[b].
-//   CONTRACT  16 channel slices x ceil(K/32) class slices, 128 threads, 34 KB.  A unit loads its [C/16 x 32] block
+//   CONTRACT  16 channel slices x ceil(K/32) class slices, 128 threads, 25 KB.  A unit loads its [C/16 x 32] block
 //             of B_r into shared memory, executes griddepcontrol.wait, loads g of its channels for 32 videos (frames
-//             summed), contracts (4 x 4 register tiles, two channel halves), and writes its partial [32 x 32]
-//             block.  The 16th unit to arrive for a class slice adds the 16 partials in fixed order
+//             summed, one round trip), contracts (2 x 4 register tiles, two channel halves, 16 videos at a time) and
+//             writes its partial [32 x 32] block.
+//   FINISH    one 128-thread CTA per (32 videos, class slice): adds the 16 partials in index order
 //             (bit-reproducible), bias, scale, and stores the logits (or the peer stores of the fused all-gather).
-// All three are programmatic dependents that trigger at once: STREAM(n) -> REDUCE(n) -> CONTRACT(n) -> STREAM(n+1).
-// REDUCE(n) and CONTRACT(n) are small enough to be resident (parked in griddepcontrol.wait, a hardware wait) beside
-// STREAM(n) on every SM, so STREAM(n+1)'s CTA takes an SM the moment STREAM(n)'s CTA leaves it and HBM idles only
-// for the first-tile latency between calls, on one stream as on four.  STREAM(n+1) executes griddepcontrol.wait
-// before its first global write (CONTRACT(n), and so everything before it, has then completed).  Reading X before
-// that wait is only legal when X was complete before the previous kernel in the stream started:
-// ApaTuning.inputs_stable (default 0 = wait first).  The only counters are the CONTRACT units' arrival counters
-// (each launch adds exactly 16 to each) and a slices-done counter that every launch leaves at a multiple of 2^20.
+// All four are programmatic dependents that trigger as soon as they know which call they belong to:
+// STREAM(n) -> REDUCE(n) -> CONTRACT(n) -> FINISH(n) -> STREAM(n+1) -> ...  The three tail kernels are small enough to be
+// resident (parked in griddepcontrol.wait, a hardware wait) beside STREAM(n) on every SM, so STREAM(n+1)'s CTA takes
+// an SM the moment STREAM(n)'s CTA leaves it, on one stream as on four.  No kernel ever waits for a kernel it does
+// not read from: every per-call buffer of the workspace (partials, g, partial logits, arrival counters) exists
+// kFlowDepth = 2 times and call L uses copy L % 2.  L comes from ticket counters in the workspace (one atomic per
+// CTA; every launch pads its counter to the next multiple of 2^20, so CUDA-graph replays and changing shapes need
+// no host state), and a STREAM CTA of call L only checks (one acquire load, true in steady state) that call L - 2
+// has completed before it stores its first partial.  Reading X before the previous kernel in the stream has
+// completed is only legal when X was complete before that kernel started: ApaTuning.inputs_stable (default 0 =
+// griddepcontrol.wait first, which serialises back-to-back calls).
 #include "apa_common.cuh"
 #include "apa_kernels.h"
 
@@ -37,13 +41,14 @@ namespace apa {
 namespace {
 
 constexpr int kFTR = 3;        // rows per X tile
-constexpr int kFStages = 4;    // ring depth: 96 KB in flight per SM; with the staging area no second STREAM CTA fits beside it
 constexpr int kNJ = 16;        // channel slices of the contraction
 constexpr int kKW = 32;        // classes per contract unit
 constexpr int kGPad = 4;       // gs[video][C/16 + 4]: consecutive videos start 4 banks apart
 constexpr int kCThreads = 128; // CONTRACT block
 constexpr int kRThreads = 128; // REDUCE block: 128 float4 columns = 512 channels
 constexpr unsigned long long kStride = 1ull << 20;
+// control words (u64) of the flow form in the workspace control block
+enum { kCtrTS = 0, kCtrTR = 1, kCtrTC = 2, kCtrDone = 3, kCtrGwStep = 4 /* [kFlowDepth] */, kCtrTF = 6 };
 
 __device__ __forceinline__ float fdot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
@@ -64,6 +69,19 @@ __device__ __forceinline__ unsigned long long atom_add_acq_rel(unsigned long lon
   asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], %2;" : "=l"(prev) : "l"(p), "l"(v) : "memory");
   return prev;
 }
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// One thread per CTA: which call (launch index on this workspace) this launch belongs to.  `ctr` only ever grows;
+// the CTA that takes a launch's last ticket pads it to the next multiple of 2^20.  Must complete before the CTA
+// triggers its dependents (the next launch of the same kernel must not draw tickets before this one has all of its).
+__device__ __forceinline__ unsigned long long flow_ticket(unsigned long long* ctr, unsigned int nctas) {
+  const unsigned long long prev = atom_add_relaxed(ctr, 1ull);
+  if ((prev & (kStride - 1)) == (unsigned long long)(nctas - 1)) (void)atom_add_relaxed(ctr, kStride - nctas);
+  return prev >> 20;
+}
 __device__ __forceinline__ unsigned long long fglobaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -80,38 +98,39 @@ __device__ __forceinline__ void flow_image_ctas(long long N, int G, int HW, int 
   *hi = int(c < G - 1 ? c : G - 1);
 }
 
-constexpr int kNG = 2;                        // consumer groups: two tiles are in work at any time
-constexpr int kWPG = kConsumerWarps / kNG;    // warps per group (4): a warp covers C / 4 channels of a row
-constexpr size_t kStageBytes = 32 * 1024;     // partials of a CTA's non-final image segments wait here
-__host__ __device__ inline size_t stream_smem_bytes(int C) {
-  return size_t(kFStages) * kFTR * C * 4 + kStageBytes + 512 + 512 + 16 * 8;
+// Shapes of the STREAM kernel (ApaTuning.cluster_size picks one for A/B runs; 0 = default):
+//   shape 0: two consumer groups, 4-stage ring (96 KB), <= 128 registers: one CTA per SM
+//   shape 1: two consumer groups, 3-stage ring (72 KB), <= 96 registers: two CTAs per SM
+//   shape 2: one consumer group,  3-stage ring (72 KB), <= 72 registers: three CTAs per SM
+constexpr int kNG = 2;                        // partial-g slots per (CTA, image): sized for two consumer groups
+__host__ __device__ inline size_t stream_smem_bytes(int C, int stages) {
+  return size_t(stages) * kFTR * C * 4 + 512 + 16 * 8 + 64;
 }
 
 // ================================================================================================ STREAM
-template <int Q, int RMAX, int MODE>
-__global__ void __launch_bounds__(kFusedThreads, 1) __maxnreg__((RMAX == 1) ? 128 : 216)
+template <int Q, int RMAX, int MODE, int NG, int STG, int MAXREG>
+__global__ void __launch_bounds__(kFusedThreads, 1) __maxnreg__((RMAX == 1) ? MAXREG : 216)
 apa_flow_stream_kernel(const FusedParams p) {
-  constexpr int C = Q * 1024, TR = kFTR, QT = Q * kNG;   // QT float4s of a row per thread
+  constexpr int kFStages = STG, kWPG = kConsumerWarps / NG;   // warps per group: a warp covers C / kWPG channels
+  constexpr int C = Q * 1024, TR = kFTR, QT = Q * NG;    // QT float4s of a row per thread
   constexpr size_t kTileBytes = size_t(TR) * C * 4;
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* stg = reinterpret_cast<float*>(smem + kFStages * kTileBytes);              // [seg][R][group][C]
-  float* stgstat = reinterpret_cast<float*>(smem + kFStages * kTileBytes + kStageBytes);   // [seg][group][8]
-  float* partS = stgstat + 128;                                                      // [group][2][16]
+  float* partS = reinterpret_cast<float*>(smem + kFStages * kTileBytes);            // [group][2][32]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(partS + 128);
   uint64_t* empty_bar = full_bar + 8;
+  unsigned long long* call_s = reinterpret_cast<unsigned long long*>(empty_bar + 8);
   static_assert(kFStages <= 8, "barrier arrays");
   const int R = p.R, G = p.fl_G, HW = p.HW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long N = (long long)p.B * HW;
   const int t = blockIdx.x;
 
-  griddep_launch_dependents();  // REDUCE / CONTRACT of this call, then the next call's STREAM, may be scheduled
   const bool wait_first = !p.inputs_stable || p.attn_in != nullptr || p.attn_raw != nullptr;
   if (wait_first) griddep_wait();
 
   const int row_lo = flow_row_lo(N, G, t), row_hi = flow_row_lo(N, G, t + 1);
   const int b_first = row_lo / HW, b_last = (row_hi - 1) / HW;
-  if (tid == 0) {
+  if (tid == kConsumerThreads) {   // the producer lane sets up the ring and starts streaming at once
     for (int i = 0; i < kFStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], kWPG);
@@ -138,15 +157,43 @@ apa_flow_stream_kernel(const FusedParams p) {
         }
       }
     }
-    return;
+    return;   // (the consumers trigger the dependents, after the CTA's ticket is drawn)
   }
-  if (tid == 0 && p.ts != nullptr && t < 160) {
-    p.ts[size_t(t) * 64 + 0] = clock64();
-    p.ts[size_t(t) * 64 + 62] = fglobaltimer_ns();
-    unsigned int smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    p.ts[size_t(t) * 64 + 61] = smid;
+  if (tid == 0) {
+    // which call this is (copy L % 2 of the per-call buffers); the copy is free once call L - 2 has completed
+    const unsigned long long L = flow_ticket(p.fl_ctr + kCtrTS, gridDim.x);
+    if (t == 0 && p.gw_world > 0) {
+      // the step of this gather call; everything before this call in the stream that is not one of our own
+      // kernels has completed (it does not trigger early), so this rank no longer reads older gathered buffers
+      const unsigned long long step = atom_add_relaxed(p.gw_done + 2, 1ull) + 1;
+      peer_gather_publish_started(p.gw_world, p.gw_rank, p.gw_flags, step);
+      p.fl_ctr[kCtrGwStep + (L & 1)] = step;   // read by CONTRACT(L) after its griddepcontrol.wait
+    }
+    if (L >= kFlowDepth && !p.fl_debug_nowait) {
+      const long long t0 = clock64();
+      while ((ld_acquire(p.fl_ctr + kCtrDone) >> 20) + kFlowDepth < L + 1) {
+        __nanosleep(64);
+        if (clock64() - t0 > APA_SPIN_TIMEOUT_CYCLES) __trap();
+      }
+    }
+    *call_s = L;
+    if (p.ts != nullptr && t < 160) {
+      p.ts[size_t(t) * 64 + 0] = clock64();
+      p.ts[size_t(t) * 64 + 62] = fglobaltimer_ns();
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.ts[size_t(t) * 64 + 61] = smid;
+    }
   }
+  named_bar_sync(3, kConsumerThreads);
+  // When to let REDUCE / CONTRACT of this call (and, behind them, the next call's STREAM) be scheduled: they park in
+  // griddepcontrol.wait until this grid has finished, and parked CTAs pile up on whichever SMs have room -- which
+  // then have none for a STREAM CTA.  So by default a CTA triggers only `lead` tiles before its last one.
+  const int lead = p.trigger_lead;
+  if (lead < 0) griddep_launch_dependents();
+  const size_t cp = size_t(*call_s & (kFlowDepth - 1));   // which copy of the per-call buffers
+  float* const gpart = p.gpart + cp * p.fl_gpart_stride;
+  float* const gstat = p.gstat + cp * p.fl_gstat_stride;
 
   // =========================================================================== consumers: two groups of 4 warps;
   // group g takes the CTA's tiles g, g + 2, ... and keeps its own partial sums (slot 2 (CTA + image) + g)
@@ -166,11 +213,16 @@ apa_flow_stream_kernel(const FusedParams p) {
     cw[j] = (j >= 1 && j < R) ? __ldg(p.attn_w[j]) : 0.f;
     cb[j] = (j >= 1 && j < R) ? __ldg(p.attn_b[j]) : 0.f;
   }
-  float* part0 = partS + grp * 32;
-  const int stage_cap = int(kStageBytes / (size_t(R) * kNG * C * 4));   // image segments that fit the staging area
+  float* part0 = partS + grp * 64;
   uint32_t tile0 = 0, flip = 0;       // index (within the CTA) of the current segment's first tile
-  int staged = 0;
-  bool waited = wait_first;
+  const uint32_t cta_tiles = [&] {     // tiles of this CTA (all segments)
+    uint32_t n = 0;
+    for (int b = b_first; b <= b_last; ++b)
+      n += uint32_t(min(row_hi, (b + 1) * HW) - max(row_lo, b * HW) + TR - 1) / TR;
+    return n;
+  }();
+  const uint32_t trig_tile = (lead >= 0 && cta_tiles > uint32_t(lead) + 2u) ? cta_tiles - 2u - uint32_t(lead) : 0u;
+  bool triggered = (lead < 0);
   for (int b = b_first; b <= b_last; ++b) {
     const int seg_lo = max(row_lo, b * HW);
     const int nrows = min(row_hi, (b + 1) * HW) - seg_lo;
@@ -185,8 +237,9 @@ apa_flow_stream_kernel(const FusedParams p) {
       for (int i = 0; i < QT * 4; ++i) f[j][i] = 0.f;
     }
     // my first tile of this segment: the smallest i >= tile0 with i % 2 == grp
-    for (uint32_t i = tile0 + ((tile0 ^ uint32_t(grp)) & 1u); i < tile0 + ntiles; i += kNG, flip ^= 16u) {
+    for (uint32_t i = (NG == 1) ? tile0 : tile0 + ((tile0 ^ uint32_t(grp)) & 1u); i < tile0 + ntiles; i += NG, flip ^= 32u) {
       const uint32_t stage = i % kFStages, phase = (i / kFStages) & 1u;
+      if (!triggered && i >= trig_tile) { griddep_launch_dependents(); triggered = true; }
       const int off = int(i - tile0) * TR;
       const int rows = min(TR, nrows - off);
       const int gi = seg_lo + off;
@@ -235,6 +288,7 @@ apa_flow_stream_kernel(const FusedParams p) {
         if (grp == 0) named_bar_sync(1, kWPG * 32);
         else named_bar_sync(2, kWPG * 32);
         float v = (lane < TR * kWPG) ? part[lane] : 0.f;
+        if (kWPG == 8) v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         v += __shfl_xor_sync(0xffffffffu, v, 1);
 #pragma unroll
@@ -298,57 +352,12 @@ apa_flow_stream_kernel(const FusedParams p) {
       }
     }
     tile0 += ntiles;
-    // ---- this group's partial of image b.  Non-final segments wait in shared memory (the CTA must not stall in
-    //      the middle of its stream); the last one stays in registers; everything is flushed after the wait below.
-    const bool last_seg = (b == b_last);
-    if (!last_seg && !waited && staged < stage_cap) {
-#pragma unroll
-      for (int j = 0; j < RMAX; ++j)
-        if (j < R) {
-          float* dst = stg + ((size_t(staged) * R + j) * kNG + grp) * C + col0;
-#pragma unroll
-          for (int qq = 0; qq < QT; ++qq)
-            *reinterpret_cast<float4*>(dst + qq * 128) =
-                make_float4(f[j][qq * 4 + 0], f[j][qq * 4 + 1], f[j][qq * 4 + 2], f[j][qq * 4 + 3]);
-        }
-      if (gtid == 0) {
-#pragma unroll
-        for (int j = 0; j < RMAX; ++j) stgstat[(staged * kNG + grp) * 8 + j] = s[j];
-        stgstat[(staged * kNG + grp) * 8 + 4] = mx;
-      }
-      ++staged;
-      continue;
-    }
-    // the previous CONTRACT launch (which reads the workspace through REDUCE's output... and REDUCE itself) must
-    // have completely finished before the first global write of this launch
-    if (!waited) {
-      if (tid == 0 && p.ts != nullptr && t < 160) p.ts[size_t(t) * 64 + 2] = clock64();
-      griddep_wait();
-      waited = true;
-    }
-    for (int k = 0; k < staged; ++k) {   // flush what waited in shared memory (my own values: no barrier needed)
-      const int slot = 2 * (t + b_first + k) + grp;
-#pragma unroll
-      for (int j = 0; j < RMAX; ++j)
-        if (j < R) {
-          const float* src = stg + ((size_t(k) * R + j) * kNG + grp) * C + col0;
-          float* dst = p.gpart + (size_t(slot) * R + j) * C + col0;
-#pragma unroll
-          for (int qq = 0; qq < QT; ++qq)
-            *reinterpret_cast<float4*>(dst + qq * 128) = *reinterpret_cast<const float4*>(src + qq * 128);
-        }
-      if (gtid == 0) {
-#pragma unroll
-        for (int j = 0; j < RMAX; ++j) p.gstat[size_t(slot) * 8 + j] = stgstat[(k * kNG + grp) * 8 + j];
-        p.gstat[size_t(slot) * 8 + 4] = stgstat[(k * kNG + grp) * 8 + 4];
-      }
-    }
-    staged = 0;
-    const int slot = 2 * (t + b) + grp;
+    // ---- this group's partial of image b
+    const int slot = NG * (t + b) + grp;
 #pragma unroll
     for (int j = 0; j < RMAX; ++j)
       if (j < R) {
-        float* dst = p.gpart + (size_t(slot) * R + j) * C + col0;
+        float* dst = gpart + (size_t(slot) * R + j) * C + col0;
 #pragma unroll
         for (int qq = 0; qq < QT; ++qq)
           *reinterpret_cast<float4*>(dst + qq * 128) =
@@ -356,18 +365,14 @@ apa_flow_stream_kernel(const FusedParams p) {
       }
     if (gtid == 0) {
 #pragma unroll
-      for (int j = 0; j < RMAX; ++j) p.gstat[size_t(slot) * 8 + j] = s[j];
-      p.gstat[size_t(slot) * 8 + 4] = mx;
+      for (int j = 0; j < RMAX; ++j) gstat[size_t(slot) * 8 + j] = s[j];
+      gstat[size_t(slot) * 8 + 4] = mx;
     }
   }
-  if (tid == 0) {
-    // everything before this call in the stream is complete: this rank no longer reads older gathered buffers
-    if (t == 0 && p.gw_world > 0)
-      peer_gather_publish_started(p.gw_world, p.gw_rank, p.gw_flags, peer_gather_step(p.gw_done));
-    if (p.ts != nullptr && t < 160) {
-      p.ts[size_t(t) * 64 + 5] = clock64();
-      p.ts[size_t(t) * 64 + 63] = fglobaltimer_ns();
-    }
+  if (!triggered) griddep_launch_dependents();
+  if (tid == 0 && p.ts != nullptr && t < 160) {
+    p.ts[size_t(t) * 64 + 5] = clock64();
+    p.ts[size_t(t) * 64 + 63] = fglobaltimer_ns();
   }
 }
 
@@ -376,36 +381,44 @@ template <bool SOFTMAX>
 __global__ void __launch_bounds__(kRThreads, 8)
 apa_flow_reduce_kernel(const FusedParams p) {
   __shared__ float scl[320];   // per partial of this image: softmax scale exp(m_e - M) / S (1 otherwise)
+  __shared__ unsigned long long call_s;
   const int R = p.R, G = p.fl_G, HW = p.HW, C = p.C;
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
   const int c = (blockIdx.y * kRThreads + tid) * 4;
   const long long N = (long long)p.B * HW;
+  if (tid == 0) call_s = flow_ticket(p.fl_ctr + kCtrTR, gridDim.x * gridDim.y);
+  __syncthreads();
   griddep_launch_dependents();
   griddep_wait();   // STREAM of this call has finished and its partial g / stats are visible
+  const size_t cp = size_t(call_s & (kFlowDepth - 1));
+  const float* const gpart = p.gpart + cp * p.fl_gpart_stride;
+  const float* const gstat = p.gstat + cp * p.fl_gstat_stride;
+  float* const gout = p.g + cp * p.fl_g_stride;
+  float* const gsum = p.gsum + cp * p.fl_gsum_stride;
   int lo, hi;
   flow_image_ctas(N, G, HW, b, &lo, &hi);
-  const int n = kNG * (hi - lo + 1), s0 = kNG * (lo + b);   // partials of image b (runs x consumer groups), first slot
+  const int n = p.fl_ng * (hi - lo + 1), s0 = p.fl_ng * (lo + b);   // partials of image b (runs x consumer groups), first slot
   if (SOFTMAX) {
     float M = -INFINITY;
-    for (int e = 0; e < n; ++e) M = fmaxf(M, __ldcg(p.gstat + size_t(s0 + e) * 8 + 4));
+    for (int e = 0; e < n; ++e) M = fmaxf(M, __ldcg(gstat + size_t(s0 + e) * 8 + 4));
     float S = 0.f;
-    for (int e = 0; e < n; ++e) S += expf(__ldcg(p.gstat + size_t(s0 + e) * 8 + 4) - M) * __ldcg(p.gstat + size_t(s0 + e) * 8);
-    for (int e = tid; e < n; e += kRThreads) scl[e] = expf(__ldcg(p.gstat + size_t(s0 + e) * 8 + 4) - M) / S;
+    for (int e = 0; e < n; ++e) S += expf(__ldcg(gstat + size_t(s0 + e) * 8 + 4) - M) * __ldcg(gstat + size_t(s0 + e) * 8);
+    for (int e = tid; e < n; e += kRThreads) scl[e] = expf(__ldcg(gstat + size_t(s0 + e) * 8 + 4) - M) / S;
     if (tid == 0 && blockIdx.y == 0) {
-      p.gsum[size_t(b) * 4] = 1.f;
+      gsum[size_t(b) * 4] = 1.f;
       if (p.smx != nullptr) { p.smx[2 * b] = M; p.smx[2 * b + 1] = S; }
     }
     __syncthreads();
   } else if (tid < 4 && blockIdx.y == 0) {
     float mass = 0.f;
     if (tid < R)
-      for (int e = 0; e < n; ++e) mass += __ldcg(p.gstat + size_t(s0 + e) * 8 + tid);
-    p.gsum[size_t(b) * 4 + tid] = mass;
+      for (int e = 0; e < n; ++e) mass += __ldcg(gstat + size_t(s0 + e) * 8 + tid);
+    gsum[size_t(b) * 4 + tid] = mass;
   }
   if (c < C) {
     for (int j = 0; j < R; ++j) {
-      const float* gp = p.gpart + (size_t(s0) * R + j) * C + c;
+      const float* gp = gpart + (size_t(s0) * R + j) * C + c;
       float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int e0 = 0; e0 < n; e0 += 8) {   // eight loads in flight, added in run order
         float4 gv[8];
@@ -422,15 +435,16 @@ apa_flow_reduce_kernel(const FusedParams p) {
           a4.w = fmaf(sc, gv[q8].w, a4.w);
         }
       }
-      *reinterpret_cast<float4*>(p.g + (size_t(b) * R + j) * C + c) = a4;
+      *reinterpret_cast<float4*>(gout + (size_t(b) * R + j) * C + c) = a4;
     }
   }
 }
 
 // ================================================================================================ CONTRACT
+constexpr int kVH = kVideoTile / 2;   // videos staged in shared memory at a time
 __host__ __device__ inline size_t contract_smem_bytes(int C) {
   const int CH = C / kNJ;
-  return size_t(CH) * kKW * 4 + size_t(kVideoTile) * (CH + kGPad) * 4 + kVideoTile * 4 * 4 + 64;
+  return size_t(CH) * kKW * 4 + size_t(kVH) * (CH + kGPad) * 4 + 64;
 }
 
 template <int Q>
@@ -439,10 +453,8 @@ apa_flow_contract_kernel(const FusedParams p) {
   constexpr int C = Q * 1024, CH = C / kNJ, GS = CH + kGPad;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* Ws = reinterpret_cast<float*>(smem);       // [CH][kKW]   block of B_r
-  float* gs = Ws + CH * kKW;                        // [32 videos][GS]; later red[2][32][kKW]
-  float* sS = gs + kVideoTile * GS;                 // [32 videos][4] attention mass per rank
-  unsigned long long* step_s = reinterpret_cast<unsigned long long*>(sS + kVideoTile * 4);
-  int* flag_s = reinterpret_cast<int*>(step_s + 1);
+  float* gs = Ws + CH * kKW;                        // [16 videos][GS]; later red[2][16][kKW]
+  unsigned long long* call_s = reinterpret_cast<unsigned long long*>(gs + kVH * GS);
   const int R = p.R, K = p.K, F = p.F, NS = p.fl_NS;
   const int tid = threadIdx.x;
   const int u = blockIdx.x;            // unit: channel slice cj (fastest), class slice sl
@@ -454,8 +466,13 @@ apa_flow_contract_kernel(const FusedParams p) {
   const int ntile = (Bv + kVideoTile - 1) / kVideoTile;
   const int ts_row = 160 + u;
 
-  griddep_launch_dependents();  // the next call's STREAM may start right away
+  if (tid == 0) *call_s = flow_ticket(p.fl_ctr + kCtrTC, gridDim.x);
+  __syncthreads();
+  griddep_launch_dependents();  // FINISH of this call and the next call's STREAM may be scheduled
   if (!p.inputs_stable) griddep_wait();
+  const size_t cp = size_t(*call_s & (kFlowDepth - 1));   // which copy of the per-call buffers
+  const float* const gin = p.g + cp * p.fl_g_stride;
+  float* const cpart = p.cpart + cp * p.fl_cpart_stride;
   if (tid == 0 && p.ts != nullptr && ts_row < 320) {
     p.ts[size_t(ts_row) * 64 + 0] = clock64();
     p.ts[size_t(ts_row) * 64 + 62] = fglobaltimer_ns();
@@ -468,201 +485,222 @@ apa_flow_contract_kernel(const FusedParams p) {
     }
   };
   load_w(0);        // does not depend on this call's STREAM / REDUCE
-  griddep_wait();   // REDUCE (and so STREAM) of this call has finished: g[b] and gsum[b] are visible
+  griddep_wait();   // REDUCE (and so STREAM) of this call has finished: g[b] is visible
   if (tid == 0 && p.ts != nullptr && ts_row < 320) p.ts[size_t(ts_row) * 64 + 1] = clock64();
 
-  // thread tile of the contraction: 4 videos x 4 classes, one half of the unit's channels
+  // thread tile of the contraction: 2 videos x 4 classes of a 16-video half, one half of the unit's channels
   const int ks = tid >> 6;                       // channel half
-  const int vr = (tid & 63) >> 3, cq = tid & 7;  // video group (4 videos), class group (4 classes)
-  constexpr int NP = kVideoTile * (CH / 4) / kCThreads;   // float4s of g per thread and rank (8, or 4 for C = 1024)
+  const int vr = (tid & 63) >> 3, cq = tid & 7;  // video pair, class group (4 classes)
+  constexpr int NP = kVideoTile * (CH / 4) / kCThreads;   // float4s of g per thread, rank and tile (8, or 4 for C = 1024)
+  constexpr int NH = NP / 2;                              // ... per 16-video half
   for (int tile = 0; tile < ntile; ++tile) {
     const int v0 = tile * kVideoTile;
-    if (tile != 0) __syncthreads();  // sS / red of the previous tile fully consumed
-    if (tid < kVideoTile * 4) {      // attention mass per (video, rank): sum over frames
-      const int vi = tid >> 2, j = tid & 3, v = v0 + vi;
-      float mass = 0.f;
-      if (v < Bv && j < R)
-        for (int fr = 0; fr < F; ++fr) mass += __ldcg(p.gsum + size_t(v * F + fr) * 4 + j);
-      sS[tid] = mass;
-    }
-    float acc[4][4];
+    float acc[2][2][4];   // [half][video of the pair][class]
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int m = 0; m < 4; ++m) acc[i][m] = 0.f;
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc[h][i][m] = 0.f;
     for (int j = 0; j < R; ++j) {
       if (j != 0 || tile != 0) {
         __syncthreads();                      // previous operands fully consumed
         if (R > 1) load_w(j);                 // rank 1: the block loaded before the wait stays valid
       }
-      // ---- operand g: this unit's channels of 32 videos, frames summed.  thread = (video, 4 channels); all NP
-      //      loads of a frame in flight together
+      // ---- operand g: this unit's channels of 32 videos, frames summed.  All NP loads of a frame are in flight
+      //      together (one round trip); the two 16-video halves then pass through shared memory one after the other.
+      float4 a4[NP];
 #pragma unroll
-      for (int h0 = 0; h0 < NP; h0 += NP) {
-        float4 a4[NP];
-#pragma unroll
-        for (int h = 0; h < NP; ++h) a4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int fr = 0; fr < F; ++fr) {
-#pragma unroll
-          for (int h = 0; h < NP; ++h) {
-            const int idx = tid + (h0 + h) * kCThreads;
-            const int vi = idx / (CH / 4), c4 = idx - vi * (CH / 4);
-            if (v0 + vi < Bv) {
-              const float4 gv = __ldcg(reinterpret_cast<const float4*>(
-                  p.g + ((size_t(v0 + vi) * F + fr) * R + j) * C + c_base + c4 * 4));
-              a4[h].x += gv.x; a4[h].y += gv.y; a4[h].z += gv.z; a4[h].w += gv.w;
-            }
-          }
-        }
+      for (int h = 0; h < NP; ++h) a4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int fr = 0; fr < F; ++fr) {
 #pragma unroll
         for (int h = 0; h < NP; ++h) {
-          const int idx = tid + (h0 + h) * kCThreads;
+          const int idx = tid + h * kCThreads;            // half = h / NH, then (video in half, 4 channels)
           const int vi = idx / (CH / 4), c4 = idx - vi * (CH / 4);
-          *reinterpret_cast<float4*>(gs + vi * GS + c4 * 4) = a4[h];
+          if (v0 + vi < Bv) {
+            const float4 gv = __ldcg(reinterpret_cast<const float4*>(
+                gin + ((size_t(v0 + vi) * F + fr) * R + j) * C + c_base + c4 * 4));
+            a4[h].x += gv.x; a4[h].y += gv.y; a4[h].z += gv.z; a4[h].w += gv.w;
+          }
         }
       }
-      __syncthreads();
-      if (tid == 0 && tile == 0 && j == 0 && p.ts != nullptr && ts_row < 320) p.ts[size_t(ts_row) * 64 + 2] = clock64();
-      // ---- contraction: acc[i][m] += g[4 vr + i][c] * W[c][4 cq + m] over this thread's channel half
-      {
-        const float* g0 = gs + (vr * 4) * GS + ks * (CH / 2);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half != 0) __syncthreads();       // first half fully consumed
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const int idx = tid + h * kCThreads;            // index within the half
+          const int vi = idx / (CH / 4), c4 = idx - vi * (CH / 4);
+          *reinterpret_cast<float4*>(gs + vi * GS + c4 * 4) = a4[half * NH + h];
+        }
+        __syncthreads();
+        // ---- contraction: acc[half][i][m] += g[2 vr + i][c] * W[c][4 cq + m] over this thread's channel half
+        const float* g0 = gs + (vr * 2) * GS + ks * (CH / 2);
         const float* w0 = Ws + (ks * (CH / 2)) * kKW + cq * 4;
 #pragma unroll 2
         for (int c = 0; c < CH / 2; c += 4) {
-          float4 gv[4], wv[4];
+          float4 gv[2], wv[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) gv[i] = *reinterpret_cast<const float4*>(g0 + i * GS + c);
+          for (int i = 0; i < 2; ++i) gv[i] = *reinterpret_cast<const float4*>(g0 + i * GS + c);
 #pragma unroll
           for (int m = 0; m < 4; ++m) wv[m] = *reinterpret_cast<const float4*>(w0 + (c + m) * kKW);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc[i][0] = fmaf(gv[i].x, wv[0].x, acc[i][0]); acc[i][1] = fmaf(gv[i].x, wv[0].y, acc[i][1]);
-            acc[i][2] = fmaf(gv[i].x, wv[0].z, acc[i][2]); acc[i][3] = fmaf(gv[i].x, wv[0].w, acc[i][3]);
-            acc[i][0] = fmaf(gv[i].y, wv[1].x, acc[i][0]); acc[i][1] = fmaf(gv[i].y, wv[1].y, acc[i][1]);
-            acc[i][2] = fmaf(gv[i].y, wv[1].z, acc[i][2]); acc[i][3] = fmaf(gv[i].y, wv[1].w, acc[i][3]);
-            acc[i][0] = fmaf(gv[i].z, wv[2].x, acc[i][0]); acc[i][1] = fmaf(gv[i].z, wv[2].y, acc[i][1]);
-            acc[i][2] = fmaf(gv[i].z, wv[2].z, acc[i][2]); acc[i][3] = fmaf(gv[i].z, wv[2].w, acc[i][3]);
-            acc[i][0] = fmaf(gv[i].w, wv[3].x, acc[i][0]); acc[i][1] = fmaf(gv[i].w, wv[3].y, acc[i][1]);
-            acc[i][2] = fmaf(gv[i].w, wv[3].z, acc[i][2]); acc[i][3] = fmaf(gv[i].w, wv[3].w, acc[i][3]);
+          for (int i = 0; i < 2; ++i) {
+            float* a = acc[half][i];
+            a[0] = fmaf(gv[i].x, wv[0].x, a[0]); a[1] = fmaf(gv[i].x, wv[0].y, a[1]);
+            a[2] = fmaf(gv[i].x, wv[0].z, a[2]); a[3] = fmaf(gv[i].x, wv[0].w, a[3]);
+            a[0] = fmaf(gv[i].y, wv[1].x, a[0]); a[1] = fmaf(gv[i].y, wv[1].y, a[1]);
+            a[2] = fmaf(gv[i].y, wv[1].z, a[2]); a[3] = fmaf(gv[i].y, wv[1].w, a[3]);
+            a[0] = fmaf(gv[i].z, wv[2].x, a[0]); a[1] = fmaf(gv[i].z, wv[2].y, a[1]);
+            a[2] = fmaf(gv[i].z, wv[2].z, a[2]); a[3] = fmaf(gv[i].z, wv[2].w, a[3]);
+            a[0] = fmaf(gv[i].w, wv[3].x, a[0]); a[1] = fmaf(gv[i].w, wv[3].y, a[1]);
+            a[2] = fmaf(gv[i].w, wv[3].z, a[2]); a[3] = fmaf(gv[i].w, wv[3].w, a[3]);
           }
         }
       }
+      if (tid == 0 && tile == 0 && j == 0 && p.ts != nullptr && ts_row < 320) p.ts[size_t(ts_row) * 64 + 2] = clock64();
     }
-    // ---- the two channel halves meet in shared memory (red aliases gs), fixed order
-    __syncthreads();
-    float* red = gs;  // [2][32 videos][kKW]
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<float4*>(red + (ks * kVideoTile + vr * 4 + i) * kKW + cq * 4) =
-          make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    __syncthreads();
+    // ---- the two channel halves meet in shared memory (red aliases gs), fixed order; then this unit's partial
+    //      [32 videos][32 classes] block goes to the workspace (FINISH adds the 16 channel slices)
     const int cslot = tile * NS + sl;
-    float* cp = p.cpart + (size_t(cslot) * kNJ + cj) * (kVideoTile * kKW);
+    float* cpo = cpart + (size_t(cslot) * kNJ + cj) * (kVideoTile * kKW);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int o = (tid + h * kCThreads) * 4;
+    for (int half = 0; half < 2; ++half) {
+      __syncthreads();
+      float* red = gs;  // [2][16 videos][kKW]
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        *reinterpret_cast<float4*>(red + (ks * kVH + vr * 2 + i) * kKW + cq * 4) =
+            make_float4(acc[half][i][0], acc[half][i][1], acc[half][i][2], acc[half][i][3]);
+      __syncthreads();
+      const int o = tid * 4;   // 16 x 32 outputs of the half = one float4 per thread
       float4 r0 = *reinterpret_cast<const float4*>(red + o);
-      const float4 r1 = *reinterpret_cast<const float4*>(red + kVideoTile * kKW + o);
+      const float4 r1 = *reinterpret_cast<const float4*>(red + kVH * kKW + o);
       r0.x += r1.x; r0.y += r1.y; r0.z += r1.z; r0.w += r1.w;
-      *reinterpret_cast<float4*>(cp + o) = r0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned long long prev = atom_add_acq_rel(p.fl_arr + cslot, 1ull);
-      *flag_s = ((prev + 1) % kNJ == 0) ? 1 : 0;
-      if (tile == 0 && p.ts != nullptr && ts_row < 320) p.ts[size_t(ts_row) * 64 + 3] = clock64();
-    }
-    __syncthreads();
-    if (*flag_s) {
-      // ---- 16th arrival for this (tile, class slice): fixed-order sum of the 16 partial blocks, bias, logits
-      size_t gw_off = 0;
-      if (p.gw_world > 0) {  // this step's ring buffer must be free on every peer (they started step - depth + 1)
-        if (tid == 0) {
-          const unsigned long long step = peer_gather_step(p.gw_done);
-          if (p.gw_world > 1 && step >= (unsigned long long)p.gw_depth)
-            peer_gather_wait_all(p.gw_world, p.gw_flags[p.gw_rank], p.gw_world, step - p.gw_depth + 1);
-          *step_s = step;
-        }
-        __syncthreads();
-        gw_off = size_t(*step_s % (unsigned long long)p.gw_depth) * size_t(p.gw_world) * Bv * K;
-      }
-      const float* cb0 = p.cpart + size_t(cslot) * kNJ * (kVideoTile * kKW);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int o = (tid + h * kCThreads) * 4;
-        float sum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c0 = 0; c0 < kNJ; c0 += 8) {   // eight loads in flight at a time, summed in index order
-          float4 pv[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            pv[c] = __ldcg(reinterpret_cast<const float4*>(cb0 + size_t(c0 + c) * (kVideoTile * kKW) + o));
-#pragma unroll
-          for (int c = 0; c < 8; ++c) { sum[0] += pv[c].x; sum[1] += pv[c].y; sum[2] += pv[c].z; sum[3] += pv[c].w; }
-        }
-        const int vi = o / kKW, kk0 = o % kKW;
-        const int v = v0 + vi;
-        if (v < Bv) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int kk = kk0 + m, k = k_lo + kk;
-            if (kk < width) {
-              float val = sum[m];
-              for (int j = 0; j < R; ++j) val = fmaf(__ldg(p.td_b[j] + k), sS[vi * 4 + j], val);
-              val *= p.inv_scale;
-              if (p.gw_world > 0) {
-                const size_t off = gw_off + (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
-                for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
-              } else {
-                p.logits[size_t(v) * K + k] = val;
-              }
-            }
-          }
-        }
-      }
-      if (p.gw_world > 0) {
-        if (p.gw_world > 1) __threadfence_system();  // my peer stores are visible system-wide before I am counted
-        __syncthreads();
-        if (tid == 0) {
-          const unsigned long long prev2 = atom_add_acq_rel(p.fl_ctr + 2, 1ull);
-          const unsigned long long nslices = (unsigned long long)ntile * NS;
-          if ((prev2 & (kStride - 1)) == nslices - 1) {  // the launch's last logits are stored: complete the step
-            (void)atom_add_relaxed(p.fl_ctr + 2, kStride - nslices);
-            peer_gather_complete(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, *step_s);
-          }
-        }
-      }
+      *reinterpret_cast<float4*>(cpo + half * (kVH * kKW) + o) = r0;
     }
   }
   if (tid == 0 && p.ts != nullptr && ts_row < 320) {
+    p.ts[size_t(ts_row) * 64 + 3] = clock64();
     p.ts[size_t(ts_row) * 64 + 5] = clock64();
     p.ts[size_t(ts_row) * 64 + 63] = fglobaltimer_ns();
   }
 }
 
+// ================================================================================================ FINISH
+// One 128-thread CTA per (video tile, class slice): adds the 16 channel-slice partials in index order
+// (bit-reproducible), bias x attention mass, scale, and stores the logits (or the peer stores of the fused all-gather).
+__global__ void __launch_bounds__(kCThreads, 8)
+apa_flow_finish_kernel(const FusedParams p) {
+  __shared__ float sS[kVideoTile * 4];
+  __shared__ unsigned long long call_s[2];   // [0] call, [1] gather step
+  const int R = p.R, K = p.K, F = p.F, NS = p.fl_NS;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x / NS, sl = blockIdx.x - tile * NS;
+  const int k_lo = int((long long)K * sl / NS), k_hi = int((long long)K * (sl + 1) / NS);
+  const int width = k_hi - k_lo;
+  const int Bv = p.B / F, v0 = tile * kVideoTile;
+  if (tid == 0) call_s[0] = flow_ticket(p.fl_ctr + kCtrTF, gridDim.x);
+  __syncthreads();
+  griddep_launch_dependents();
+  griddep_wait();   // CONTRACT of this call has finished: the partial blocks are visible
+  const size_t cp = size_t(call_s[0] & (kFlowDepth - 1));
+  const float* const gsum = p.gsum + cp * p.fl_gsum_stride;
+  const float* const cb0 = p.cpart + cp * p.fl_cpart_stride + size_t(blockIdx.x) * kNJ * (kVideoTile * kKW);
+  if (tid < kVideoTile * 4) {      // attention mass per (video, rank): sum over frames
+    const int vi = tid >> 2, j = tid & 3, v = v0 + vi;
+    float mass = 0.f;
+    if (v < Bv && j < R)
+      for (int fr = 0; fr < F; ++fr) mass += __ldcg(gsum + size_t(v * F + fr) * 4 + j);
+    sS[tid] = mass;
+  }
+  size_t gw_off = 0;
+  if (p.gw_world > 0) {  // this step's ring buffer must be free on every peer (they started step - depth + 1)
+    if (tid == 0) {
+      const unsigned long long step = __ldcg(p.fl_ctr + kCtrGwStep + cp);   // drawn by STREAM CTA 0 of this call
+      if (p.gw_world > 1 && step >= (unsigned long long)p.gw_depth)
+        peer_gather_wait_all(p.gw_world, p.gw_flags[p.gw_rank], p.gw_world, step - p.gw_depth + 1);
+      call_s[1] = step;
+    }
+  }
+  __syncthreads();
+  if (p.gw_world > 0) gw_off = size_t(call_s[1] % (unsigned long long)p.gw_depth) * size_t(p.gw_world) * Bv * K;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int o = (tid + h * kCThreads) * 4;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c0 = 0; c0 < kNJ; c0 += 8) {   // eight loads in flight at a time, summed in index order
+      float4 pv[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        pv[c] = __ldcg(reinterpret_cast<const float4*>(cb0 + size_t(c0 + c) * (kVideoTile * kKW) + o));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { sum[0] += pv[c].x; sum[1] += pv[c].y; sum[2] += pv[c].z; sum[3] += pv[c].w; }
+    }
+    const int vi = o / kKW, kk0 = o % kKW;
+    const int v = v0 + vi;
+    if (v < Bv) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int kk = kk0 + m, k = k_lo + kk;
+        if (kk < width) {
+          float val = sum[m];
+          for (int j = 0; j < R; ++j) val = fmaf(__ldg(p.td_b[j] + k), sS[vi * 4 + j], val);
+          val *= p.inv_scale;
+          if (p.gw_world > 0) {
+            const size_t off = gw_off + (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
+            for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
+          } else {
+            p.logits[size_t(v) * K + k] = val;
+          }
+        }
+      }
+    }
+  }
+  if (p.gw_world > 1) __threadfence_system();  // my peer stores are visible system-wide before I am counted
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned long long prev2 = atom_add_acq_rel(p.fl_ctr + kCtrDone, 1ull);
+    if ((prev2 & (kStride - 1)) == (unsigned long long)(gridDim.x - 1)) {
+      // the call's last logits are stored: the gather step is complete, and so is the call (pad the counter to the
+      // next multiple of 2^20: its upper bits count the completed calls, which frees copy L % 2 for call L + 2)
+      if (p.gw_world > 0) peer_gather_complete(p.gw_world, p.gw_rank, p.gw_flags, p.gw_done, call_s[1]);
+      (void)atom_add_acq_rel(p.fl_ctr + kCtrDone, kStride - (unsigned long long)gridDim.x);
+    }
+  }
+}
+
 using FKernelFn = void (*)(const FusedParams);
 
-FKernelFn flow_stream_select(int Q, int rmax, int mode) {
+template <int NG, int STG, int MAXREG>
+FKernelFn flow_stream_select_shape(int Q, int rmax, int mode) {
   if (Q == 2) {
     if (rmax == 1) {
-      if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<2, 1, MODE_PLAIN>;
-      if (mode == MODE_RELU) return &apa_flow_stream_kernel<2, 1, MODE_RELU>;
-      return &apa_flow_stream_kernel<2, 1, MODE_SOFTMAX>;
+      if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<2, 1, MODE_PLAIN, NG, STG, MAXREG>;
+      if (mode == MODE_RELU) return &apa_flow_stream_kernel<2, 1, MODE_RELU, NG, STG, MAXREG>;
+      return &apa_flow_stream_kernel<2, 1, MODE_SOFTMAX, NG, STG, MAXREG>;
     }
-    if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<2, APA_MAX_RANK, MODE_PLAIN>;
-    if (mode == MODE_RELU) return &apa_flow_stream_kernel<2, APA_MAX_RANK, MODE_RELU>;
+    if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<2, APA_MAX_RANK, MODE_PLAIN, NG, STG, MAXREG>;
+    if (mode == MODE_RELU) return &apa_flow_stream_kernel<2, APA_MAX_RANK, MODE_RELU, NG, STG, MAXREG>;
     return nullptr;
   }
   if (Q == 1) {
     if (rmax == 1) {
-      if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<1, 1, MODE_PLAIN>;
-      if (mode == MODE_RELU) return &apa_flow_stream_kernel<1, 1, MODE_RELU>;
-      return &apa_flow_stream_kernel<1, 1, MODE_SOFTMAX>;
+      if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<1, 1, MODE_PLAIN, NG, STG, MAXREG>;
+      if (mode == MODE_RELU) return &apa_flow_stream_kernel<1, 1, MODE_RELU, NG, STG, MAXREG>;
+      return &apa_flow_stream_kernel<1, 1, MODE_SOFTMAX, NG, STG, MAXREG>;
     }
-    if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<1, APA_MAX_RANK, MODE_PLAIN>;
-    if (mode == MODE_RELU) return &apa_flow_stream_kernel<1, APA_MAX_RANK, MODE_RELU>;
+    if (mode == MODE_PLAIN) return &apa_flow_stream_kernel<1, APA_MAX_RANK, MODE_PLAIN, NG, STG, MAXREG>;
+    if (mode == MODE_RELU) return &apa_flow_stream_kernel<1, APA_MAX_RANK, MODE_RELU, NG, STG, MAXREG>;
   }
   return nullptr;
+}
+FKernelFn flow_stream_select(int Q, int rmax, int mode, int shape, int* stages, int* ng) {
+  if (shape == 1) { *stages = 3; *ng = 2; return flow_stream_select_shape<2, 3, 96>(Q, rmax, mode); }
+  if (shape == 2) { *stages = 3; *ng = 1; return flow_stream_select_shape<1, 3, 72>(Q, rmax, mode); }
+  *stages = 4; *ng = 2;
+  return flow_stream_select_shape<2, 4, 128>(Q, rmax, mode);
 }
 FKernelFn flow_contract_select(int Q) {
   if (Q == 2) return &apa_flow_contract_kernel<2>;
@@ -716,24 +754,38 @@ size_t flow_slices(int B, int K, int F) {  // (video tile, class slice) pairs = 
   return size_t(ntile) * flow_class_slices(K);
 }
 size_t flow_cpart_floats(int B, int K, int F) { return flow_slices(B, K, F) * kNJ * kVideoTile * kKW; }
-size_t flow_smem(int C) { return stream_smem_bytes(C); }
+size_t flow_smem(int C) { return stream_smem_bytes(C, 4); }
 
 cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuning, cudaStream_t stream,
                         int* stream_grid, int* contract_grid) {
   static_assert(kVideoTile * kKW == 8 * kCThreads, "two float4s of the partial block per thread");
+  static_assert(kVH * kKW == 4 * kCThreads, "one float4 of a 16-video half per thread");
   FusedParams p = p_in;
   const int Q = p.C / 1024, rmax = (p.R == 1) ? 1 : APA_MAX_RANK;
-  FKernelFn sfn = flow_stream_select(Q, rmax, mode), cfn = flow_contract_select(Q);
+  int stages = 4, ng = 2;
+  const int shape = tuning ? tuning->cluster_size : 0;
+  FKernelFn sfn = flow_stream_select(Q, rmax, mode, shape, &stages, &ng), cfn = flow_contract_select(Q);
+  p.fl_ng = ng;
   FKernelFn rfn = (mode == MODE_SOFTMAX) ? &apa_flow_reduce_kernel<true> : &apa_flow_reduce_kernel<false>;
   if (sfn == nullptr || cfn == nullptr) return cudaErrorInvalidValue;
-  const size_t smem1 = stream_smem_bytes(p.C), smem2 = contract_smem_bytes(p.C);
+  const size_t smem1 = stream_smem_bytes(p.C, stages), smem2 = contract_smem_bytes(p.C);
   cudaError_t err = flow_prepare(reinterpret_cast<const void*>(sfn), smem1);
   if (err != cudaSuccess) return err;
   err = flow_prepare(reinterpret_cast<const void*>(cfn), smem2);
   if (err != cudaSuccess) return err;
   p.fl_G = flow_stream_ctas(p.B, p.HW, tuning);
+  {
+    const size_t slots = flow_gpart_slots(p.B);
+    p.fl_gpart_stride = slots * p.R * p.C;
+    p.fl_gstat_stride = slots * 8;
+    p.fl_g_stride = size_t(p.B) * p.R * p.C;
+    p.fl_gsum_stride = size_t(p.B) * 4;
+    p.fl_cpart_stride = flow_cpart_floats(p.B, p.K, p.F);
+    p.fl_arr_stride = flow_slices(p.B, p.K, p.F);
+  }
   p.fl_NS = flow_class_slices(p.K);
   p.inputs_stable = (tuning && tuning->inputs_stable) ? 1 : 0;
+  p.fl_debug_nowait = (tuning && tuning->fused >= 100) ? 1 : 0;
   const int grid2 = kNJ * p.fl_NS;
   if (stream_grid) *stream_grid = p.fl_G;
   if (contract_grid) *contract_grid = grid2;
@@ -750,6 +802,8 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   cfg.numAttrs = na;
   err = cudaLaunchKernelEx(&cfg, sfn, p);
   if (err != cudaSuccess) return err;
+  const int dbg = tuning ? tuning->fused : -1;   // measurement only: 100 = STREAM alone, 101 = STREAM + REDUCE
+  if (dbg == 100) return cudaSuccess;
   cudaLaunchConfig_t cfgr = {};
   cfgr.gridDim = dim3(p.B, (p.C / 4 + kRThreads - 1) / kRThreads, 1);
   cfgr.blockDim = dim3(kRThreads, 1, 1);
@@ -758,6 +812,7 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   cfgr.numAttrs = na;
   err = cudaLaunchKernelEx(&cfgr, rfn, p);
   if (err != cudaSuccess) return err;
+  if (dbg == 101) return cudaSuccess;
   cudaLaunchConfig_t cfg2 = {};
   cfg2.gridDim = dim3(grid2, 1, 1);
   cfg2.blockDim = dim3(kCThreads, 1, 1);
@@ -765,7 +820,16 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   cfg2.stream = stream;
   cfg2.attrs = at;
   cfg2.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg2, cfn, p);
+  err = cudaLaunchKernelEx(&cfg2, cfn, p);
+  if (err != cudaSuccess) return err;
+  if (dbg == 102) return cudaSuccess;
+  cudaLaunchConfig_t cfg3 = {};
+  cfg3.gridDim = dim3(unsigned(flow_slices(p.B, p.K, p.F)), 1, 1);
+  cfg3.blockDim = dim3(kCThreads, 1, 1);
+  cfg3.stream = stream;
+  cfg3.attrs = at;
+  cfg3.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg3, &apa_flow_finish_kernel, p);
 }
 
 }  // namespace apa

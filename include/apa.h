@@ -179,7 +179,7 @@ int apa_attn_pool_fwd_host(const ApaDesc* desc, const float* X_host, const ApaWe
  * stores its [batch/frames, K] block straight into a gathered buffer on every peer (NVLink peer stores from
  * the kernel's last step) at row offset rank * batch/frames, then publishes a per-rank step flag.  The gathered
  * buffers form a ring of `depth` buffers on every rank: call number `step` (1, 2, 3, ... counted on the device in
- * counters[1], so CUDA-graph replays keep counting; the same on every rank) lands in buffer step % depth.
+ * `counters`, so CUDA-graph replays keep counting; the same on every rank) lands in buffer step % depth.
  *   completeness  After the call, in stream order, buffer (step - lag) % depth holds the blocks of ALL ranks for
  *                 step - lag, where lag = ApaTuning.gather_wait_lag (0 by default: this step, every call then
  *                 waits for the slowest rank; lag >= 1 pipelines the consumer behind the producers; lag < 0:
@@ -199,7 +199,8 @@ typedef struct ApaPeerGather {
   int32_t reserved0;                                 /* must be 0                                          */
   float* peer_logits[APA_MAX_PEERS];                 /* peer q's ring [depth][world * batch/frames][K]      */
   unsigned long long* peer_flags[APA_MAX_PEERS];     /* peer q's flag array [2 * world]                     */
-  unsigned long long* counters;                      /* 2 local words: [0] scratch, [1] calls completed     */
+  unsigned long long* counters;                      /* 4 local words: [0] scratch, [1] calls completed,    */
+                                                     /*                [2] steps drawn, [3] reserved        */
 } ApaPeerGather;
 
 /* apa_attn_pool_fwd for the batch-sharded multi-GPU path (single-map head only): logits go to the peers'

@@ -32,12 +32,12 @@ for form, name in ((0, "auto"), (ops.APA_FORM_FLOW, "flow"), (ops.APA_FORM_PIPEL
     for lanes in (1, 2, 4):
         for stable in ((1,) if form != ops.APA_FORM_FLOW else (0, 1)):
             CONFIGS.append((name, form, lanes, stable, 0))
-CONFIGS += [("flow", ops.APA_FORM_FLOW, 1, 1, 74), ("flow", ops.APA_FORM_FLOW, 4, 1, 74),
-            ("flow", ops.APA_FORM_FLOW, 1, 1, 111), ("flow", ops.APA_FORM_FLOW, 2, 1, 111)]
+CONFIGS += [("flow", ops.APA_FORM_FLOW, 4, 1, 74), ("flow", ops.APA_FORM_FLOW, 3, 1, 0)]
+LEADS = (0, 2, 6, -1)
 
 
-def run_cfg(name, form, lanes, stable, max_ctas):
-    tun = ops.make_tuning(form=form, inputs_stable=stable, max_ctas=max_ctas)
+def run_cfg(name, form, lanes, stable, max_ctas, lead=0):
+    tun = ops.make_tuning(form=form, inputs_stable=stable, max_ctas=max_ctas, pdl_trigger_lead=lead)
     opl = [ops.AttnPoolOp(P, K, HW, channels=C, frames=F, rank=rank, flags=bits, tuning=tun, device=dev)
            for _ in range(lanes)]
     plan = ops.attn_pool_plan(opl[0].desc(B), tun)
@@ -95,14 +95,15 @@ def run_cfg(name, form, lanes, stable, max_ctas):
         torch.cuda.synchronize()
         lat.append(a.elapsed_time(b) * 1e3)
     lat.sort()
-    print("%-9s lanes=%d stable=%d max_ctas=%3d [%s, kind %d, grid %d]: %7.2f us/step  %5.2f TB/s  frac %.3f | one launch: %6.1f us (median of 12)"
-          % (name, lanes, stable, max_ctas, mode, plan["cluster_local"], plan["grid"], us, algo / us / 1e6,
+    print("%-9s lanes=%d stable=%d max_ctas=%3d lead=%2d [%s, kind %d, grid %d]: %7.2f us/step  %5.2f TB/s  frac %.3f | one launch: %6.1f us (median of 12)"
+          % (name, lanes, stable, max_ctas, lead, mode, plan["cluster_local"], plan["grid"], us, algo / us / 1e6,
              algo / us / 1e6 / 6.5748, lat[len(lat) // 2]), flush=True)
 
 
 print("B=%d HW=%d K=%d F=%d: %.2f MB algorithmic per step, roofline %.2f us at 6574.8 GB/s" % (B, HW, K, F, algo / 1e6, algo / 6574.8e3))
 for c in CONFIGS:
-    try:
-        run_cfg(*c)
-    except Exception as e:
-        print("%-9s lanes=%d stable=%d max_ctas=%d: FAILED %s" % (c[0], c[2], c[3], c[4], e), flush=True)
+    for lead in (LEADS if (c[1] == ops.APA_FORM_FLOW and c[3] == 1) else (0,)):
+        try:
+            run_cfg(*c, lead=lead)
+        except Exception as e:
+            print("%-9s lanes=%d stable=%d max_ctas=%d: FAILED %s" % (c[0], c[2], c[3], c[4], e), flush=True)

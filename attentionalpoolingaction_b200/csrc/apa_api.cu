@@ -1,5 +1,6 @@
 // apa_api.cu — the C ABI declared in include/apa.h: validation, workspace carving, path selection.
-// Host-side only; every kernel lives in apa_pool_fused.cu / apa_dense.cu.
+// Host-side only; the kernels live in apa_pool_flow.cu / apa_pool_cluster.cu (single-map head), apa_gemm_tc.cu and
+// apa_dense.cu (dense path, Gram).
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
@@ -9,7 +10,6 @@
 #include "apa_kernels.h"
 
 namespace {
-
 
 using namespace apa;
 
@@ -21,17 +21,19 @@ inline int mode_of(int flags) {
   return MODE_PLAIN;
 }
 
-constexpr size_t kCtrlBytes = 4096;         // [0, 2048): 256 x u64 grid-barrier counters, indexed by gridDim.x
-constexpr size_t kFlowCtrOff = 2048;        // [2048, 4096): the flow form's ticket / done / arrival counters
-constexpr size_t kTsBytes = 320 * 64 * 8;  // debug timeline: up to 320 CTAs x 64 stamps
+constexpr size_t kCtrlBytes = 4096;         // control block; the flow form's counters start at kFlowCtrOff
+constexpr size_t kFlowCtrOff = 2048;
+constexpr size_t kTsBytes = 320 * 64 * 8;   // debug timeline: up to 320 CTAs x 64 stamps
 
 struct Carve {
-  size_t ctrl, ts, g, sn, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, cpart, gsum, fl_g, fl_arr, total;
-  int path;  // 0 fused single-map, 1 dense
+  size_t ts, smx, attn_raw, pose_pre, a0, A, T, gpart, gstat, g, gsum, cpart, total;
+  int path;  // 0 single-map fast path, 1 dense
 };
 
-bool use_fused_path(const ApaDesc* d, int want_topdown) {
-  return !(d->flags & APA_FLAG_PER_CLASS) && !want_topdown && fused_supported(d->channels, d->rank);
+// the single-map fast path: one attention map, no materialised top-down end point, a shape the kernels take
+bool use_fast_path(const ApaDesc* d, int want_topdown) {
+  return !(d->flags & APA_FLAG_PER_CLASS) && !want_topdown &&
+         flow_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames);
 }
 
 Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
@@ -40,9 +42,8 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
   const size_t B = d->batch, HW = d->hw, C = d->channels, K = d->num_classes, R = d->rank;
   const size_t M = (d->flags & APA_FLAG_PER_CLASS) ? K : 1;
   const bool single = (d->flags & APA_FLAG_SINGLE_LAYER_ATT) != 0;
-  c.path = use_fused_path(d, want_topdown) ? 0 : 1;
-  size_t off = kCtrlBytes;  // control block: one grid-barrier counter per grid size
-  c.ctrl = 0;
+  c.path = use_fast_path(d, want_topdown) ? 0 : 1;
+  size_t off = kCtrlBytes;
   auto take = [&](size_t floats) {
     size_t o = off;
     off = align_up(off + floats * sizeof(float), 256);
@@ -50,24 +51,16 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
   };
   if (c.path == 0) {
     c.ts = take(kTsBytes / sizeof(float));
-    c.g = take(B * R * C);
-    c.sn = take(B * R);
     c.smx = take(B * 2);
     if (want_attn) c.attn_raw = take(B * HW);
     if (!single) c.a0 = take(B * HW * 8);  // up to 8 partial-dot planes from the pose GEMM epilogue
-    if (split_eligible(d->channels, d->rank)) {  // pipeline / flow forms: partial g and stats per row run
-      size_t slots = B * size_t(split_lp_cap(d->batch, d->hw));
-      if (flow_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) {
-        // the flow form keeps kFlowDepth copies of every per-call buffer (call L uses copy L % kFlowDepth)
-        if (kFlowDepth * flow_gpart_slots(d->batch) > slots) slots = kFlowDepth * flow_gpart_slots(d->batch);
-        c.cpart = take(kFlowDepth * flow_cpart_floats(d->batch, d->num_classes, d->frames));
-        c.gsum = take(kFlowDepth * B * 4);
-        c.fl_g = take(kFlowDepth * B * R * C);
-        c.fl_arr = take(kFlowDepth * flow_slices(d->batch, d->num_classes, d->frames) * 2);
-      }
-      c.gpart = take(slots * R * C);
-      c.gstat = take(slots * 8);
-    }
+    // the flow form keeps kFlowDepth copies of every per-call buffer (call L uses copy L % kFlowDepth)
+    const size_t slots = flow_gpart_slots(d->batch);
+    c.gpart = take(kFlowDepth * slots * R * C);
+    c.gstat = take(kFlowDepth * slots * 8);
+    c.g = take(kFlowDepth * B * R * C);
+    c.gsum = take(kFlowDepth * B * 4);
+    c.cpart = take(kFlowDepth * flow_cpart_floats(d->batch, d->num_classes, d->frames));
   } else {
     if (!want_attn) c.A = take(B * HW * M * R);
     if (!want_topdown) c.T = take(B * HW * K * R);
@@ -77,35 +70,13 @@ Carve carve(const ApaDesc* d, int want_attn, int want_topdown, int want_pose) {
   return c;
 }
 
-// ApaTuning.form (APA_FORM_*) selects the form of the fused single-map head (A/B tests, tools).
-bool use_flow(const ApaDesc* d, const ApaTuning* t) {
-  if (!flow_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) return false;
-  const int force = t ? t->form : 0;
-  if (force == APA_FORM_FLOW) return true;
-  if (force != APA_FORM_AUTO) return false;
-  // measured (scripts/bench_flow.py, flow_parts.py; profiles/): the flow form has the shortest single call at every
-  // shape and the highest throughput with several batches in flight; it is the default wherever it applies
-  return true;
-}
-
-bool use_split(const ApaDesc* d, const ApaTuning* t) {
-  if (!split_eligible(d->channels, d->rank)) return false;
-  const int force = t ? t->form : 0;
-  if (force == APA_FORM_PIPELINE) return true;
-  if (force != APA_FORM_AUTO) return false;
-  if (t && (t->fused >= 0 || t->max_ctas != 0 || t->cluster_size != 0)) return false;  // explicit single-kernel requests
-  // measured (scripts/bench_forms.py): the pipeline wins when several frames are averaged per video (its
-  // contraction sums the frames' partial g before the matrix product); otherwise the single-kernel forms do
-  return d->frames > 1;
-}
-
-bool use_local(const ApaDesc* d, const ApaWeights* w, const ApaTuning* t) {
-  if (!local_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) return false;
-  if (t && (t->fused == 0 || (t->cluster_size != 0 && t->cluster_size != 16) || t->max_ctas != 0)) return false;
-  if (t && (t->form == APA_FORM_GRID_BARRIER || t->form == APA_FORM_FLOW)) return false;
+// APA_FORM_CLUSTER only on request and only where that kernel applies; everything else takes the flow form
+bool use_cluster(const ApaDesc* d, const ApaWeights* w, const ApaTuning* t) {
+  if (t == nullptr || t->form != APA_FORM_CLUSTER) return false;
+  if (!cluster_eligible(d->batch, d->hw, d->channels, d->num_classes, d->rank, d->frames)) return false;
   if (w)
     for (int r = 0; r < d->rank; ++r)
-      if (reinterpret_cast<uintptr_t>(w->topdown_w[r]) & 15u) return false;  // bulk copies need 16 B alignment
+      if (reinterpret_cast<uintptr_t>(w->topdown_w[r]) & 15u) return false;  // its bulk copies of B_r need 16 B alignment
   return true;
 }
 
@@ -124,6 +95,16 @@ int check_desc(const ApaDesc* d) {
     if (d->reserved[i] != 0) return APA_ERR_UNSUPPORTED;
   // 32-bit index headroom inside the kernels
   if (double(d->batch) * d->hw >= 2147483647.0) return APA_ERR_SHAPE;
+  return APA_OK;
+}
+
+int check_tuning(const ApaTuning* t) {
+  if (t == nullptr) return APA_OK;
+  if (t->form != APA_FORM_AUTO && t->form != APA_FORM_FLOW && t->form != APA_FORM_CLUSTER) return APA_ERR_UNSUPPORTED;
+  if (t->stream_ctas < 0 || t->stream_shape < 0 || t->stream_shape > 2 || t->cluster_shape < 0 || t->cluster_shape > 3)
+    return APA_ERR_UNSUPPORTED;
+  for (int i = 0; i < 6; ++i)
+    if (t->reserved[i] != 0) return APA_ERR_UNSUPPORTED;
   return APA_OK;
 }
 
@@ -167,8 +148,9 @@ const char* apa_strerror(int status) {
     case APA_ERR_SOFTMAX_RANK:
       return "apa: SOFTMAX_ATT with RANK>1 is a graph-build error in the reference (nets_factory.py:278)";
     case APA_ERR_WORKSPACE: return "apa: workspace too small or not 256-byte aligned";
-    case APA_ERR_UNSUPPORTED: return "apa: unsupported descriptor (abi version / flags / reserved fields)";
-    case APA_ERR_ALIGN: return "apa: X and outputs must be 16-byte aligned";
+    case APA_ERR_UNSUPPORTED:
+      return "apa: unsupported descriptor or tuning (abi version / flags / form / reserved fields)";
+    case APA_ERR_ALIGN: return "apa: X and the weight matrices must be 16-byte aligned";
     case APA_ERR_DEVICE: return "apa: current device is not sm_100 (B200)";
     default: break;
   }
@@ -186,8 +168,7 @@ size_t apa_attn_pool_workspace(const ApaDesc* desc, int want_attn, int want_topd
 int apa_attn_pool_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
   if (workspace == nullptr) return APA_ERR_NULL;
   if (workspace_bytes < kCtrlBytes || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APA_ERR_WORKSPACE;
-  // every counter of every form lives in the workspace and starts from zero (control block, per-image and
-  // per-slice arrival counters of the flow form): clear all of it once
+  // every counter of the kernels lives in the workspace and starts from zero
   APA_CUDA(cudaMemsetAsync(workspace, 0, workspace_bytes, static_cast<cudaStream_t>(stream)));
   return APA_OK;
 }
@@ -196,73 +177,46 @@ int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_at
                        int want_pose, int32_t plan[8]) {
   int st = check_desc(desc);
   if (st != APA_OK) return st;
+  st = check_tuning(tuning);
+  if (st != APA_OK) return st;
   if (plan == nullptr) return APA_ERR_NULL;
   for (int i = 0; i < 8; ++i) plan[i] = 0;
   const Carve c = carve(desc, want_attn, want_topdown, want_pose);
   plan[0] = c.path;
   const bool single = (desc->flags & APA_FLAG_SINGLE_LAYER_ATT) != 0;
   int launches = 0;
-  if (!single || want_pose) launches += 1 + (want_pose ? 1 : 0) + (single ? 0 : 1);
+  {  // the PoseLogits scope, as fwd_impl runs it
+    const int rows = desc->batch * desc->hw;
+    const bool fuse_a0 = !single && c.path == 0 && !want_pose &&
+                         dense_gemm_tc_eligible(rows, desc->pose_channels, desc->channels) &&
+                         dense_gemm_tc_dot_parts(desc->pose_channels) <= 8 && !dense_force_simt();
+    if (fuse_a0) launches += 1;                                   // pose GEMM with the row-dot epilogue
+    else if (!single || want_pose) launches += 1 + (want_pose ? 1 : 0) + ((!single && c.path == 0) ? 1 : 0);
+  }
   if (c.path == 0) {
-    FusedPlan fp;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
-      (void)cudaGetLastError();
-      ndev = 0;
-    }
-    bool planned = false;
-    if (ndev > 0 && check_device() == APA_OK)
-      planned = fused_make_plan(desc->batch, desc->hw, desc->channels, desc->num_classes, desc->rank,
-                                mode_of(desc->flags), tuning, &fp) == cudaSuccess;
-    if (!planned) {
-      (void)cudaGetLastError();
-      fused_make_plan_nodevice(desc->batch, desc->hw, desc->channels, desc->num_classes, desc->rank,
-                               mode_of(desc->flags), tuning, &fp);
-    }
-    plan[1] = fp.cluster;
-    plan[2] = fp.cluster * fp.nclusters;
-    plan[3] = fp.fused;
-    plan[5] = int32_t(fp.smem);
-    if (use_local(desc, nullptr, tuning)) {
+    if (use_cluster(desc, nullptr, tuning)) {
       int li = 4;
       size_t lsm = 0;
-      local_plan(desc->batch, desc->channels, desc->rank, desc->num_classes, tuning, &li, &lsm);
+      cluster_plan(desc->batch, desc->channels, desc->rank, desc->num_classes, tuning, &li, &lsm);
       const int ncl = desc->batch / li < 9 ? desc->batch / li : 9;  // 148 SMs / 16
-      plan[1] = 16;
+      plan[1] = APA_FORM_CLUSTER;
       plan[2] = 16 * ncl;
-      plan[3] = 1;
-      plan[5] = int32_t(lsm);
-      plan[6] = 1;  // cluster-local kernel
+      plan[4] = int32_t(lsm);
+      launches += 1;
+    } else {
+      plan[1] = APA_FORM_FLOW;
+      plan[2] = flow_stream_ctas(desc->batch, desc->hw, tuning);
+      plan[4] = int32_t(flow_smem(desc->channels, tuning));
+      plan[5] = flow_contract_grid(desc->num_classes);
+      launches += 4;  // STREAM, REDUCE, CONTRACT, FINISH
     }
-    bool two = !fp.fused;
-    if (use_flow(desc, tuning)) {
-      plan[1] = 0;
-      plan[2] = flow_stream_ctas(desc->batch, desc->hw, tuning);   // STREAM grid
-      plan[3] = 0;
-      plan[5] = int32_t(flow_smem(desc->channels));
-      plan[6] = 3;                                   // flow form: row-balanced STREAM + small CONTRACT
-      plan[7] = flow_contract_grid(desc->num_classes);
-      two = true;
-    } else if (use_split(desc, tuning)) {
-      const int lp = split_lp(desc->batch, desc->hw, tuning);
-      const int units = desc->batch * lp, cap = 148 * (desc->rank == 1 ? 3 : 1);
-      plan[1] = lp;                                  // row slices per image
-      plan[2] = units < cap ? units : cap;           // STREAM grid
-      plan[3] = 0;
-      plan[5] = int32_t(split_stream_smem(desc->channels));
-      plan[6] = 2;                                   // STREAM + CONTRACT pipeline
-      plan[7] = split_contract_grid(desc->num_classes);
-      two = true;
-    }
-    launches += two ? 2 : 1;
-    if (plan[6] == 3) launches += 2;               // flow form: STREAM, REDUCE, CONTRACT, FINISH
     if (want_attn) launches += 1;
   } else {
     const int R = desc->rank;
     launches += 2 * R + 1;  // attention convs, top-down convs, pool
     if (desc->flags & (APA_FLAG_SOFTMAX_ATT | APA_FLAG_RELU_ATT)) launches += 1;
   }
-  plan[4] = launches;
+  plan[3] = launches;
   return APA_OK;
 }
 
@@ -294,9 +248,20 @@ int apa_attn_pool_fwd_gather(const ApaDesc* d, const float* X, const ApaWeights*
     if (gw->peer_logits[q] == nullptr || gw->peer_flags[q] == nullptr) return APA_ERR_NULL;
   int st = check_desc(d);
   if (st != APA_OK) return st;
-  if (d->flags & APA_FLAG_PER_CLASS) return APA_ERR_UNSUPPORTED;  // the fused gather lives in the single-map kernels
-  if (!fused_supported(d->channels, d->rank)) return APA_ERR_UNSUPPORTED;
+  if (!use_fast_path(d, 0)) return APA_ERR_UNSUPPORTED;  // the fused gather lives in the single-map kernels
   return fwd_impl(d, X, w, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, tuning, stream_, gw);
+}
+
+int apa_peer_gather_wait(const ApaPeerGather* gw, int32_t lag, void* stream) {
+  if (gw == nullptr || gw->counters == nullptr) return APA_ERR_NULL;
+  if (lag < 0) return APA_ERR_SHAPE;
+  if (gw->world < 1 || gw->world > APA_MAX_PEERS || gw->rank < 0 || gw->rank >= gw->world) return APA_ERR_SHAPE;
+  for (int q = 0; q < gw->world; ++q)
+    if (gw->peer_flags[q] == nullptr) return APA_ERR_NULL;
+  int st = check_device();
+  if (st != APA_OK) return st;
+  APA_CUDA(peer_gather_wait_launch(gw, lag, false, static_cast<cudaStream_t>(stream)));
+  return APA_OK;
 }
 
 }  // extern "C"
@@ -307,6 +272,8 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
              float* topdown_out, float* pose_out, void* workspace, size_t workspace_bytes,
              const ApaTuning* tuning, void* stream_, const ApaPeerGather* gw) {
   int st = check_desc(d);
+  if (st != APA_OK) return st;
+  st = check_tuning(tuning);
   if (st != APA_OK) return st;
   if (X == nullptr || w == nullptr || workspace == nullptr) return APA_ERR_NULL;
   const int B = d->batch, HW = d->hw, C = d->channels, K = d->num_classes, R = d->rank, F = d->frames;
@@ -319,9 +286,11 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
   const bool need_pose_pre = !single || pose_out != nullptr;
   if (need_pose_pre && (!w->pose_w || !w->pose_b)) return APA_ERR_NULL;
   if (pose_out && (!w->pose_logits_w || !w->pose_logits_b || d->num_pose_keypoints <= 0)) return APA_ERR_NULL;
-  if ((reinterpret_cast<uintptr_t>(X) & 15u) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
-    return (reinterpret_cast<uintptr_t>(X) & 15u) ? APA_ERR_ALIGN : APA_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return APA_ERR_WORKSPACE;
   const Carve c = carve(d, attn_out != nullptr, topdown_out != nullptr, pose_out != nullptr);
+  // vector (16-byte) accesses: X tiles move by bulk copies, w_0 is read as float4 on the fast path
+  if (reinterpret_cast<uintptr_t>(X) & 15u) return APA_ERR_ALIGN;
+  if (c.path == 0 && single && (reinterpret_cast<uintptr_t>(w->attn_w[0]) & 15u)) return APA_ERR_ALIGN;
   if (workspace_bytes < c.total) return APA_ERR_WORKSPACE;
   st = check_device();
   if (st != APA_OK) return st;
@@ -332,7 +301,7 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
   const int rows = B * HW;
 
   // ---- PoseLogits scope (nets_factory.py:147-160): P = relu(X Wp + bp); PoseLogits = P Wq + bq.
-  // When P only feeds the 1-wide attention conv (config 003, fused path, no PoseLogits requested) it is
+  // When P only feeds the 1-wide attention conv (config 003, fast path, no PoseLogits requested) it is
   // never written: the tensor-core GEMM's epilogue emits the partial dots relu(P).w_0 directly.
   float* P = nullptr;
   const bool fuse_a0 = !single && c.path == 0 && pose_out == nullptr &&
@@ -351,9 +320,7 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
   const int Cs = single ? C : d->pose_channels;
 
   if (c.path == 0) {
-    // ---- fused single-map path
-    FusedPlan plan;
-    APA_CUDA(fused_make_plan(B, HW, C, K, R, mode, tuning, &plan));
+    // ---- single-map fast path
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.X = X;
@@ -389,50 +356,32 @@ int fwd_impl(const ApaDesc* d, const float* X, const ApaWeights* w, float* logit
       p.gw_depth = gw->depth;
     }
     p.attn_raw = attn_out ? wsf(c.attn_raw) : nullptr;
-    p.g = wsf(c.g);
-    p.sn = wsf(c.sn);
     p.smx = wsf(c.smx);
-    p.barrier = reinterpret_cast<unsigned long long*>(ws + c.ctrl) + ((plan.cluster * plan.nclusters) & 255);
-    // PDL trigger: by default as soon as a CTA starts consuming (measured best: the next launch's clusters take
-    // the free CTA slots as they appear); reserved[0] > 0 = that many tiles before the end, < 0 = at the end
-    p.trigger_lead = (tuning && tuning->pdl_trigger_lead != 0) ? (tuning->pdl_trigger_lead < 0 ? 0 : tuning->pdl_trigger_lead) : 1 << 20;
+    p.trigger_lead = tuning ? tuning->pdl_trigger_lead : 0;
+    p.inputs_stable = (tuning && tuning->inputs_stable) ? 1 : 0;
     p.ts = (tuning && tuning->debug_timestamps) ? reinterpret_cast<unsigned long long*>(ws + c.ts) : nullptr;
     p.B = B; p.HW = HW; p.C = C; p.K = K; p.R = R; p.F = F;
     p.inv_scale = 1.0f / (float(HW) * float(F));
-    // small batches: the cluster-local kernel (no grid barrier, g never leaves shared memory)
     bool launched = false;
-    int grid = fused_grid(plan);
-    // the fused all-gather prefers the flow form (its flow control lives in the kernel) unless another form is forced
-    const bool flow_gather = gw != nullptr && (tuning == nullptr || tuning->form == APA_FORM_AUTO) &&
-                             flow_eligible(B, HW, C, K, R, F);
-    if (flow_gather || use_flow(d, tuning)) {
-      p.gpart = wsf(c.gpart);
-      p.gstat = wsf(c.gstat);
-      p.cpart = wsf(c.cpart);
-      p.gsum = wsf(c.gsum);
-      p.g = wsf(c.fl_g);
-      p.fl_arr = reinterpret_cast<unsigned long long*>(ws + c.fl_arr);
-      p.fl_ctr = reinterpret_cast<unsigned long long*>(ws + kFlowCtrOff);
-      int g1 = 0;
-      p.trigger_lead = tuning ? tuning->pdl_trigger_lead : 0;   // flow form: 0 = at the last tiles, < 0 = at once
-      APA_CUDA(flow_launch(p, mode, tuning, stream, &g1, &grid));
-      launched = true;
-    }
-    if (!launched && gw != nullptr) APA_CUDA(peer_gather_begin_launch(gw, stream));  // flow control for the other forms
-    if (!launched && use_split(d, tuning)) {
-      p.gpart = wsf(c.gpart);
-      p.gstat = wsf(c.gstat);
-      int g1 = 0, g2 = 0;
-      cudaError_t se = split_launch(p, mode, tuning, stream, &g1, &g2);
-      if (se == cudaSuccess) { launched = true; grid = g2; }  // the CONTRACT CTAs do the gather bookkeeping
-      else (void)cudaGetLastError();
-    }
-    if (!launched && use_local(d, w, tuning)) {
-      cudaError_t le = local_launch(p, mode, tuning, stream, &grid);
+    if (use_cluster(d, w, tuning)) {
+      // this kernel has no flow control of its own for the gathered ring: a 1-warp kernel in front of it does it
+      if (gw != nullptr) APA_CUDA(peer_gather_begin_launch(gw, stream));
+      int grid = 0;
+      cudaError_t le = cluster_launch(p, mode, tuning, stream, &grid);
       if (le == cudaSuccess) launched = true;
-      else { (void)cudaGetLastError(); grid = fused_grid(plan); }  // e.g. 16-CTA clusters not launchable here
+      else if (gw != nullptr) return int(le);   // the begin kernel has already announced the step
+      else (void)cudaGetLastError();            // e.g. 16-CTA clusters not launchable here: the flow form
     }
-    if (!launched) APA_CUDA(fused_launch(p, plan, stream));
+    if (!launched) {
+      p.gpart = wsf(c.gpart);
+      p.gstat = wsf(c.gstat);
+      p.g = wsf(c.g);
+      p.gsum = wsf(c.gsum);
+      p.cpart = wsf(c.cpart);
+      p.fl_ctr = reinterpret_cast<unsigned long long*>(ws + kFlowCtrOff);
+      int g1 = 0, g2 = 0;
+      APA_CUDA(flow_launch(p, mode, tuning, stream, &g1, &g2));
+    }
     if (gw != nullptr) {
       // completeness: by default this call's step; lag >= 1 pipelines the consumer behind the producers
       const int lag = tuning ? tuning->gather_wait_lag : 0;
@@ -480,18 +429,6 @@ int apa_attn_pool_fwd_host(const ApaDesc* d, const float* X_host, const ApaWeigh
   if (st != APA_OK) return st;
   APA_CUDA(cudaMemcpyAsync(logits_host, logits_staging, lbytes, cudaMemcpyDeviceToHost, stream));
   APA_CUDA(cudaStreamSynchronize(stream));
-  return APA_OK;
-}
-
-int apa_peer_gather_wait(const ApaPeerGather* gw, int32_t lag, void* stream) {
-  if (gw == nullptr || gw->counters == nullptr) return APA_ERR_NULL;
-  if (lag < 0) return APA_ERR_SHAPE;
-  if (gw->world < 1 || gw->world > APA_MAX_PEERS || gw->rank < 0 || gw->rank >= gw->world) return APA_ERR_SHAPE;
-  for (int q = 0; q < gw->world; ++q)
-    if (gw->peer_flags[q] == nullptr) return APA_ERR_NULL;
-  int st = check_device();
-  if (st != APA_OK) return st;
-  APA_CUDA(peer_gather_wait_launch(gw, lag, false, static_cast<cudaStream_t>(stream)));
   return APA_OK;
 }
 

@@ -13,10 +13,9 @@ enum { MODE_PLAIN = 0, MODE_RELU = 1, MODE_SOFTMAX = 2 };
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = 32 * kConsumerWarps;
 constexpr int kFusedThreads = kConsumerThreads + 32;  // + 1 bulk-copy producer warp
-constexpr int kVideoTile = 32;  // videos per phase-2 tile
-constexpr int kColTile = 16;    // classes per phase-2 pass
+constexpr int kVideoTile = 32;  // videos per tile of the contraction
 
-// Parameters of the fused single-map (M == 1) kernel.  See apa_pool_fused.cu.
+// Parameters of the single-map (M == 1) head kernels (apa_pool_flow.cu, apa_pool_cluster.cu).
 struct FusedParams {
   const float* X;        // [B, HW, C]
   const float* attn_in;  // optional precomputed a_0 as attn_in_parts partial sums [parts][B*HW] (attention
@@ -28,84 +27,46 @@ struct FusedParams {
   const float* td_b[APA_MAX_RANK];    // [K]
   float* logits;                      // [B/F, K]
   float* attn_raw;                    // optional [B*HW]: a_0 before chain/relu/softmax
-  float* g;                           // workspace [B, R, C]: attention-weighted feature sums
-  float* sn;                          // workspace [B, R]: sum of attention weights (1 if softmax)
-  float* smx;                         // workspace [B, 2]: softmax (max, sum) per image
-  unsigned long long* barrier;        // grid-barrier arrival counter for this grid size (control block)
-  unsigned long long* ts;             // optional debug timeline, 64 words per CTA (see apa_pool_fused.cu)
+  float* smx;                         // workspace [B, 2]: softmax (max, sum) per image (attention end point)
+  unsigned long long* ts;             // optional debug timeline, 64 words per CTA
   int B, HW, C, K, R, F;
-  int do_phase1, do_phase2;           // fused: 1,1   split: (1,0) then (0,1)
   int trigger_lead;                   // PDL: trigger the next launch this many tiles before a CTA's last tile
+  int inputs_stable;                  // X / weights may be read before the previous kernel in the stream completed
   float inv_scale;                    // 1 / (HW * F)
   // fused all-gather over peer memory (gw_world == 0: plain store to `logits`)
-  int gw_world, gw_rank;
+  int gw_world, gw_rank, gw_depth;    // gw_depth: buffers in every rank's gathered ring (call `step` lands in step % depth)
   float* gw_logits[APA_MAX_PEERS];
   unsigned long long* gw_flags[APA_MAX_PEERS];
-  unsigned long long* gw_done;
-  // two-kernel pipeline (apa_pool_split.cu)
-  float* gpart;                       // workspace [B, lp, R, C]: per-row-slice partial g
-  float* gstat;                       // workspace [B, lp, 8]: (s_r[4], running max) per row slice
-  int lp;                             // row slices per image
+  unsigned long long* gw_done;        // the gather object's local counters (include/apa.h ApaPeerGather.counters)
   // flow form (apa_pool_flow.cu)
-  unsigned long long* fl_ctr;         // control words: STREAM / REDUCE / CONTRACT tickets, completed calls, gather steps
-  size_t fl_gpart_stride, fl_gstat_stride, fl_g_stride, fl_gsum_stride, fl_cpart_stride, fl_arr_stride;
+  float* gpart;                       // workspace [copy][slot][R][C]: partial g per (STREAM CTA, image, consumer group)
+  float* gstat;                       // workspace [copy][slot][8]: (s_r[4], running max) per partial
+  float* g;                           // workspace [copy][B][R][C]: attention-weighted feature sums per image
+  float* gsum;                        // workspace [copy][B][4]: attention mass per rank of the reduced image
+  float* cpart;                       // workspace [copy][tiles * class slices][16][32 videos][32 classes] partial logits
+  unsigned long long* fl_ctr;         // control words: STREAM / REDUCE / CONTRACT / FINISH tickets, completed calls, gather steps
+  size_t fl_gpart_stride, fl_gstat_stride, fl_g_stride, fl_gsum_stride, fl_cpart_stride;
                                       // distance between the kFlowDepth copies of the per-call buffers
-  unsigned long long* fl_arr;         // [video tiles * class slices] arrival counters of the CONTRACT units
-  float* gsum;                        // workspace [B][4]: attention mass per rank of the reduced image
-  float* cpart;                       // workspace [tiles * class slices][16][32 videos][32 classes] partial logits
   int fl_G, fl_NS, fl_ng;             // STREAM CTAs, class slices, consumer groups (partials per CTA and image)
-  int inputs_stable;                  // X / weights may be read before the previous kernel in the stream completed
-  int fl_debug_nowait;                // measurement builds of the chain without its tail: skip the completed-calls check
-  int gw_depth;                       // buffers in every rank's gathered ring (call `step` lands in step % depth)
+  int fl_debug_nowait;                // measurement runs of the chain without its tail: skip the completed-calls check
 };
 
-struct FusedPlan {
-  int Q;        // C / 1024
-  int rmax;     // 1 or APA_MAX_RANK (template instance)
-  int mode;     // MODE_*
-  int cluster;  // CTAs per image
-  int nclusters;
-  int fused;    // 1: single kernel + grid barrier
-  int cooperative;
-  int pdl;      // launch as a programmatic dependent of the previous kernel in the stream
-  size_t smem;
-};
+// ---- cluster form (apa_pool_cluster.cu): 16-CTA clusters, everything after the stream stays in shared memory
+bool cluster_eligible(int B, int HW, int C, int K, int R, int F);
+void cluster_plan(int B, int C, int R, int K, const ApaTuning* tuning, int* images_per_cluster, size_t* smem);
+cudaError_t cluster_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out);
 
-// Pick cluster size / grid for (B, HW, C, K) on the current device. Returns cudaSuccess or error.
-cudaError_t fused_make_plan(int B, int HW, int C, int K, int R, int mode, const ApaTuning* tuning,
-                            FusedPlan* plan);
-// Same decision without touching the device (assumes a 148-SM B200); for plan introspection on CPU.
-void fused_make_plan_nodevice(int B, int HW, int C, int K, int R, int mode, const ApaTuning* tuning,
-                              FusedPlan* plan);
-cudaError_t fused_launch(const FusedParams& p, const FusedPlan& plan, cudaStream_t stream);
-bool fused_supported(int C, int R);
-
-// ---- cluster-local small-batch form (apa_pool_local.cu): 16-CTA clusters, no grid barrier, g stays in smem
-bool local_eligible(int B, int HW, int C, int K, int R, int F);
-void local_plan(int B, int C, int R, int K, const ApaTuning* tuning, int* images_per_cluster, size_t* smem);
-cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out);
-int fused_grid(const FusedPlan& plan);
-
-// ---- two-kernel pipeline (apa_pool_split.cu): lean STREAM kernel (partial g -> workspace) + CONTRACT kernel
-bool split_eligible(int C, int R);
-int split_lp_cap(int B, int HW);                             // workspace is sized for this many row slices
-int split_lp(int B, int HW, const ApaTuning* tuning);
-int split_contract_grid(int K);
-size_t split_stream_smem(int C);
-cudaError_t split_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream,
-                         int* stream_grid, int* contract_grid);
-
-// ---- flow form (apa_pool_flow.cu): row-balanced STREAM kernel + small CONTRACT kernel parked in griddepcontrol.wait
+// ---- flow form (apa_pool_flow.cu): row-balanced STREAM kernel + three small tail kernels parked in griddepcontrol.wait
 constexpr int kFlowStreamCtas = 148;   // one STREAM CTA per SM of a B200
 constexpr int kFlowDepth = 2;          // copies of the per-call buffers: call L uses copy L % 2
 bool flow_eligible(int B, int HW, int C, int K, int R, int F);
 int flow_stream_ctas(int B, int HW, const ApaTuning* tuning);
 int flow_class_slices(int K);
-size_t flow_gpart_slots(int B);                 // partial-g slots the workspace holds
-size_t flow_slices(int B, int K, int F);        // (video tile, class slice) pairs = arrival counters
-size_t flow_cpart_floats(int B, int K, int F);  // partial-logit floats the workspace holds
-size_t flow_smem(int C);
 int flow_contract_grid(int K);
+size_t flow_gpart_slots(int B);                 // partial-g slots one copy of the workspace holds
+size_t flow_slices(int B, int K, int F);        // (video tile, class slice) pairs
+size_t flow_cpart_floats(int B, int K, int F);  // partial-logit floats one copy of the workspace holds
+size_t flow_smem(int C, const ApaTuning* tuning);
 cudaError_t flow_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream,
                         int* stream_grid, int* contract_grid);
 

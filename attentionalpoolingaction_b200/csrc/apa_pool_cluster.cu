@@ -1,10 +1,10 @@
-// apa_pool_local.cu — the cluster-local form of the fused head: everything after the HBM stream stays inside
+// apa_pool_cluster.cu — the cluster form of the single-map head: everything after the HBM stream stays inside
 // one 16-CTA thread-block cluster, so there is NO grid barrier and the attention-weighted features g never
-// leave shared memory.  Same math as apa_pool_fused.cu (single attention map, rank 1..4, plain / relu /
+// leave shared memory.  Same math as apa_pool_flow.cu (single attention map, rank 1..4, plain / relu /
 // spatial softmax); reference sites nets_factory.py:259-328, :350-352.
 //
 //   cluster = 16 CTAs = LI images x LP row slices (LI x LP = 16; LI = 4 or 8).  CTA rank r: image r / LP, slice r % LP.
-//   phase 1   as in the grid-barrier kernel: producer lane streams TR-row x C tiles (cp.async.bulk) through an
+//   phase 1   producer lane streams TR-row x C tiles (cp.async.bulk) through an
 //             STG-stage mbarrier ring; 8 consumer warps form a[row] and accumulate g in registers.
 //   exchange 1  phase 2 splits the contraction g.B over the 16 CTAs by CHANNEL: CTA j owns channels
 //             [j C/16, (j+1) C/16) for all LI images and all K classes.  So every CTA PUSHES (st.shared::cluster)
@@ -121,6 +121,9 @@ apa_pool_local_kernel(const FusedParams p) {
   const int WR = local_wr(K);                    // weight rows per ring stage
   const int wchunks = CH / WR;                   // per rank
 
+  // Reading X (or a_0 from the pose GEMM, the kernel right before this one) before the previous kernel in the
+  // stream has completed is only legal when the caller vouches for it (ApaTuning.inputs_stable)
+  if (!p.inputs_stable || p.attn_in != nullptr || p.attn_raw != nullptr) griddep_wait();
   // =========================================================================== producer warp
   if (warp == kConsumerWarps) {
     if (lane == 0) {
@@ -538,25 +541,28 @@ std::atomic<int> g_local_pdl_refused{0};
 
 }  // namespace
 
-bool local_eligible(int B, int HW, int C, int K, int R, int F) {
+bool cluster_eligible(int B, int HW, int C, int K, int R, int F) {
   (void)HW;
   return C == 2048 && F == 1 && B % kLI == 0 && B >= kLI && K >= 1 && K <= 3 * kConsumerThreads && R >= 1 &&
          R <= APA_MAX_RANK && (size_t(K) * 8 * 4) <= size_t(32) * 1024;
 }
 
-int local_shape(int B, int C, int R, int K, const ApaTuning* tuning) {
-  // form 4 / 5 / 6 forces shape 0 / 1 / 2 (when the problem allows it); otherwise the widest that fits
-  const int force = tuning ? tuning->form : 0;
-  if (R != 1 || force == 4) return 0;
-  if (force == 5) return 1;
-  if (B % 8 == 0 && (force == 6 || shape_smem(C, R, K, 2) <= kThreeSlotSmem)) return 2;
+int cluster_shape_of(int B, int C, int R, int K, const ApaTuning* tuning) {
+  // cluster_shape 1 / 2 / 3 forces shape 0 / 1 / 2 (when the problem allows it); otherwise the widest that fits
+  const int force = tuning ? tuning->cluster_shape : 0;
+  if (R != 1 || force == 1) return 0;
+  if (force == 2) return 1;
+  if (B % 8 == 0 && (force == 3 || shape_smem(C, R, K, 2) <= kThreeSlotSmem)) return 2;
   return (shape_smem(C, R, K, 1) <= kThreeSlotSmem) ? 1 : 0;
 }
 
-cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out) {
+cudaError_t cluster_launch(const FusedParams& p_in, int mode, const ApaTuning* tuning, cudaStream_t stream, int* grid_out) {
+  FusedParams p = p_in;
+  // measured best for this form: let the next launch be scheduled as soon as a CTA starts consuming
+  p.trigger_lead = (tuning && tuning->pdl_trigger_lead > 0) ? tuning->pdl_trigger_lead : 1 << 20;
   const int Q = p.C / 1024, rmax = (p.R == 1) ? 1 : APA_MAX_RANK;
   const int nc = (p.K + kConsumerThreads - 1) / kConsumerThreads;
-  const int shape = local_shape(p.B, p.C, p.R, p.K, tuning);
+  const int shape = cluster_shape_of(p.B, p.C, p.R, p.K, tuning);
   const int li = kShapes[shape].li;
   LKernelFn fn = local_select(Q, rmax, mode, nc, shape);
   if (fn == nullptr) return cudaErrorInvalidValue;
@@ -624,8 +630,8 @@ cudaError_t local_launch(const FusedParams& p, int mode, const ApaTuning* tuning
   return err;
 }
 
-void local_plan(int B, int C, int R, int K, const ApaTuning* tuning, int* images_per_cluster, size_t* smem) {
-  const int shape = local_shape(B, C, R, K, tuning);
+void cluster_plan(int B, int C, int R, int K, const ApaTuning* tuning, int* images_per_cluster, size_t* smem) {
+  const int shape = cluster_shape_of(B, C, R, K, tuning);
   if (images_per_cluster) *images_per_cluster = kShapes[shape].li;
   if (smem) *smem = shape_smem(C, R, K, shape);
 }

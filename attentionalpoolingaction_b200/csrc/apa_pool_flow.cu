@@ -98,7 +98,7 @@ __device__ __forceinline__ void flow_image_ctas(long long N, int G, int HW, int 
   *hi = int(c < G - 1 ? c : G - 1);
 }
 
-// Shapes of the STREAM kernel (ApaTuning.cluster_size picks one for A/B runs; 0 = default):
+// Shapes of the STREAM kernel (ApaTuning.stream_shape picks one for A/B runs; 0 = default):
 //   shape 0: two consumer groups, 4-stage ring (96 KB), <= 128 registers: one CTA per SM
 //   shape 1: two consumer groups, 3-stage ring (72 KB), <= 96 registers: two CTAs per SM
 //   shape 2: one consumer group,  3-stage ring (72 KB), <= 72 registers: three CTAs per SM
@@ -736,10 +736,12 @@ int flow_class_slices(int K) { return (K + kKW - 1) / kKW; }
 int flow_contract_grid(int K) { return kNJ * flow_class_slices(K); }
 
 int flow_stream_ctas(int B, int HW, const ApaTuning* tuning) {
-  long long n = (long long)B * HW;
+  const long long n = (long long)B * HW;
   int g = kFlowStreamCtas;
-  if (tuning && tuning->max_ctas > 0 && tuning->max_ctas < g) g = tuning->max_ctas;
-  if (n < g) g = int(n);
+  if (tuning && tuning->stream_ctas > 0 && tuning->stream_ctas < g) g = tuning->stream_ctas;
+  // small batches: at least 16 rows (128 KB) per CTA, so that an image is cut into few partials (REDUCE adds them
+  // one by one) and a CTA's stream is more than the first-tile latency
+  if (n / 16 < g) g = int(n / 16 > 0 ? n / 16 : 1);
   return g;
 }
 
@@ -754,7 +756,9 @@ size_t flow_slices(int B, int K, int F) {  // (video tile, class slice) pairs = 
   return size_t(ntile) * flow_class_slices(K);
 }
 size_t flow_cpart_floats(int B, int K, int F) { return flow_slices(B, K, F) * kNJ * kVideoTile * kKW; }
-size_t flow_smem(int C) { return stream_smem_bytes(C, 4); }
+size_t flow_smem(int C, const ApaTuning* tuning) {
+  return stream_smem_bytes(C, (tuning && tuning->stream_shape != 0) ? 3 : 4);
+}
 
 cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuning, cudaStream_t stream,
                         int* stream_grid, int* contract_grid) {
@@ -763,7 +767,7 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   FusedParams p = p_in;
   const int Q = p.C / 1024, rmax = (p.R == 1) ? 1 : APA_MAX_RANK;
   int stages = 4, ng = 2;
-  const int shape = tuning ? tuning->cluster_size : 0;
+  const int shape = tuning ? tuning->stream_shape : 0;
   FKernelFn sfn = flow_stream_select(Q, rmax, mode, shape, &stages, &ng), cfn = flow_contract_select(Q);
   p.fl_ng = ng;
   FKernelFn rfn = (mode == MODE_SOFTMAX) ? &apa_flow_reduce_kernel<true> : &apa_flow_reduce_kernel<false>;
@@ -781,11 +785,10 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
     p.fl_g_stride = size_t(p.B) * p.R * p.C;
     p.fl_gsum_stride = size_t(p.B) * 4;
     p.fl_cpart_stride = flow_cpart_floats(p.B, p.K, p.F);
-    p.fl_arr_stride = flow_slices(p.B, p.K, p.F);
   }
   p.fl_NS = flow_class_slices(p.K);
   p.inputs_stable = (tuning && tuning->inputs_stable) ? 1 : 0;
-  p.fl_debug_nowait = (tuning && tuning->fused >= 100) ? 1 : 0;
+  p.fl_debug_nowait = (tuning && tuning->debug_cut_tail > 0) ? 1 : 0;
   const int grid2 = kNJ * p.fl_NS;
   if (stream_grid) *stream_grid = p.fl_G;
   if (contract_grid) *contract_grid = grid2;
@@ -802,8 +805,8 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   cfg.numAttrs = na;
   err = cudaLaunchKernelEx(&cfg, sfn, p);
   if (err != cudaSuccess) return err;
-  const int dbg = tuning ? tuning->fused : -1;   // measurement only: 100 = STREAM alone, 101 = STREAM + REDUCE
-  if (dbg == 100) return cudaSuccess;
+  const int dbg = tuning ? tuning->debug_cut_tail : 0;   // measurement only: launch just the first 1 / 2 / 3 kernels
+  if (dbg == 1) return cudaSuccess;
   cudaLaunchConfig_t cfgr = {};
   cfgr.gridDim = dim3(p.B, (p.C / 4 + kRThreads - 1) / kRThreads, 1);
   cfgr.blockDim = dim3(kRThreads, 1, 1);
@@ -812,7 +815,7 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   cfgr.numAttrs = na;
   err = cudaLaunchKernelEx(&cfgr, rfn, p);
   if (err != cudaSuccess) return err;
-  if (dbg == 101) return cudaSuccess;
+  if (dbg == 2) return cudaSuccess;
   cudaLaunchConfig_t cfg2 = {};
   cfg2.gridDim = dim3(grid2, 1, 1);
   cfg2.blockDim = dim3(kCThreads, 1, 1);
@@ -822,7 +825,7 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   cfg2.numAttrs = na;
   err = cudaLaunchKernelEx(&cfg2, cfn, p);
   if (err != cudaSuccess) return err;
-  if (dbg == 102) return cudaSuccess;
+  if (dbg == 3) return cudaSuccess;
   cudaLaunchConfig_t cfg3 = {};
   cfg3.gridDim = dim3(unsigned(flow_slices(p.B, p.K, p.F)), 1, 1);
   cfg3.blockDim = dim3(kCThreads, 1, 1);

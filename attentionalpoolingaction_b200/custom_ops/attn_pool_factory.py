@@ -87,27 +87,24 @@ class ApaWeights(ctypes.Structure):
 
 class ApaTuning(ctypes.Structure):
     _fields_ = [
-        ("cluster_size", ctypes.c_int32),
-        ("fused", ctypes.c_int32),
-        ("max_ctas", ctypes.c_int32),
-        ("no_cooperative", ctypes.c_int32),
-        ("no_pdl", ctypes.c_int32),
-        ("debug_timestamps", ctypes.c_int32),
         ("form", ctypes.c_int32),
-        ("pdl_trigger_lead", ctypes.c_int32),
+        ("stream_ctas", ctypes.c_int32),
+        ("stream_shape", ctypes.c_int32),
+        ("cluster_shape", ctypes.c_int32),
+        ("no_pdl", ctypes.c_int32),
         ("inputs_stable", ctypes.c_int32),
+        ("pdl_trigger_lead", ctypes.c_int32),
         ("gather_wait_lag", ctypes.c_int32),
+        ("debug_timestamps", ctypes.c_int32),
+        ("debug_cut_tail", ctypes.c_int32),
         ("reserved", ctypes.c_int32 * 6),
     ]
 
 
 # ApaTuning.form (include/apa.h APA_FORM_*)
 APA_FORM_AUTO = 0
-APA_FORM_GRID_BARRIER = 1
-APA_FORM_LOCAL0, APA_FORM_LOCAL1, APA_FORM_LOCAL2 = 4, 5, 6
-APA_FORM_PIPELINE = 7
-APA_FORM_NO_PIPELINE = 8
-APA_FORM_FLOW = 9
+APA_FORM_FLOW = 1
+APA_FORM_CLUSTER = 2
 
 
 APA_MAX_PEERS = 8
@@ -221,13 +218,14 @@ def make_desc(batch, hw, channels, num_classes, frames=1, rank=1, flags=APA_FLAG
     return d
 
 
-def make_tuning(cluster_size=0, fused=-1, max_ctas=0, no_cooperative=0, no_pdl=0, debug_timestamps=0,
-                form=APA_FORM_AUTO, pdl_trigger_lead=0, inputs_stable=0, gather_wait_lag=0):
+def make_tuning(form=APA_FORM_AUTO, stream_ctas=0, stream_shape=0, cluster_shape=0, no_pdl=0, inputs_stable=0,
+                pdl_trigger_lead=0, gather_wait_lag=0, debug_timestamps=0, debug_cut_tail=0):
+    """ApaTuning (include/apa.h).  `inputs_stable=1` is a promise by the caller: X and the weights were completely
+    written before the previous kernel in the stream was launched (lets back-to-back calls overlap)."""
     t = ApaTuning()
-    t.cluster_size, t.fused, t.max_ctas = int(cluster_size), int(fused), int(max_ctas)
-    t.no_cooperative, t.no_pdl, t.debug_timestamps = int(no_cooperative), int(no_pdl), int(debug_timestamps)
-    t.form, t.pdl_trigger_lead = int(form), int(pdl_trigger_lead)
-    t.inputs_stable, t.gather_wait_lag = int(inputs_stable), int(gather_wait_lag)
+    t.form, t.stream_ctas, t.stream_shape, t.cluster_shape = int(form), int(stream_ctas), int(stream_shape), int(cluster_shape)
+    t.no_pdl, t.inputs_stable, t.pdl_trigger_lead = int(no_pdl), int(inputs_stable), int(pdl_trigger_lead)
+    t.gather_wait_lag, t.debug_timestamps, t.debug_cut_tail = int(gather_wait_lag), int(debug_timestamps), int(debug_cut_tail)
     return t
 
 
@@ -246,11 +244,10 @@ def attn_pool_plan(desc, tuning=None, want_attn=False, want_topdown=False, want_
                                  int(want_attn), int(want_topdown), int(want_pose), ctypes.byref(out))
     if st != APA_OK:
         raise ApaError(st, "apa_attn_pool_plan")
-    # cluster_local: 0 grid-barrier kernel, 1 cluster-local kernel, 2 STREAM + CONTRACT pipeline (then
-    # cluster_size = row slices per image, grid = STREAM grid, contract_grid = CONTRACT grid), 3 flow form
-    # (grid = STREAM + CONTRACT CTAs of the one launch, contract_grid = its CONTRACT CTAs)
-    keys = ("path", "cluster_size", "grid", "fused", "launches", "smem_bytes", "cluster_local", "contract_grid")
-    return OrderedDict(zip(keys, list(out)[:8]))
+    # form: APA_FORM_FLOW / APA_FORM_CLUSTER on the single-map fast path (path 0), 0 on the dense path;
+    # grid = CTAs of the streaming kernel, contract_grid = CTAs of the flow form's CONTRACT kernel
+    keys = ("path", "form", "grid", "launches", "smem_bytes", "contract_grid")
+    return OrderedDict(zip(keys, list(out)[:6]))
 
 
 def strerror(status):

@@ -270,10 +270,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
-    ap.add_argument("--form", type=int, default=0, help="ApaTuning.form (0 = library default)")
-    ap.add_argument("--max-ctas", type=int, default=0)
+    ap.add_argument("--form", type=int, default=0, help="ApaTuning.form (0 = library default: the flow form)")
+    ap.add_argument("--stream-ctas", type=int, default=-1,
+                    help="ApaTuning.stream_ctas: STREAM CTAs per call (-1 = this bench's throughput setting, 37 for "
+                         "the 32-map batches; 0 = library default, 148 = one per SM = shortest single call)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="independent batches in flight (1..4)")
+    ap.add_argument("--streams", type=int, default=6, help="independent batches in flight (1..8)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch")
     ap.add_argument("--inputs-stable", type=int, default=1,
                     help="ApaTuning.inputs_stable: the bench's inputs are resident before the timed region")
@@ -316,7 +318,10 @@ def main():
     x_bytes = B * HW * C * 4
     algo_bytes, algo_flops = algorithmic(cfg)
     hbm_peak, bf16_peak, peak_src = _peaks()
-    nstreams = max(1, min(4, args.streams))
+    nstreams = max(1, min(8, args.streams))
+    # throughput setting: with several batches in flight, fewer STREAM CTAs per call pack the SMs better (four calls
+    # stream side by side on disjoint SMs while the others are in their tails); big batches keep one CTA per SM
+    stream_ctas = args.stream_ctas if args.stream_ctas >= 0 else (37 if (B <= 64 and nstreams >= 4) else 0)
     is_gram = cfg["kind"] == "gram"
     lag = max(0, min(args.gather_lag, args.gather_depth - 1))
 
@@ -340,7 +345,7 @@ def main():
         fl = dict(orc.DEFAULT_FLAGS, **cfg["flags"])
         params = orc.make_params(K, C, flags=fl, seed=42)
         bits, rnk = ops.flags_from_cfg_net(fl)
-        tuning = ops.make_tuning(no_pdl=int(args.no_pdl), form=args.form, max_ctas=args.max_ctas,
+        tuning = ops.make_tuning(no_pdl=int(args.no_pdl), form=args.form, stream_ctas=stream_ctas,
                                  inputs_stable=args.inputs_stable, gather_wait_lag=lag)
         P = {k: torch.from_numpy(v) for k, v in params.items()}
         # one op (= one workspace) per in-flight batch: consecutive steps are independent batches
@@ -482,9 +487,13 @@ def main():
     if not is_gram and not args.no_latency and rank == 0:
         latency = {"method": "CUDA events around one graph-launched call after a device sync, X not in L2, "
                              "median of 15; includes the graph launch itself"}
+        op_lat = ops.AttnPoolOp(P, K, HW, channels=C, frames=F, rank=rnk, flags=bits, device=dev,
+                                tuning=ops.make_tuning(form=args.form, inputs_stable=args.inputs_stable))
+        latency["setting"] = "library default (148 STREAM CTAs, one per SM)"
         for tag, b in (("b%d" % Bv, B), ("b1", F)):
             lg = torch.empty((b // F, K), device=dev)
             xs1 = [r[:b] for r in ring]
+            op = op_lat
             with torch.cuda.stream(side):
                 op(xs1[0], logits=lg)
                 torch.cuda.synchronize()
@@ -505,6 +514,7 @@ def main():
                     lat.append(a.elapsed_time(b_) * 1e3)
             latency[tag] = statistics.median(lat)
             graphs_alive.extend(grs)
+        op = opl[0]
 
     # e2e: host buffers through apa_attn_pool_fwd_host (H2D + kernel + D2H + sync per step)
     if not is_gram:
@@ -526,13 +536,14 @@ def main():
             t_e2e = float(t.item())
         # the bound of this leg: the same pinned buffer copied host -> device with nothing else (PCIe)
         stage = torch.empty_like(ring[0])
-        stage.copy_(xh[0], non_blocking=True)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(10):
+        for i in range(3):
             stage.copy_(xh[i % 2], non_blocking=True)
         torch.cuda.synchronize()
-        copy_gbs = 10 * x_bytes / (time.perf_counter() - t0) / 1e9
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            stage.copy_(xh[i % 2], non_blocking=True)
+            torch.cuda.synchronize()
+        copy_gbs = args.e2e_steps * x_bytes / (time.perf_counter() - t0) / 1e9
         del stage
         e2e_gbs = x_bytes * args.e2e_steps / t_e2e / 1e9
         e2e = {"value": world * Bv * args.e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": x_bytes,
@@ -569,8 +580,8 @@ def main():
         if os.path.exists(tp) and args.config == 1:
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        kernel = {0: "apa_pool_fused_kernel", 1: "apa_pool_local_kernel", 2: "apa_stream_kernel + apa_contract_kernel",
-                  3: "apa_flow_kernel"}.get(plan.get("cluster_local"), "gemm_tf32x3_kernel (gram)")
+        kernel = {1: "apa_flow_stream_kernel (+ reduce / contract / finish tail kernels)",
+                  2: "apa_pool_local_kernel (cluster form)"}.get(plan.get("form"), "gemm_tf32x3_kernel (gram)")
         if cfg["bound"] == "tensor" and not is_gram:
             kernel = "gemm_tf32x3_kernel (pose pre-logits 2048->768) + " + kernel
         line = {
@@ -588,7 +599,7 @@ def main():
                     if world > 1 else "single GPU",
                 "l2": "inputs rotate over %d buffers x %.1f MB (%.0f MB > 2x 126 MB L2): every step reads HBM"
                       % (nbuf, x_bytes / 1e6, nbuf * x_bytes / 1e6),
-                "launch": launch_mode, "plan": plan, "batches_in_flight": nstreams,
+                "launch": launch_mode, "plan": plan, "batches_in_flight": nstreams, "stream_ctas_per_call": stream_ctas or 148,
                 "inputs_stable": args.inputs_stable, "parity_rel_err_vs_fp64_oracle": parity,
                 "clock_sampling": "nvidia-smi every 100 ms across warm-up, the K timed steps, the "
                                   "roofline loop (%d steps), the latency and e2e loops" % n_roof,

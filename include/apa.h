@@ -63,7 +63,7 @@ enum {
                                  /*  tensor) -- rejected, not given invented semantics                */
   APA_ERR_WORKSPACE        = -5, /* workspace too small or misaligned                                 */
   APA_ERR_UNSUPPORTED      = -6, /* valid in the reference but not built here         */
-  APA_ERR_ALIGN            = -7, /* X / outputs not 16-byte aligned                                   */
+  APA_ERR_ALIGN            = -7, /* X or a weight matrix is not 16-byte aligned                       */
   APA_ERR_DEVICE           = -8  /* not an sm_100 device                                              */
 };
 
@@ -101,39 +101,36 @@ typedef struct ApaWeights {
   const float* pose_logits_b;
 } ApaWeights;
 
-/* Which kernel form runs the single-map (M == 1) head.  AUTO picks by shape; the others exist for A/B
- * measurements and tests (every form computes the same function).                                       */
+/* Which kernel form runs the single-map (M == 1) head (both compute the same function). */
 enum {
-  APA_FORM_AUTO         = 0,
-  APA_FORM_GRID_BARRIER = 1, /* one kernel, p-CTA clusters per image, one grid barrier (apa_pool_fused.cu)   */
-  APA_FORM_LOCAL0       = 4, /* 16-CTA cluster-local kernel, shapes 0/1/2 (apa_pool_local.cu)                */
-  APA_FORM_LOCAL1       = 5,
-  APA_FORM_LOCAL2       = 6,
-  APA_FORM_PIPELINE     = 7, /* STREAM kernel + cluster CONTRACT kernel (apa_pool_split.cu)                  */
-  APA_FORM_NO_PIPELINE  = 8,
-  APA_FORM_FLOW         = 9  /* one launch: ticketed STREAM CTAs + CONTRACT CTAs (apa_pool_flow.cu)          */
+  APA_FORM_AUTO    = 0, /* the flow form wherever it applies                                                   */
+  APA_FORM_FLOW    = 1, /* row-balanced STREAM kernel + three small tail kernels (apa_pool_flow.cu)            */
+  APA_FORM_CLUSTER = 2  /* one kernel of 16-CTA clusters, the tail stays in shared memory (apa_pool_cluster.cu): */
+                        /* batch % 4 == 0, frames == 1, channels == 2048, classes <= 768                        */
 };
 
 /* Launch/tuning knobs; pass NULL for defaults. Does not change results beyond fp32 rounding. */
 typedef struct ApaTuning {
-  int32_t cluster_size; /* CTAs per image in the grid-barrier kernel / row slices in the pipeline: 0 = auto  */
-  int32_t fused;        /* grid-barrier kernel: 1 = one kernel, 0 = two kernels, -1 = auto                    */
-  int32_t max_ctas;     /* 0 = all SMs (flow form: number of STREAM CTAs)                                     */
-  int32_t no_cooperative; /* 1 = never use the cooperative-launch attribute for the grid-barrier kernel       */
-  int32_t no_pdl;       /* 1 = do not launch as a programmatic dependent of the previous kernel in the stream */
-                        /*     (back-to-back calls on one stream then do not overlap)                         */
-  int32_t debug_timestamps; /* 1 = kernels write a per-CTA clock64 timeline into the workspace               */
-  int32_t form;         /* APA_FORM_*                                                                         */
-  int32_t pdl_trigger_lead; /* cluster-local / pipeline forms: trigger the next launch this many tiles before */
-                        /*     a CTA's last tile (0 = at once, < 0 = at the end of the stream)                */
-  int32_t inputs_stable; /* 1 = the caller guarantees X and the weights were completely written before the    */
-                        /*     PREVIOUS kernel in `stream` was launched, so the head may read them before that */
-                        /*     kernel has finished (lets back-to-back calls on one stream overlap through      */
-                        /*     programmatic dependent launch).  0 (default) = wait for the previous kernel.    */
-  int32_t gather_wait_lag; /* apa_attn_pool_fwd_gather: after the call the gathered buffer of step             */
-                        /*     (step - lag) is complete in stream order; 0 = this step (strict), < 0 = do not  */
-                        /*     wait at all (call apa_peer_gather_wait before consuming)                        */
-  int32_t reserved[6];  /* must be 0                                                                          */
+  int32_t form;         /* APA_FORM_*                                                                          */
+  int32_t stream_ctas;  /* flow form: STREAM CTAs per call. 0 = 148, one per SM: the shortest single call.      */
+                        /*   With several independent batches in flight (one stream each) fewer CTAs per call   */
+                        /*   (37..49) pack the SMs better and raise throughput.                                 */
+  int32_t stream_shape; /* flow form, A/B runs: 0 = one STREAM CTA per SM (default), 1 = two, 2 = three          */
+  int32_t cluster_shape;/* cluster form: 0 = widest shape that fits, 1..3 = shapes 0..2 (apa_pool_cluster.cu)    */
+  int32_t no_pdl;       /* 1 = do not launch as programmatic dependents of the previous kernel in the stream    */
+  int32_t inputs_stable;/* 1 = the caller guarantees X and the weights were completely written before the       */
+                        /*   PREVIOUS kernel in `stream` was launched, so the head may read them before that     */
+                        /*   kernel has finished (back-to-back calls on one stream then overlap through         */
+                        /*   programmatic dependent launch).  0 (default) = wait for the previous kernel first.  */
+  int32_t pdl_trigger_lead; /* when a streaming CTA lets the call's next kernel be scheduled: this many tiles     */
+                        /*   before its last one (0 = at the last tiles; < 0 = as soon as the CTA starts)        */
+  int32_t gather_wait_lag; /* apa_attn_pool_fwd_gather: after the call the gathered buffer of step               */
+                        /*   (step - lag) is complete in stream order; 0 = this step (strict), < 0 = do not      */
+                        /*   wait at all (call apa_peer_gather_wait before consuming)                            */
+  int32_t debug_timestamps; /* 1 = kernels write a per-CTA clock64 / globaltimer timeline into the workspace     */
+  int32_t debug_cut_tail;   /* measurement only (results are then wrong): flow form launches only its first 1, 2 */
+                        /*   or 3 kernels (STREAM / + REDUCE / + CONTRACT)                                      */
+  int32_t reserved[6];  /* must be 0                                                                           */
 } ApaTuning;
 
 /* Library/ABI version (APA_ABI_VERSION of the build). */
@@ -146,12 +143,13 @@ const char* apa_strerror(int status);
 int apa_attn_pool_check(const ApaDesc* desc);
 
 /* Bytes of device workspace apa_attn_pool_fwd needs for `desc` (and whether the optional
- * outputs are requested). 0 on invalid desc. The workspace must be 256-byte aligned and its
- * first 2048 bytes (grid-barrier counters) must have been zeroed once (apa_attn_pool_workspace_init) before first use;
- * one workspace must not be used by two in-flight calls at the same time.                   */
+ * outputs are requested). 0 on invalid desc. The workspace must be 256-byte aligned and must have
+ * been zeroed once (apa_attn_pool_workspace_init) before first use (it holds the kernels' counters);
+ * calls that share a workspace must be issued on one stream (they may overlap there: the per-call
+ * buffers exist twice), two streams need two workspaces.                                     */
 size_t apa_attn_pool_workspace(const ApaDesc* desc, int want_attn, int want_topdown, int want_pose);
 
-/* Enqueue zeroing of the workspace control block on `stream`. */
+/* Enqueue zeroing of the workspace on `stream`. */
 int apa_attn_pool_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
 /* The head, forward, device buffers.  Replaces the graph built by
@@ -220,11 +218,10 @@ int apa_peer_gather_wait(const ApaPeerGather* gather, int32_t lag, void* stream)
 int apa_gram_fwd(int32_t batch, int32_t hw, int32_t channels, const float* X, float* G,
                  void* stream);
 
-/* Introspection for tests/bench: how the last-validated desc would be executed.
- * Fills plan[0]=path (0 fused-rank1-map, 1 dense), [1]=cluster_size, [2]=grid CTAs,
- * [3]=fused(0/1), [4]=kernel launches per call, [5]=smem bytes, [6]=1 if the cluster-local small-batch
- * kernel (16-CTA clusters, no grid barrier) is used, 2 for the STREAM + CONTRACT pipeline (then [1] = row
- * slices per image, [2] = STREAM grid, [7] = CONTRACT grid).                                 */
+/* Introspection for tests/bench: how `desc` would be executed.
+ * Fills plan[0] = path (0 single-map fast path, 1 dense), [1] = form (APA_FORM_FLOW / APA_FORM_CLUSTER, 0 on
+ * the dense path), [2] = CTAs of the streaming kernel, [3] = kernel launches per call, [4] = shared memory
+ * bytes of the streaming kernel, [5] = CTAs of the flow form's CONTRACT kernel, [6..7] = 0.     */
 int apa_attn_pool_plan(const ApaDesc* desc, const ApaTuning* tuning, int want_attn,
                        int want_topdown, int want_pose, int32_t plan[8]);
 

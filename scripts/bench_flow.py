@@ -28,16 +28,16 @@ xs = [torch.relu(torch.randn((B, HW, C), device=dev, generator=g)) for _ in rang
 ref, _ = orc.attn_pool_head(xs[0][:2 * F].cpu().numpy(), params, fl, K, frames_per_video=F, want_pose=False)
 
 CONFIGS = []
-for form, name in ((0, "auto"), (ops.APA_FORM_FLOW, "flow"), (ops.APA_FORM_PIPELINE, "pipeline")):
-    for lanes in (1, 2, 4):
-        for stable in ((1,) if form != ops.APA_FORM_FLOW else (0, 1)):
+for form, name in ((ops.APA_FORM_FLOW, "flow"), (ops.APA_FORM_CLUSTER, "cluster")):
+    for lanes in (1, 2, 4, 6):
+        for stable in (0, 1):
             CONFIGS.append((name, form, lanes, stable, 0))
-CONFIGS += [("flow", ops.APA_FORM_FLOW, 4, 1, 74), ("flow", ops.APA_FORM_FLOW, 3, 1, 0)]
-LEADS = (0, 2, 6, -1)
+CONFIGS += [("flow", ops.APA_FORM_FLOW, 4, 1, 49), ("flow", ops.APA_FORM_FLOW, 6, 1, 37), ("flow", ops.APA_FORM_FLOW, 8, 1, 25)]
+LEADS = (0,)
 
 
 def run_cfg(name, form, lanes, stable, max_ctas, lead=0):
-    tun = ops.make_tuning(form=form, inputs_stable=stable, max_ctas=max_ctas, pdl_trigger_lead=lead)
+    tun = ops.make_tuning(form=form, inputs_stable=stable, stream_ctas=max_ctas, pdl_trigger_lead=lead)
     opl = [ops.AttnPoolOp(P, K, HW, channels=C, frames=F, rank=rank, flags=bits, tuning=tun, device=dev)
            for _ in range(lanes)]
     plan = ops.attn_pool_plan(opl[0].desc(B), tun)
@@ -96,7 +96,7 @@ def run_cfg(name, form, lanes, stable, max_ctas, lead=0):
         lat.append(a.elapsed_time(b) * 1e3)
     lat.sort()
     print("%-9s lanes=%d stable=%d max_ctas=%3d lead=%2d [%s, kind %d, grid %d]: %7.2f us/step  %5.2f TB/s  frac %.3f | one launch: %6.1f us (median of 12)"
-          % (name, lanes, stable, max_ctas, lead, mode, plan["cluster_local"], plan["grid"], us, algo / us / 1e6,
+          % (name, lanes, stable, max_ctas, lead, mode, plan["form"], plan["grid"], us, algo / us / 1e6,
              algo / us / 1e6 / 6.5748, lat[len(lat) // 2]), flush=True)
 
 

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Where the flow form's time goes: the chain with its tail cut off (ApaTuning.fused = 100: STREAM alone, 101: STREAM +
-REDUCE; results are then wrong by construction) against the full chain, by lanes and trigger lead."""
+"""Where the flow form's time goes: the chain with its tail cut off (ApaTuning.debug_cut_tail = 1: STREAM alone, 2: +
+REDUCE, 3: + CONTRACT; results are then wrong by construction) against the full chain, by lanes, trigger lead and
+STREAM CTAs per call."""
 import os, sys, math
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,7 +21,7 @@ xs = [torch.relu(torch.randn((B, HW, C), device=dev)) for _ in range(nbuf)]
 
 
 def run(tag, fused, lanes, lead, max_ctas=0, shape=0):
-    tun = ops.make_tuning(form=ops.APA_FORM_FLOW, inputs_stable=1, fused=fused, pdl_trigger_lead=lead, max_ctas=max_ctas, cluster_size=shape)
+    tun = ops.make_tuning(form=ops.APA_FORM_FLOW, inputs_stable=1, debug_cut_tail=fused, pdl_trigger_lead=lead, stream_ctas=max_ctas, stream_shape=shape)
     opl = [ops.AttnPoolOp(P, K, HW, rank=rank, flags=bits, tuning=tun, device=dev) for _ in range(lanes)]
     outs = [torch.empty((B, K), device=dev) for _ in range(lanes)]
     side = torch.cuda.Stream()
@@ -58,7 +59,8 @@ def run(tag, fused, lanes, lead, max_ctas=0, shape=0):
 
 
 import itertools
-for lanes, g in itertools.product((4, 6, 8), (25, 37, 49, 74)):
-    run("full chain", -1, lanes, 0, g)
-run("full chain", -1, 8, -1, 37)
-run("full chain", -1, 6, -1, 49)
+for lanes in (1, 2, 4):
+    for cut, tag in ((1, "STREAM alone"), (2, "STREAM + REDUCE"), (3, "STREAM+REDUCE+CONTRACT"), (0, "full chain")):
+        run(tag, cut, lanes, 0)
+for lanes, g in itertools.product((4, 6, 8), (25, 37, 49, 74, 148)):
+    run("full chain", 0, lanes, 0, g)

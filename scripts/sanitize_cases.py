@@ -15,13 +15,13 @@ which = sys.argv[1] if len(sys.argv) > 1 else "all"
 S = dict(SINGLE_LAYER_ATT=True)
 
 
-def head(name, B, HW, C, K, flags, F=1, form=0, gather=False, want=(False, False, False), reps=2):
+def head(name, B, HW, C, K, flags, F=1, form=0, gather=False, want=(False, False, False), reps=2, shape=0):
     fl = dict(orc.DEFAULT_FLAGS, **flags)
     params = orc.make_params(K, C, 64, 5, flags=fl, seed=2)
     X = orc.make_features(B, HW, C, seed=2)
     ref, _ = orc.attn_pool_head(X, params, fl, K, frames_per_video=F, want_pose=False)
     bits, rank = ops.flags_from_cfg_net(fl)
-    t = ops.make_tuning(form=form, inputs_stable=1)
+    t = ops.make_tuning(form=form, inputs_stable=1, stream_shape=shape)
     op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, frames=F, rank=rank,
                         flags=bits, num_pose_keypoints=5, tuning=t, device="cuda:0")
     Xd = torch.from_numpy(X).cuda()
@@ -48,12 +48,13 @@ if which in ("all", "flow"):
     head("flow gather (world 1, depth 2)", 8, 49, 2048, 37, S, form=ops.APA_FORM_FLOW, gather=True)
     head("flow attention end point", 4, 25, 2048, 37, dict(S, SOFTMAX_ATT=True), form=ops.APA_FORM_FLOW,
          want=(True, False, False))
-if which in ("all", "older"):
-    head("cluster-local b8", 8, 49, 2048, 37, S, form=ops.APA_FORM_LOCAL0)
-    head("cluster-local shape 2 softmax", 8, 25, 2048, 37, dict(S, SOFTMAX_ATT=True), form=ops.APA_FORM_LOCAL2)
-    head("pipeline frames2", 8, 25, 2048, 37, S, F=2, form=ops.APA_FORM_PIPELINE)
-    head("grid-barrier b5 rank2", 5, 25, 2048, 37, dict(S, RANK=2), form=ops.APA_FORM_GRID_BARRIER)
-    head("cluster-local gather (world 1)", 8, 49, 2048, 37, S, form=ops.APA_FORM_LOCAL0, gather=True)
+    head("flow stream shape 1", 8, 49, 2048, 37, S, form=ops.APA_FORM_FLOW, shape=1)
+    head("flow stream shape 2", 8, 49, 2048, 37, dict(S, RELU_ATT=True), form=ops.APA_FORM_FLOW, shape=2)
+if which in ("all", "cluster"):
+    head("cluster form b8", 8, 49, 2048, 37, S, form=ops.APA_FORM_CLUSTER)
+    head("cluster form softmax", 8, 25, 2048, 37, dict(S, SOFTMAX_ATT=True), form=ops.APA_FORM_CLUSTER)
+    head("cluster form rank2", 4, 25, 2048, 37, dict(S, RANK=2), form=ops.APA_FORM_CLUSTER)
+    head("cluster form gather (world 1)", 8, 49, 2048, 37, S, form=ops.APA_FORM_CLUSTER, gather=True)
 if which in ("all", "dense"):
     head("config 003 (tcgen05 pose GEMM + a0)", 8, 64, 2048, 37, dict(RANK=2), form=ops.APA_FORM_FLOW)
     head("per-class dense path", 4, 64, 2048, 40, dict(S, PER_CLASS=True))

@@ -38,14 +38,15 @@ def test_struct_layouts_match_header():
     prog = r'''
 #include <stdio.h>
 #include "apa.h"
-int main(void){ printf("%zu %zu %zu %d %d\n", sizeof(ApaDesc), sizeof(ApaWeights), sizeof(ApaTuning),
-                       APA_ABI_VERSION, APA_MAX_RANK); return 0; }'''
+int main(void){ printf("%zu %zu %zu %zu %d %d\n", sizeof(ApaDesc), sizeof(ApaWeights), sizeof(ApaTuning),
+                       sizeof(ApaPeerGather), APA_ABI_VERSION, APA_MAX_RANK); return 0; }'''
     exe = "/tmp/apa_sizes_%d" % os.getpid()
     subprocess.run(["gcc", "-x", "c", "-I", os.path.join(ROOT, "include"), "-o", exe, "-"], input=prog,
                    text=True, check=True)
-    d, w, t, ver, mr = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
+    d, w, t, g, ver, mr = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
     os.remove(exe)
-    assert (d, w, t) == (ctypes.sizeof(ops.ApaDesc), ctypes.sizeof(ops.ApaWeights), ctypes.sizeof(ops.ApaTuning))
+    assert (d, w, t, g) == (ctypes.sizeof(ops.ApaDesc), ctypes.sizeof(ops.ApaWeights), ctypes.sizeof(ops.ApaTuning),
+                            ctypes.sizeof(ops.ApaPeerGather))
     assert ver == ops.APA_ABI_VERSION == ops.attn_pool_lib.apa_abi_version()
     assert mr == ops.APA_MAX_RANK
 
@@ -85,62 +86,51 @@ def test_workspace_sizes():
     assert ops.attn_pool_workspace(cfg3) >= 128 * 196 * 768 * 4
 
 
-@pytest.mark.parametrize("B,frames,K,expect_cluster", [(32, 1, 393, 16), (30, 1, 393, 4), (15, 1, 393, 8),
-                                                      (130, 1, 393, 1), (2, 1, 393, 16)])
-def test_plan_without_device(B, frames, K, expect_cluster):
-    """Plan introspection falls back to the nominal 148-SM B200 when no device is visible."""
-    import torch
-    if torch.cuda.is_available():
-        pytest.skip("device present: plan comes from the occupancy query")
-    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
-    plan = ops.attn_pool_plan(ops.make_desc(B, 196, 2048, K, frames=frames))
-    assert plan["path"] == 0 and plan["fused"] == 1 and plan["launches"] == 1
-    assert plan["cluster_size"] == expect_cluster
-    assert plan["cluster_local"] == (1 if (B % 4 == 0 and frames == 1) else 0)
-    assert plan["grid"] <= 148 and plan["grid"] % plan["cluster_size"] == 0
-    assert plan["smem_bytes"] <= 227 * 1024
-    dense = ops.attn_pool_plan(ops.make_desc(2, 196, 2048, 393, flags=ops.APA_FLAG_SINGLE_LAYER_ATT |
-                                             ops.APA_FLAG_PER_CLASS))
-    assert dense["path"] == 1
-    # several frames per video (HICO 10-crop): the STREAM + CONTRACT pipeline, two launches
-    pipe = ops.attn_pool_plan(ops.make_desc(320, 196, 2048, 600, frames=10))
-    assert pipe["path"] == 0 and pipe["cluster_local"] == 2 and pipe["launches"] == 2 and pipe["fused"] == 0
-    assert pipe["cluster_size"] == 1 and pipe["grid"] == 320 and pipe["contract_grid"] == 16 * 11
-    assert pipe["smem_bytes"] <= 76800
-    t = ops.make_tuning()
-    t.form = 1      # the grid-barrier kernel stays selectable
-    assert ops.attn_pool_plan(ops.make_desc(320, 196, 2048, 600, frames=10), t)["cluster_local"] == 0
-
-
-
 @pytest.mark.parametrize("kw,expect", [
-    # (descriptor, tuning code) -> (cluster_local, cluster_size, grid, launches, smem_bytes)
-    (dict(B=32), (1, 16, 64, 1, 73024)),                 # config 2: cluster-local throughput shape (8 images / cluster)
-    (dict(B=36), (1, 16, 144, 1, 66752)),                # B % 8 != 0: 4 images / cluster, 3 CTAs / SM
-    (dict(B=32, rank=2), (1, 16, 128, 1, 122048)),       # rank chain: 2-CTA/SM shape
-    (dict(B=32, K=600), (1, 16, 128, 1, 67904)),         # K = 600: the 8-image shape no longer fits 3 per SM
-    (dict(B=30), (0, 4, 120, 1, 107472)),                # odd batch: grid-barrier kernel
-    (dict(B=32, C=1024), (0, 4, 128, 1, 103376)),
-    (dict(B=32, K=800), (0, 4, 128, 1, 107472)),         # K > 768: not cluster-local
-    (dict(B=320, F=10, K=600), (2, 1, 320, 2, 74048)),   # several frames per video: STREAM + CONTRACT pipeline
-    (dict(B=32, code=4), (1, 16, 128, 1, 113856)),       # forced shapes / forms
-    (dict(B=32, code=5), (1, 16, 128, 1, 66752)),
-    (dict(B=32, code=7), (2, 4, 128, 2, 74048)),
-    (dict(B=32, code=1), (0, 4, 128, 1, 107472)),
+    # (descriptor, tuning) -> (form, grid of the streaming kernel, launches per call, CONTRACT grid)
+    (dict(B=32), (1, 148, 4, 16 * 13)),                       # config 2: flow form, one STREAM CTA per SM
+    (dict(B=1), (1, 12, 4, 16 * 13)),                         # the eval.py batch: at least 16 rows per STREAM CTA
+    (dict(B=1, HW=10), (1, 1, 4, 16 * 13)),
+    (dict(B=30), (1, 148, 4, 16 * 13)),                       # any batch
+    (dict(B=320, F=10, K=600), (1, 148, 4, 16 * 19)),         # HICO 10-crop
+    (dict(B=32, C=1024, rank=3), (1, 148, 4, 16 * 13)),
+    (dict(B=32, stream_ctas=37), (1, 37, 4, 16 * 13)),        # throughput setting: fewer STREAM CTAs per call
+    (dict(B=32, form=2), (2, 64, 1, 0)),                      # cluster form on request: 8 images per cluster
+    (dict(B=36, form=2), (2, 144, 1, 0)),
+    (dict(B=32, form=2, cluster_shape=1), (2, 128, 1, 0)),
+    (dict(B=30, form=2), (1, 148, 4, 16 * 13)),               # ... and the flow form where it does not apply
+    (dict(B=32, form=2, F=2), (1, 148, 4, 16 * 13)),
+    (dict(B=32, pose=True), (1, 148, 5, 16 * 13)),            # config 003: the pose GEMM in front
 ])
 def test_dispatch_policy_without_device(kw, expect):
-    """Which form of the single-map head a descriptor gets, pinned on the nominal B200."""
-    import torch
-    if torch.cuda.is_available():
-        pytest.skip("device present: plan comes from the occupancy query")
+    """Which form of the single-map head a descriptor gets: no device needed."""
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     kw = dict(kw)
-    t = ops.make_tuning()
-    t.form = kw.pop("code", 0)
-    d = ops.make_desc(kw.get("B"), 196, kw.get("C", 2048), kw.get("K", 393), frames=kw.get("F", 1), rank=kw.get("rank", 1))
+    t = ops.make_tuning(form=kw.pop("form", 0), stream_ctas=kw.pop("stream_ctas", 0), cluster_shape=kw.pop("cluster_shape", 0))
+    flags = 0 if kw.pop("pose", False) else ops.APA_FLAG_SINGLE_LAYER_ATT
+    d = ops.make_desc(kw.get("B"), kw.get("HW", 196), kw.get("C", 2048), kw.get("K", 393), frames=kw.get("F", 1),
+                      rank=kw.get("rank", 1), flags=flags)
     p = ops.attn_pool_plan(d, t)
-    assert (p["cluster_local"], p["cluster_size"], p["grid"], p["launches"], p["smem_bytes"]) == expect
     assert p["path"] == 0
+    assert (p["form"], p["grid"], p["launches"], p["contract_grid"]) == expect
+    assert 0 < p["smem_bytes"] <= 227 * 1024
+
+
+def test_dense_path_plan_and_tuning_validation():
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    dense = ops.attn_pool_plan(ops.make_desc(2, 196, 2048, 393, flags=ops.APA_FLAG_SINGLE_LAYER_ATT |
+                                             ops.APA_FLAG_PER_CLASS))
+    assert dense["path"] == 1 and dense["form"] == 0
+    assert ops.attn_pool_plan(ops.make_desc(2, 196, 512, 393))["path"] == 1          # C outside {1024, 2048}
+    assert ops.attn_pool_plan(ops.make_desc(2, 196, 2048, 393), want_topdown=True)["path"] == 1
+    for bad in (dict(form=7), dict(stream_shape=3), dict(cluster_shape=4), dict(stream_ctas=-1)):
+        with pytest.raises(ops.ApaError) as e:
+            ops.attn_pool_plan(ops.make_desc(2, 196, 2048, 393), ops.make_tuning(**bad))
+        assert e.value.status == ops.APA_ERR_UNSUPPORTED
+    t = ops.make_tuning()
+    t.reserved[2] = 1
+    with pytest.raises(ops.ApaError):
+        ops.attn_pool_plan(ops.make_desc(2, 196, 2048, 393), t)
 
 
 def test_forward_without_gpu_fails_loudly():

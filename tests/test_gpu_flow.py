@@ -1,5 +1,6 @@
-"""The flow form of the single-map head (csrc/apa_pool_flow.cu: ticketed STREAM + CONTRACT CTAs in one launch)
-against the fp64 oracle through the C ABI.  Same tolerance as tests/test_gpu_parity.py."""
+"""The flow form of the single-map head (csrc/apa_pool_flow.cu: row-balanced STREAM kernel + REDUCE / CONTRACT /
+FINISH tail kernels, per-call buffers kept twice) against the fp64 oracle through the C ABI.  Same tolerance as
+tests/test_gpu_parity.py."""
 import numpy as np
 import pytest
 
@@ -25,7 +26,7 @@ def _run(B, HW, C, K, flags, seed=0, F=1, want=(False, False, False), tuning=Non
     bits, rank = ops.flags_from_cfg_net(fl)
     tuning = tuning if tuning is not None else _flow_tuning()
     plan = ops.attn_pool_plan(ops.make_desc(B, HW, C, K, frames=F, rank=rank, flags=bits), tuning, *want)
-    assert plan["cluster_local"] == 3, plan
+    assert plan["form"] == ops.APA_FORM_FLOW and plan["path"] == 0, plan
     op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, frames=F,
                         rank=rank, flags=bits, tuning=tuning, device="cuda:0")
     logits, ep = op(torch.from_numpy(X).cuda(), want_attn=want[0], want_topdown=want[1], want_pose=want[2])
@@ -77,16 +78,19 @@ def test_flow_parity(case):
 
 @pytest.mark.parametrize("g", [1, 7, 37, 148])
 def test_flow_any_number_of_stream_ctas(g):
-    """ApaTuning.max_ctas = number of STREAM CTAs: any cut of the row space gives the same logits to fp32 rounding."""
+    """ApaTuning.stream_ctas = number of STREAM CTAs: any cut of the row space, and every shape of the STREAM kernel,
+    gives the same logits to fp32 rounding."""
     from oracle import attn_pool_oracle as orc
     for flags in (SINGLE, dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=2, RELU_ATT=True)):
-        got, _, ref, _ = _run(9, 196, 2048, 393, flags, seed=3, tuning=_flow_tuning(max_ctas=g))
-        orc.assert_parity(got, ref, TOL)
+        for shape in (0, 1, 2):
+            got, _, ref, _ = _run(9, 196, 2048, 393, flags, seed=3, tuning=_flow_tuning(stream_ctas=g, stream_shape=shape))
+            orc.assert_parity(got, ref, TOL)
 
 
+@pytest.mark.parametrize("lead", [0, -1, 3])
 @pytest.mark.parametrize("stable", [0, 1])
 @pytest.mark.parametrize("pdl", [0, 1])
-def test_flow_back_to_back_same_workspace(stable, pdl):
+def test_flow_back_to_back_same_workspace(stable, pdl, lead):
     """40 launches queued on one stream, one workspace (the counters only ever grow), changing inputs; with
     inputs_stable=1 consecutive launches overlap through programmatic dependent launch."""
     import torch
@@ -97,7 +101,7 @@ def test_flow_back_to_back_same_workspace(stable, pdl):
     X = orc.make_features(32, 196, 2048, seed=5)
     bits, rank = ops.flags_from_cfg_net(fl)
     op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 393, 196, rank=rank, flags=bits,
-                        tuning=_flow_tuning(inputs_stable=stable, no_pdl=1 - pdl), device="cuda:0")
+                        tuning=_flow_tuning(inputs_stable=stable, no_pdl=1 - pdl, pdl_trigger_lead=lead), device="cuda:0")
     Xd = torch.from_numpy(X).cuda()
     xs = [torch.roll(Xd, i, 0).contiguous() for i in range(4)]
     outs = [torch.empty((32, 393), device="cuda") for _ in range(4)]

@@ -60,22 +60,22 @@ def test_every_form_of_the_head_sees_a_reference_fixture(name):
     X = torch.from_numpy(z["X"]).cuda()
     H, W = meta["hw"]
     bits, rank = ops.flags_from_cfg_net(meta["flags"])
-    forms = [(ops.APA_FORM_FLOW, 3), (ops.APA_FORM_GRID_BARRIER, 0), (ops.APA_FORM_PIPELINE, 2)]
+    forms = [(ops.APA_FORM_FLOW, 0, 0), (ops.APA_FORM_FLOW, 1, 0), (ops.APA_FORM_FLOW, 2, 0)]
     if meta["frames"] == 1:
-        forms.append((ops.APA_FORM_LOCAL0, 1))
+        forms += [(ops.APA_FORM_CLUSTER, 0, 1), (ops.APA_FORM_CLUSTER, 0, 3)]
     seen = set()
-    for form, kind in forms:
-        t = ops.make_tuning(form=form)
+    for form, sshape, cshape in forms:
+        t = ops.make_tuning(form=form, stream_shape=sshape, cluster_shape=cshape)
         op = ops.AttnPoolOp(variables, meta["num_classes"], H * W, channels=meta["channels"], frames=meta["frames"],
                             rank=rank, flags=bits, num_pose_keypoints=meta["num_pose_keypoints"], tuning=t,
                             device="cuda:0")
         plan = ops.attn_pool_plan(op.desc(X.shape[0]), t)
-        assert plan["path"] == 0 and plan["cluster_local"] == kind, (form, dict(plan))
-        seen.add(plan["cluster_local"])
+        assert plan["path"] == 0 and plan["form"] == form, (form, dict(plan))
+        seen.add(plan["form"])
         logits, _ = op(X)
         torch.cuda.synchronize()
         orc.assert_parity(logits.cpu().numpy(), z["logits"], TOL, "%s form %d" % (name, form))
-    assert len(seen) == len(forms)
+    assert seen == {f for f, _, _ in forms}
 
 
 def test_reference_build_error_is_an_abi_error():

@@ -62,30 +62,15 @@ FUSED_CASES = [
 
 @pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
 def test_fused_path_parity(case):
-    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    """The single-map fast path in its default form (flow), every flag set and the edge shapes."""
     from oracle import attn_pool_oracle as orc
     _, B, HW, C, K, flags, F = case
     got, _, ref, _ = _run(B, HW, C, K, flags, F=F)
     orc.assert_parity(got, ref, TOL)
-    if F > 1:   # the default for several frames per video is the pipeline: cover the grid-barrier kernel too
-        t = ops.make_tuning()
-        t.form = 1
-        got, _, ref, _ = _run(B, HW, C, K, flags, F=F, tuning=t)
-        orc.assert_parity(got, ref, TOL)
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
-@pytest.mark.parametrize("fused", [1, 0])
-def test_cluster_sizes_and_split_launch(cluster, fused):
-    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
-    from oracle import attn_pool_oracle as orc
-    for flags in (SINGLE, dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=2, RELU_ATT=True)):
-        got, _, ref, _ = _run(9, 196, 2048, 393, flags, seed=3, tuning=ops.make_tuning(cluster, fused))
-        orc.assert_parity(got, ref, TOL)
-
-
-LOCAL_CASES = [
-    # the cluster-local small-batch kernel: B % 4 == 0, F == 1, C == 2048 (id, B, HW, K, flags)
+CLUSTER_CASES = [
+    # the cluster form (APA_FORM_CLUSTER): B % 4 == 0, F == 1, C == 2048 (id, B, HW, K, flags)
     ("b32_k393", 32, 196, 393, SINGLE),
     ("b4_k600_nc3", 4, 196, 600, SINGLE),
     ("b8_softmax", 8, 196, 393, dict(SINGLE, SOFTMAX_ATT=True)),
@@ -98,94 +83,41 @@ LOCAL_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", LOCAL_CASES, ids=[c[0] for c in LOCAL_CASES])
-def test_cluster_local_kernel(case):
-    """The 16-CTA-cluster kernel (no grid barrier) against the oracle, and bit-for-bit run-to-run."""
+@pytest.mark.parametrize("case", CLUSTER_CASES, ids=[c[0] for c in CLUSTER_CASES])
+def test_cluster_form(case):
+    """The 16-CTA-cluster kernel (the tail stays in shared memory) against the oracle and the flow form, all of its
+    shapes, bit-for-bit run-to-run, with and without the caller's inputs_stable promise."""
     import torch
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     from oracle import attn_pool_oracle as orc
     _, B, HW, K, flags = case
     fl = dict(orc.DEFAULT_FLAGS, **flags)
     bits, rank = ops.flags_from_cfg_net(fl)
-    plan = ops.attn_pool_plan(ops.make_desc(B, HW, 2048, K, rank=rank, flags=bits))
-    assert plan["cluster_local"] == 1 and plan["cluster_size"] == 16
-    got, _, ref, _ = _run(B, HW, 2048, K, flags, seed=31)
+    t = ops.make_tuning(form=ops.APA_FORM_CLUSTER)
+    plan = ops.attn_pool_plan(ops.make_desc(B, HW, 2048, K, rank=rank, flags=bits), t)
+    assert plan["form"] == ops.APA_FORM_CLUSTER and plan["launches"] == (1 if fl["SINGLE_LAYER_ATT"] else 2)
+    got, _, ref, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
     orc.assert_parity(got, ref, TOL)
-    # the general (grid-barrier) kernel on the same inputs agrees to fp32 rounding
-    t = ops.make_tuning()
-    t.form = 1
-    got2, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
+    got2, _, _, _ = _run(B, HW, 2048, K, flags, seed=31)        # the default (flow) form agrees to fp32 rounding
     orc.assert_parity(got2, ref, TOL)
     assert np.abs(got - got2).max() <= 1e-5 * max(1e-30, np.abs(ref).max())
-    # both ring shapes of the cluster-local kernel (4-row x 3-stage: 2 CTAs/SM, 3-row x 2-stage: 3 CTAs/SM)
-    for force in (4, 5, 6):
-        t = ops.make_tuning()
-        t.form = force
-        got3, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
-        orc.assert_parity(got3, ref, TOL)
-        got4, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
-        assert np.array_equal(got3, got4)
+    for shape in (1, 2, 3):
+        for stable in (0, 1):
+            t = ops.make_tuning(form=ops.APA_FORM_CLUSTER, cluster_shape=shape, inputs_stable=stable)
+            got3, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
+            orc.assert_parity(got3, ref, TOL)
+            got4, _, _, _ = _run(B, HW, 2048, K, flags, seed=31, tuning=t)
+            assert np.array_equal(got3, got4)
 
 
-def _split_tuning(lp=0, no_pdl=0):
-    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
-    t = ops.make_tuning(lp, -1, no_pdl=no_pdl)
-    t.form = 7     # force the two-kernel STREAM + CONTRACT pipeline
-    return t
-
-
-@pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
-def test_split_pipeline_parity(case):
-    """The two-kernel pipeline (lean streaming kernel -> partial g in the workspace -> cluster contraction)
-    on every single-map shape: ranks, relu/softmax, frames, C = 1024, K = 1..600, B = 1..200; bit-reproducible."""
+def test_cluster_form_falls_back_to_flow_where_it_does_not_apply():
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     from oracle import attn_pool_oracle as orc
-    _, B, HW, C, K, flags, F = case
-    fl = dict(orc.DEFAULT_FLAGS, **flags)
-    bits, rank = ops.flags_from_cfg_net(fl)
-    plan = ops.attn_pool_plan(ops.make_desc(B, HW, C, K, frames=F, rank=rank, flags=bits), _split_tuning())
-    assert plan["cluster_local"] == 2 and plan["launches"] == 2
-    got, _, ref, _ = _run(B, HW, C, K, flags, F=F, tuning=_split_tuning())
-    orc.assert_parity(got, ref, TOL)
-    got2, _, _, _ = _run(B, HW, C, K, flags, F=F, tuning=_split_tuning())
-    assert np.array_equal(got, got2)
-
-
-@pytest.mark.parametrize("lp", [1, 2, 4, 8, 16])
-def test_split_pipeline_row_slices(lp):
-    """Any number of row slices per image (ApaTuning.cluster_size) gives the same logits to fp32 rounding."""
-    from oracle import attn_pool_oracle as orc
-    for flags in (SINGLE, dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=2, RELU_ATT=True)):
-        got, _, ref, _ = _run(9, 196, 2048, 393, flags, seed=3, tuning=_split_tuning(lp))
+    t = ops.make_tuning(form=ops.APA_FORM_CLUSTER)
+    for B, C, F in ((9, 2048, 1), (8, 1024, 1), (8, 2048, 2)):
+        assert ops.attn_pool_plan(ops.make_desc(B, 196, C, 393, frames=F), t)["form"] == ops.APA_FORM_FLOW
+        got, _, ref, _ = _run(B, 196, C, 393, SINGLE, F=F, seed=4, tuning=t)
         orc.assert_parity(got, ref, TOL)
-        got, _, ref, _ = _run(9, 196, 2048, 393, flags, seed=3, tuning=_split_tuning(lp, no_pdl=1))
-        orc.assert_parity(got, ref, TOL)
-
-
-def test_split_pipeline_back_to_back_and_end_points():
-    """40 queued launches share one workspace (STREAM(n+1) overlaps CONTRACT(n)); plus the attention end point
-    (softmax normalisation read back from the pipeline's stats) and the pose-source attention (config 003)."""
-    import torch
-    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
-    from oracle import attn_pool_oracle as orc
-    for flags in (SINGLE, dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=2, RELU_ATT=True)):
-        fl, params, X = _setup(32, 196, 2048, 393, flags, seed=12)
-        bits, rank = ops.flags_from_cfg_net(fl)
-        op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 393, 196, rank=rank, flags=bits,
-                            tuning=_split_tuning(), device="cuda:0")
-        xs = [torch.from_numpy(np.roll(X, i, axis=0).copy()).cuda() for i in range(4)]
-        outs = [torch.empty((32, 393), device="cuda") for _ in range(4)]
-        for rep in range(10):
-            for i in range(4):
-                op(xs[i], logits=outs[i])
-        torch.cuda.synchronize()
-        ref, _ = orc.attn_pool_head(X, params, fl, 393, want_pose=False)
-        for i in range(4):
-            orc.assert_parity(outs[i].cpu().numpy(), np.roll(ref, i, axis=0), TOL)
-    for flags in (dict(SINGLE, SOFTMAX_ATT=True), dict(SINGLE, RANK=3, RELU_ATT=True), dict(RANK=2), dict(SOFTMAX_ATT=True)):
-        got, ep, ref, ref_ep = _run(5, 196, 2048, 393, flags, seed=21, want=(True, False, False), tuning=_split_tuning())
-        orc.assert_parity(got, ref, TOL)
-        orc.assert_parity(ep["PosePrelogitsBasedAttention"], ref_ep["PosePrelogitsBasedAttention"], TOL, "attention")
 
 
 @pytest.mark.parametrize("no_pdl", [0, 1])
@@ -211,26 +143,26 @@ def test_back_to_back_launches(no_pdl):
             orc.assert_parity(outs[i].cpu().numpy(), np.roll(ref, i, axis=0), TOL)
 
 
-@pytest.mark.parametrize("B,general", [(32, 0), (32, 1), (9, 0), (32, 7), (9, 7)])
-def test_fused_gather_single_rank(B, general):
-    """apa_attn_pool_fwd_gather with world == 1: the peer-store epilogue + step flags on one GPU."""
+@pytest.mark.parametrize("B,form,depth", [(32, 0, 1), (32, 0, 3), (9, 0, 2), (32, 2, 1), (8, 2, 2)])
+def test_fused_gather_single_rank(B, form, depth):
+    """apa_attn_pool_fwd_gather with world == 1: the peer-store epilogue, the ring of gathered buffers and the step
+    flags on one GPU (both forms)."""
     import torch
     from attentionalpoolingaction_b200 import dist as apa_dist
     from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
     from oracle import attn_pool_oracle as orc
     fl, params, X = _setup(B, 196, 2048, 393, SINGLE, seed=17)
     bits, rank = ops.flags_from_cfg_net(fl)
-    t = ops.make_tuning()
-    t.form = general
     op = ops.AttnPoolOp({k: torch.from_numpy(v) for k, v in params.items()}, 393, 196, rank=rank, flags=bits,
-                        tuning=t, device="cuda:0")
-    pg = apa_dist.PeerGather(B, 393, torch.device("cuda:0"))
-    Xd = torch.from_numpy(X).cuda()
-    for _ in range(5):
-        op.forward_gather(Xd, pg)
+                        tuning=ops.make_tuning(form=form), device="cuda:0")
+    pg = apa_dist.PeerGather(B, 393, torch.device("cuda:0"), depth=depth)
+    xs = [torch.from_numpy(np.roll(X, i, axis=0).copy()).cuda() for i in range(5)]
+    steps = [op.forward_gather(xs[i], pg) for i in range(5)]
     torch.cuda.synchronize()
+    assert steps == [1, 2, 3, 4, 5]
     ref, _ = orc.attn_pool_head(X, params, fl, 393, want_pose=False)
-    orc.assert_parity(pg.out.cpu().numpy(), ref, TOL)
+    for i in range(5 - depth, 5):                # the last `depth` calls are still in the ring
+        orc.assert_parity(pg.buffer(steps[i]).cpu().numpy(), np.roll(ref, i, axis=0), TOL)
     assert int(pg.flags[0].item()) == 5        # one data flag per launch
     assert pg.sync_step() == 5                 # counted on the device
 
@@ -346,11 +278,13 @@ def test_properties_at_full_size():
     per_crop = op1(X)[0]
     pooled = opF(X)[0]
     scale = per_crop.abs().max().item()
+    assert torch.equal(op1(X)[0], per_crop)      # the same call again: bit-identical
     # crop mean == mean of per-crop logits
     assert (pooled - per_crop.reshape(B // F, F, K).mean(1)).abs().max().item() <= 1e-5 * scale
-    # permuting the batch permutes the logits (bitwise: per-image work is independent of position)
+    # permuting the batch permutes the logits -- to fp32 rounding: the rows of the whole batch are cut into equal
+    # runs, so where an image is cut (and with it the order of its partial sums) depends on its position
     perm = torch.randperm(B, device="cuda", generator=g)
-    assert torch.equal(op1(X[perm].contiguous())[0], per_crop[perm])
+    assert (op1(X[perm].contiguous())[0] - per_crop[perm]).abs().max().item() <= 1e-5 * scale
     # linear in the top-down weights and biases
     P2 = dict(P)
     tw, tb = "PosePrelogitsBasedAttention/Conv/weights", "PosePrelogitsBasedAttention/Conv/biases"

@@ -171,15 +171,19 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 // flags[q] is rank q's flag array of 2 * world words: word r = the last step whose logits rank r has completely
 // stored into q's gathered ring; word world + r = the last step rank r has STARTED after everything before it in
 // r's stream completed (= r has consumed every gathered buffer it had to, see include/apa.h).
+// ONE system-scope fence, then a relaxed store per peer (a release store per peer would be a fence per peer, i.e. one
+// NVLink round trip after the other)
 __device__ __forceinline__ void peer_gather_publish(int world, int rank, unsigned long long* const* flags,
                                                     unsigned long long step) {
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
   for (int q = 0; q < world; ++q)
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[q] + rank), "l"(step) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flags[q] + rank), "l"(step) : "memory");
 }
+// "started" releases nothing (it says that kernels which ended before this one no longer read the ring): no fence
 __device__ __forceinline__ void peer_gather_publish_started(int world, int rank, unsigned long long* const* flags,
                                                             unsigned long long step) {
   for (int q = 0; q < world; ++q)
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[q] + world + rank), "l"(step) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flags[q] + world + rank), "l"(step) : "memory");
 }
 // one thread: spin until word `first + r` of my flag array is >= target for every rank r
 __device__ __forceinline__ void peer_gather_wait_all(int world, const unsigned long long* mine, int first,

@@ -593,6 +593,7 @@ apa_flow_contract_kernel(const FusedParams p) {
 __global__ void __launch_bounds__(kCThreads, 8)
 apa_flow_finish_kernel(const FusedParams p) {
   __shared__ float sS[kVideoTile * 4];
+  __shared__ float outS[kVideoTile * kKW];   // the finished [32 videos][32 classes] block
   __shared__ unsigned long long call_s[2];   // [0] call, [1] gather step
   const int R = p.R, K = p.K, F = p.F, NS = p.fl_NS;
   const int tid = threadIdx.x;
@@ -639,23 +640,28 @@ apa_flow_finish_kernel(const FusedParams p) {
       for (int c = 0; c < 8; ++c) { sum[0] += pv[c].x; sum[1] += pv[c].y; sum[2] += pv[c].z; sum[3] += pv[c].w; }
     }
     const int vi = o / kKW, kk0 = o % kKW;
-    const int v = v0 + vi;
-    if (v < Bv) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int kk = kk0 + m, k = k_lo + kk;
-        if (kk < width) {
-          float val = sum[m];
-          for (int j = 0; j < R; ++j) val = fmaf(__ldg(p.td_b[j] + k), sS[vi * 4 + j], val);
-          val *= p.inv_scale;
-          if (p.gw_world > 0) {
-            const size_t off = gw_off + (size_t(p.gw_rank) * Bv + size_t(v)) * K + k;
-            for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
-          } else {
-            p.logits[size_t(v) * K + k] = val;
-          }
-        }
-      }
+    for (int m = 0; m < 4; ++m) {
+      const int kk = kk0 + m;
+      float val = sum[m];
+      if (kk < width)
+        for (int j = 0; j < R; ++j) val = fmaf(__ldg(p.td_b[j] + k_lo + kk), sS[vi * 4 + j], val);
+      outS[o + m] = val * p.inv_scale;
+    }
+  }
+  __syncthreads();
+  // rows of `width` consecutive floats: consecutive lanes store consecutive addresses (whole sectors, which matters
+  // most for the peer stores: NVLink delivers partial-sector writes as read-modify-writes on the receiving GPU)
+  const int nvid = min(kVideoTile, Bv - v0);
+  for (int idx = tid; idx < nvid * width; idx += kCThreads) {
+    const int vi = idx / width, kk = idx - vi * width;
+    const float val = outS[vi * kKW + kk];
+    const size_t row = size_t(v0 + vi) * K + k_lo + kk;
+    if (p.gw_world > 0) {
+      const size_t off = gw_off + size_t(p.gw_rank) * Bv * K + row;
+      for (int qq = 0; qq < p.gw_world; ++qq) p.gw_logits[qq][off] = val;
+    } else {
+      p.logits[row] = val;
     }
   }
   if (p.gw_world > 1) __threadfence_system();  // my peer stores are visible system-wide before I am counted

@@ -323,7 +323,7 @@ def main():
     # stream side by side on disjoint SMs while the others are in their tails); big batches keep one CTA per SM
     stream_ctas = args.stream_ctas if args.stream_ctas >= 0 else (37 if (B <= 64 and nstreams >= 4) else 0)
     is_gram = cfg["kind"] == "gram"
-    lag = max(0, min(args.gather_lag, args.gather_depth - 1))
+    lag = -1 if args.gather_lag < 0 else min(args.gather_lag, args.gather_depth - 1)   # -1: one wait at the end only
 
     # ring of inputs > 2x L2 so that every step streams X from HBM
     nbuf = max(2, -(-2 * L2_BYTES // x_bytes) + 1)
@@ -399,7 +399,7 @@ def main():
             ln = cur if i % nstreams == 0 else lanes[i % nstreams]
             with torch.cuda.stream(ln):
                 step(i, with_collective)
-        if peer_l is not None and with_collective and lag > 0:   # the last steps' gathered buffers are complete too
+        if peer_l is not None and with_collective and lag != 0:   # the last steps' gathered buffers are complete too
             for j, ln in enumerate([cur] + lanes[1:]):
                 with torch.cuda.stream(ln):
                     peer_l[j].wait(0)

@@ -8,7 +8,7 @@ port=29530
 for args in "" "--collective nccl"; do
   tag=$(echo "$args" | tr -d ' ')
   port=$((port+1))
-  ( timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 1001 --warmup 10 --cpu-seconds 1 --e2e-steps 3 $args ) > gpurun_out/bench_${N}gpu_$tag.log 2>&1
+  ( timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 1000 --warmup 20 --cpu-seconds 1 --e2e-steps 3 --no-latency $args ) > gpurun_out/bench_${N}gpu_$tag.log 2>&1
   echo "${N}gpu [$args] rc=$? : $(grep '^{' gpurun_out/bench_${N}gpu_$tag.log | tail -1 | python -c "
 import sys,json
 try:

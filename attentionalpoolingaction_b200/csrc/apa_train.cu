@@ -1,0 +1,690 @@
+// apa_train.cu — the head in TRAINING mode: forward with slim.dropout on the top-down branch and the backward.
+//
+// Reference sites: nets_factory.py:143-146 (dropout arg-scope: keep_prob 0.2 when cfg.NET.DROPOUT < 0, config.py:231),
+// :296 (`slim.dropout(last_conv)` feeds the top-down convs only; the attention convs read the un-dropped map),
+// :259-286 (attention convs, softmax / relu), :299-328 (top-down convs, multiply, spatial mean, rank sum), :354-374
+// (frame mean); the callers are train.py:399-420 (clone_fn builds the graph with is_training=True) and :509-513
+// (optimizer.compute_gradients differentiates it).  TF differentiates the graph automatically, so there is no
+// reference source for the backward; the algebra is the re-associated closed form stated and tested on the CPU in
+// oracle/attn_pool_backward.py (backward_reassociated), for the single-map (PER_CLASS off), SINGLE_LAYER_ATT head:
+//
+//   Xd = X * mask                     (mask = 0 or 1/keep; a counter-based hash of (seed, element index))
+//   a_0 = X.w_0 + c_0;  a_r = w_r a_{r-1} + c_r;  A_r = act(a_r)                       [batch, HW]
+//   g_r[v] = sum_{frames, hw} A_r Xd      s_r[v] = sum A_r                             [videos, C], [videos]
+//   logits[v] = (sum_r g_r.B_r + d_r s_r) / (HW F)
+//   G[v] = dlogits[v] / (HW F);   u_r[v] = B_r G[v];   t_r[v] = d_r.G[v]
+//   dA_r[b,hw] = Xd[b,hw].u_r[v] + t_r[v]          (pass 1 over X)
+//   delta_r    = chain / relu / softmax backward of dA_r                               (per image, tiny)
+//   dX[b,hw]   = mask * sum_r A_r u_r[v] + delta_0 w_0;   dw_0 = sum delta_0 X         (pass 2 over X, dX written)
+//   dB_r = g_r^T G;  dd_r = s_r^T G;  dc_r = sum delta_r;  dw_r = sum delta_r a_{r-1}  (r >= 1)
+//
+// Memory traffic: forward 2 x |X| (attention values, then the masked pooling), backward 2 x |X| read + |X| written;
+// the [HW, K] top-down maps never exist.  All kernels are plain grids (no counters, no PDL): every per-call buffer is
+// fully written before it is read in stream order, all reductions have a fixed order (bit-reproducible).
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "../../include/apa.h"
+#include "apa_common.cuh"
+#include "apa_kernels.h"
+
+namespace apa {
+namespace {
+
+constexpr int kRowsPerChunk = 28;   // rows of one image per CTA in the passes over X (196 = 7 chunks)
+constexpr int kPoolThreads = 512;   // one float4 of channels per thread: 2048 channels per sweep
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+struct Drop {
+  uint64_t key;     // splitmix64(seed)
+  uint32_t thr;     // keep iff 16-bit lane < thr;  thr = round(keep * 65536)
+  float scale;      // 1 / keep
+  int on;           // 0: keep == 1, no hashing at all
+};
+
+// mask of the four consecutive elements 4*g4 .. 4*g4+3 of X (row-major [batch, hw, channels], channels % 4 == 0)
+__device__ __forceinline__ float4 drop_mask4(const Drop& d, uint64_t g4) {
+  const uint64_t h = splitmix64(d.key + g4);
+  float4 m;
+  m.x = (uint32_t(h) & 0xFFFFu) < d.thr ? d.scale : 0.f;
+  m.y = (uint32_t(h >> 16) & 0xFFFFu) < d.thr ? d.scale : 0.f;
+  m.z = (uint32_t(h >> 32) & 0xFFFFu) < d.thr ? d.scale : 0.f;
+  m.w = (uint32_t(h >> 48) & 0xFFFFu) < d.thr ? d.scale : 0.f;
+  return m;
+}
+
+struct TrainParams {
+  const float* X;
+  int N, HW, C, K, F, R, mode, J;   // N images = videos * F;  J row chunks per image
+  const float* aw[APA_MAX_RANK];    // aw[0]: [C];  aw[r >= 1]: scalar
+  const float* ab[APA_MAX_RANK];    // scalars
+  const float* tw[APA_MAX_RANK];    // [C, K]
+  const float* tb[APA_MAX_RANK];    // [K]
+  Drop drop;
+  // saved by the forward for the backward
+  float* a0;     // [N, HW]
+  float* gv;     // [videos, R, C]
+  float* sv;     // [videos, R]
+  // forward scratch
+  float* gpart;  // [N, J, R, C]
+  float* spart;  // [N, J, R]
+  float* logits; // [videos, K]
+  // backward
+  const float* dlogits;  // [videos, K]
+  float* u;      // [videos, R, C]
+  float* tt;     // [videos, R]
+  float* dA;     // [N, R, HW]
+  float* dw0part;// [N, J, C]
+  float* pch;    // [N, 2, R]: sum delta_r, sum delta_r a_{r-1}
+  float* dX;     // [N, HW, C] or nullptr
+  float* d_aw[APA_MAX_RANK];
+  float* d_ab[APA_MAX_RANK];
+  float* d_tw[APA_MAX_RANK];
+  float* d_tb[APA_MAX_RANK];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// fixed-order block reductions (every thread gets the result); `red` holds 32 floats
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = red[0];
+  for (int i = 1; i < nw; ++i) t = fmaxf(t, red[i]);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// a_0[row] = X[row].w_0 + c_0 (un-dropped features, nets_factory.py:259-270): one warp per row.
+__global__ void __launch_bounds__(256) train_attn_kernel(TrainParams p) {
+  extern __shared__ float4 w0s[];
+  const int C4 = p.C >> 2;
+  for (int i = threadIdx.x; i < C4; i += blockDim.x) w0s[i] = __ldg(reinterpret_cast<const float4*>(p.aw[0]) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float c0 = __ldg(p.ab[0]);
+  const long rows = long(p.N) * p.HW;
+  for (long row = long(blockIdx.x) * 8 + warp; row < rows; row += long(gridDim.x) * 8) {
+    const float4* x = reinterpret_cast<const float4*>(p.X) + row * C4;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+      const float4 v = __ldg(x + c4), w = w0s[c4];
+      acc += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) p.a0[row] = acc + c0;
+  }
+}
+
+// The attention values of image b for every rank, into shared memory (A[r * HW + hw]); softmax over HW when asked.
+// Optionally also the pre-activation chain values (araw, may be nullptr).
+__device__ __forceinline__ void image_attention(const TrainParams& p, int b, float* A, float* araw, float* red) {
+  const int HW = p.HW, R = p.R;
+  float wr[APA_MAX_RANK], cr[APA_MAX_RANK];
+  for (int r = 1; r < R; ++r) { wr[r] = __ldg(p.aw[r]); cr[r] = __ldg(p.ab[r]); }
+  for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) {
+    float a = p.a0[size_t(b) * HW + hw];
+    for (int r = 0; r < R; ++r) {
+      if (r > 0) a = wr[r] * a + cr[r];
+      if (araw) araw[r * HW + hw] = a;
+      A[r * HW + hw] = (p.mode == MODE_RELU) ? fmaxf(a, 0.f) : a;
+    }
+  }
+  __syncthreads();
+  if (p.mode == MODE_SOFTMAX) {   // R == 1 (checked on the host)
+    float mx = -INFINITY;
+    for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) mx = fmaxf(mx, A[hw]);
+    mx = block_max(mx, red);
+    float s = 0.f;
+    for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) { const float e = __expf(A[hw] - mx); A[hw] = e; s += e; }
+    s = block_sum(s, red);
+    const float inv = 1.f / s;
+    for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) A[hw] *= inv;
+    __syncthreads();
+  }
+}
+
+// partial g_r of (image b, row chunk j): sum over the chunk's rows of A_r[hw] * mask * X[b, hw, :]
+__global__ void __launch_bounds__(kPoolThreads) train_pool_kernel(TrainParams p) {
+  extern __shared__ float smem[];
+  float* A = smem;                       // [R * HW]
+  float* red = smem + p.R * p.HW;        // [32]
+  const int j = blockIdx.x, b = blockIdx.y, HW = p.HW, R = p.R, C4 = p.C >> 2;
+  image_attention(p, b, A, nullptr, red);
+  const int h0 = j * kRowsPerChunk, h1 = min(HW, h0 + kRowsPerChunk);
+  const float4* Xb = reinterpret_cast<const float4*>(p.X) + size_t(b) * HW * C4;
+  const uint64_t g4b = uint64_t(b) * HW * C4;
+  for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+    float4 acc[APA_MAX_RANK];
+#pragma unroll
+    for (int r = 0; r < APA_MAX_RANK; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int hw = h0; hw < h1; ++hw) {
+      float4 x = __ldg(Xb + size_t(hw) * C4 + c4);
+      if (p.drop.on) {
+        const float4 m = drop_mask4(p.drop, g4b + uint64_t(hw) * C4 + c4);
+        x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+      }
+#pragma unroll
+      for (int r = 0; r < APA_MAX_RANK; ++r)
+        if (r < R) {
+          const float a = A[r * HW + hw];
+          acc[r].x += a * x.x; acc[r].y += a * x.y; acc[r].z += a * x.z; acc[r].w += a * x.w;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < APA_MAX_RANK; ++r)
+      if (r < R)
+        reinterpret_cast<float4*>(p.gpart)[((size_t(b) * p.J + j) * R + r) * C4 + c4] = acc[r];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < R) {
+    float s = 0.f;
+    for (int hw = h0 + lane; hw < h1; hw += 32) s += A[warp * HW + hw];
+    s = warp_sum(s);
+    if (lane == 0) p.spart[(size_t(b) * p.J + j) * R + warp] = s;
+  }
+}
+
+// g_r[v] = sum over the video's frames and row chunks (fixed order); s_r[v] likewise
+__global__ void __launch_bounds__(256) train_reduce_kernel(TrainParams p) {
+  const int v = blockIdx.y, RC4 = p.R * (p.C >> 2);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int parts = p.F * p.J;
+  if (i < RC4) {
+    const float4* src = reinterpret_cast<const float4*>(p.gpart) + size_t(v) * parts * RC4 + i;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < parts; ++q) {
+      const float4 t = src[size_t(q) * RC4];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    reinterpret_cast<float4*>(p.gv)[size_t(v) * RC4 + i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < p.R) {
+    float s = 0.f;
+    for (int q = 0; q < parts; ++q) s += p.spart[(size_t(v) * parts + q) * p.R + threadIdx.x];
+    p.sv[size_t(v) * p.R + threadIdx.x] = s;
+  }
+}
+
+// logits[v, k] = (sum_r g_r[v].B_r[:, k] + d_r[k] s_r[v]) / (HW F): 8 videos x 32 classes per CTA, one channel
+// slice per warp, the slices summed in warp order
+__global__ void __launch_bounds__(256) train_logits_kernel(TrainParams p) {
+  __shared__ float red[8][8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane, v0 = blockIdx.y * 8, V = p.N / p.F, C = p.C, K = p.K, R = p.R;
+  const int cs = (C + 7) / 8, clo = warp * cs, chi = min(C, clo + cs);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int kk = min(k, K - 1);
+  for (int r = 0; r < R; ++r) {
+    const float* tw = p.tw[r];
+    for (int c = clo; c < chi; ++c) {
+      const float w = __ldg(tw + size_t(c) * K + kk);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int v = min(v0 + i, V - 1);
+        acc[i] += p.gv[(size_t(v) * R + r) * C + c] * w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][i][lane] = acc[i];
+  __syncthreads();
+  const int v = v0 + warp;   // warp i finishes video i of the tile
+  if (v < V && k < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][warp][lane];
+    for (int r = 0; r < R; ++r) t += __ldg(p.tb[r] + k) * p.sv[size_t(v) * R + r];
+    p.logits[size_t(v) * K + k] = t / (float(p.HW) * float(p.F));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// u_r[v, c] = B_r[c, :].G[v],  t_r[v] = d_r.G[v]  with G = dlogits / (HW F): warp per channel, 8 videos per CTA
+__global__ void __launch_bounds__(256) bwd_u_kernel(TrainParams p) {
+  extern __shared__ float Gs[];   // [8][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.z, v0 = blockIdx.y * 8, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
+  const float scale = 1.f / (float(p.HW) * float(p.F));
+  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+    const int v = v0 + i / K;
+    Gs[i] = (v < V) ? p.dlogits[size_t(v) * K + (i % K)] * scale : 0.f;
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 8 + warp;
+  if (c < C) {
+    const float* tw = p.tw[r] + size_t(c) * K;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float w = __ldg(tw + k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += Gs[i * K + k] * w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = warp_sum(acc[i]);
+      if (lane == 0 && v0 + i < V) p.u[(size_t(v0 + i) * R + r) * C + c] = t;
+    }
+  }
+  if (blockIdx.x == 0 && v0 + warp < V) {
+    float t = 0.f;
+    for (int k = lane; k < K; k += 32) t += Gs[warp * K + k] * __ldg(p.tb[r] + k);
+    t = warp_sum(t);
+    if (lane == 0) p.tt[size_t(v0 + warp) * R + r] = t;
+  }
+}
+
+// pass 1 over X: dA_r[b, hw] = (mask * X[b, hw]).u_r[v] + t_r[v]; warp per row, u_r[v] in shared memory
+__global__ void __launch_bounds__(256) bwd_dattn_kernel(TrainParams p) {
+  extern __shared__ float4 us[];   // [R][C/4]
+  const int j = blockIdx.x, b = blockIdx.y, v = b / p.F, HW = p.HW, R = p.R, C4 = p.C >> 2;
+  for (int i = threadIdx.x; i < R * C4; i += blockDim.x)
+    us[i] = reinterpret_cast<const float4*>(p.u)[size_t(v) * R * C4 + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h0 = j * kRowsPerChunk, h1 = min(HW, h0 + kRowsPerChunk);
+  const float4* Xb = reinterpret_cast<const float4*>(p.X) + size_t(b) * HW * C4;
+  const uint64_t g4b = uint64_t(b) * HW * C4;
+  for (int hw = h0 + warp; hw < h1; hw += 8) {
+    float acc[APA_MAX_RANK];
+#pragma unroll
+    for (int r = 0; r < APA_MAX_RANK; ++r) acc[r] = 0.f;
+#pragma unroll 4
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+      float4 x = __ldg(Xb + size_t(hw) * C4 + c4);
+      if (p.drop.on) {
+        const float4 m = drop_mask4(p.drop, g4b + uint64_t(hw) * C4 + c4);
+        x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+      }
+#pragma unroll
+      for (int r = 0; r < APA_MAX_RANK; ++r)
+        if (r < R) {
+          const float4 w = us[r * C4 + c4];
+          acc[r] += x.x * w.x + x.y * w.y + x.z * w.z + x.w * w.w;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < APA_MAX_RANK; ++r)
+      if (r < R) {
+        const float t = warp_sum(acc[r]);
+        if (lane == 0) p.dA[(size_t(b) * R + r) * HW + hw] = t + p.tt[size_t(v) * R + r];
+      }
+  }
+}
+
+// pass 2 over X: per image the chain / relu / softmax backward (tiny, recomputed by each of the image's CTAs), then
+//   dX[b, hw, :] = mask * sum_r A_r[hw] u_r[v] + delta_0[hw] w_0      and the CTA's part of dw_0 = sum delta_0 X
+__global__ void __launch_bounds__(kPoolThreads) bwd_dx_kernel(TrainParams p) {
+  extern __shared__ float smem[];
+  const int HW = p.HW, R = p.R, C4 = p.C >> 2;
+  float* A = smem;                 // [R * HW]
+  float* araw = A + R * HW;        // [R * HW]
+  float* d0 = araw + R * HW;       // [HW]
+  float* red = d0 + HW;            // [32]
+  const int j = blockIdx.x, b = blockIdx.y, v = b / p.F;
+  image_attention(p, b, A, araw, red);
+  float wr[APA_MAX_RANK];
+  for (int r = 1; r < R; ++r) wr[r] = __ldg(p.aw[r]);
+  float sAd = 0.f;
+  if (p.mode == MODE_SOFTMAX) {
+    float t = 0.f;
+    for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) t += A[hw] * p.dA[size_t(b) * HW + hw];
+    sAd = block_sum(t, red);
+  }
+  float sd[APA_MAX_RANK], sda[APA_MAX_RANK];
+#pragma unroll
+  for (int r = 0; r < APA_MAX_RANK; ++r) sd[r] = sda[r] = 0.f;
+  for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) {
+    float da[APA_MAX_RANK];
+#pragma unroll
+    for (int r = 0; r < APA_MAX_RANK; ++r)
+      if (r < R) {
+        float d = p.dA[(size_t(b) * R + r) * HW + hw];
+        if (p.mode == MODE_RELU) d = araw[r * HW + hw] > 0.f ? d : 0.f;
+        if (p.mode == MODE_SOFTMAX) d = A[hw] * (d - sAd);
+        da[r] = d;
+      }
+    float delta = 0.f;
+#pragma unroll
+    for (int r = APA_MAX_RANK - 1; r >= 0; --r)
+      if (r < R) {
+        delta = da[r] + ((r + 1 < R) ? wr[(r + 1) & (APA_MAX_RANK - 1)] * delta : 0.f);
+        sd[r] += delta;
+        if (r > 0) sda[r] += delta * araw[(r - 1) * HW + hw];
+      }
+    d0[hw] = delta;
+  }
+  // the image's sums for dc_r and dw_r (r >= 1); chunk 0 writes them
+  for (int r = 0; r < R; ++r) {
+    const float s1 = block_sum(sd[r], red);
+    const float s2 = (r > 0) ? block_sum(sda[r], red) : 0.f;
+    if (j == 0 && threadIdx.x == 0) {
+      p.pch[(size_t(b) * 2 + 0) * R + r] = s1;
+      p.pch[(size_t(b) * 2 + 1) * R + r] = s2;
+    }
+  }
+  __syncthreads();
+  const int h0 = j * kRowsPerChunk, h1 = min(HW, h0 + kRowsPerChunk);
+  const float4* Xb = reinterpret_cast<const float4*>(p.X) + size_t(b) * HW * C4;
+  float4* dXb = p.dX ? reinterpret_cast<float4*>(p.dX) + size_t(b) * HW * C4 : nullptr;
+  const uint64_t g4b = uint64_t(b) * HW * C4;
+  for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+    float4 u4[APA_MAX_RANK];
+#pragma unroll
+    for (int r = 0; r < APA_MAX_RANK; ++r)
+      if (r < R) u4[r] = reinterpret_cast<const float4*>(p.u)[(size_t(v) * R + r) * C4 + c4];
+    const float4 w04 = __ldg(reinterpret_cast<const float4*>(p.aw[0]) + c4);
+    float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int hw = h0; hw < h1; ++hw) {
+      const float4 x = __ldg(Xb + size_t(hw) * C4 + c4);
+      const float d = d0[hw];
+      dw.x += d * x.x; dw.y += d * x.y; dw.z += d * x.z; dw.w += d * x.w;
+      if (dXb) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < APA_MAX_RANK; ++r)
+          if (r < R) {
+            const float a = A[r * HW + hw];
+            t.x += a * u4[r].x; t.y += a * u4[r].y; t.z += a * u4[r].z; t.w += a * u4[r].w;
+          }
+        if (p.drop.on) {
+          const float4 m = drop_mask4(p.drop, g4b + uint64_t(hw) * C4 + c4);
+          t.x *= m.x; t.y *= m.y; t.z *= m.z; t.w *= m.w;
+        }
+        t.x += d * w04.x; t.y += d * w04.y; t.z += d * w04.z; t.w += d * w04.w;
+        __stcs(dXb + size_t(hw) * C4 + c4, t);
+      }
+    }
+    reinterpret_cast<float4*>(p.dw0part)[(size_t(b) * p.J + j) * C4 + c4] = dw;
+  }
+}
+
+// dB_r[c, k] = sum_v g_r[v, c] G[v, k];  dd_r[k] = sum_v s_r[v] G[v, k]: warp per channel
+__global__ void __launch_bounds__(256) bwd_wgrad_kernel(TrainParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.y, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
+  const float scale = 1.f / (float(p.HW) * float(p.F));
+  const int c = blockIdx.x * 8 + warp;
+  if (c < C) {
+    for (int k0 = 0; k0 < K; k0 += 128) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int v = 0; v < V; ++v) {
+        const float g = p.gv[(size_t(v) * R + r) * C + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = k0 + i * 32 + lane;
+          acc[i] += g * (k < K ? __ldg(p.dlogits + size_t(v) * K + k) : 0.f);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + i * 32 + lane;
+        if (k < K) p.d_tw[r][size_t(c) * K + k] = acc[i] * scale;
+      }
+    }
+  }
+  if (blockIdx.x == 0)
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float t = 0.f;
+      for (int v = 0; v < V; ++v) t += p.sv[size_t(v) * R + r] * __ldg(p.dlogits + size_t(v) * K + k);
+      p.d_tb[r][k] = t * scale;
+    }
+}
+
+// dw_0[c] = sum of the CTAs' parts (fixed order); dc_r, dw_r (r >= 1) = sums over the images
+__global__ void __launch_bounds__(256) bwd_finish_kernel(TrainParams p) {
+  const int C4 = p.C >> 2, parts = p.N * p.J;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = reinterpret_cast<const float4*>(p.dw0part) + i;
+#pragma unroll 8
+    for (int q = 0; q < parts; ++q) {
+      const float4 t = src[size_t(q) * C4];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    reinterpret_cast<float4*>(p.d_aw[0])[i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 2 * p.R) {
+    const int which = threadIdx.x / p.R, r = threadIdx.x % p.R;
+    float t = 0.f;
+    for (int b = 0; b < p.N; ++b) t += p.pch[(size_t(b) * 2 + which) * p.R + r];
+    if (which == 0) p.d_ab[r][0] = t;
+    else if (r > 0) p.d_aw[r][0] = t;
+  }
+}
+
+__global__ void dropout_mask_kernel(Drop d, float* out, size_t n4) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (d.on) m = drop_mask4(d, i);
+    reinterpret_cast<float4*>(out)[i] = m;
+  }
+}
+
+inline size_t al(size_t n) { return (n + 63) & ~size_t(63); }   // floats, 256-byte granules
+
+Drop make_drop(const ApaTrain* t) {
+  Drop d;
+  const float keep = t ? t->dropout_keep : 1.f;
+  d.on = keep < 1.f;
+  d.key = splitmix64(t ? t->dropout_seed : 0ull);
+  double th = double(keep) * 65536.0 + 0.5;
+  d.thr = th < 0 ? 0u : (th > 65536.0 ? 65536u : uint32_t(th));
+  d.scale = 1.f / keep;
+  return d;
+}
+
+int train_supported(const ApaDesc* d) {
+  int st = apa_attn_pool_check(d);
+  if (st != APA_OK) return st;
+  if ((d->flags & APA_FLAG_PER_CLASS) || !(d->flags & APA_FLAG_SINGLE_LAYER_ATT)) return APA_ERR_UNSUPPORTED;
+  if (size_t(d->rank) * d->hw * 2 + d->hw + 64 > 40000) return APA_ERR_SHAPE;   // per-image attention lives in smem
+  if (size_t(d->rank) * d->channels * 4 > 200 * 1024 || size_t(d->num_classes) * 32 > 200 * 1024) return APA_ERR_SHAPE;
+  return APA_OK;
+}
+
+struct Carve {
+  size_t a0, gv, sv, saved_total;                       // saved
+  size_t gpart, spart, u, tt, dA, dw0part, pch, ws_total;   // workspace (floats)
+};
+Carve carve(const ApaDesc* d) {
+  Carve c;
+  const size_t N = d->batch, V = d->batch / d->frames, R = d->rank, C = d->channels, HW = d->hw;
+  const size_t J = (HW + kRowsPerChunk - 1) / kRowsPerChunk;
+  size_t o = 0;
+  c.a0 = o; o += al(N * HW);
+  c.gv = o; o += al(V * R * C);
+  c.sv = o; o += al(V * R);
+  c.saved_total = o;
+  o = 0;
+  c.gpart = o; o += al(N * J * R * C);
+  c.spart = o; o += al(N * J * R);
+  c.u = o; o += al(V * R * C);
+  c.tt = o; o += al(V * R);
+  c.dA = o; o += al(N * R * HW);
+  c.dw0part = o; o += al(N * J * C);
+  c.pch = o; o += al(N * 2 * R);
+  c.ws_total = o;
+  return c;
+}
+
+int fill(TrainParams& p, const ApaDesc* d, const ApaWeights* w, const ApaTrain* t, const float* X, float* saved,
+         float* ws) {
+  const Carve c = carve(d);
+  p.X = X;
+  p.N = d->batch; p.HW = d->hw; p.C = d->channels; p.K = d->num_classes; p.F = d->frames; p.R = d->rank;
+  p.mode = (d->flags & APA_FLAG_SOFTMAX_ATT) ? MODE_SOFTMAX : ((d->flags & APA_FLAG_RELU_ATT) ? MODE_RELU : MODE_PLAIN);
+  p.J = (d->hw + kRowsPerChunk - 1) / kRowsPerChunk;
+  for (int r = 0; r < d->rank; ++r) {
+    if (!w->attn_w[r] || !w->attn_b[r] || !w->topdown_w[r] || !w->topdown_b[r]) return APA_ERR_NULL;
+    p.aw[r] = w->attn_w[r]; p.ab[r] = w->attn_b[r]; p.tw[r] = w->topdown_w[r]; p.tb[r] = w->topdown_b[r];
+  }
+  if ((reinterpret_cast<uintptr_t>(X) & 15u) || (reinterpret_cast<uintptr_t>(w->attn_w[0]) & 15u)) return APA_ERR_ALIGN;
+  p.drop = make_drop(t);
+  p.a0 = saved + c.a0; p.gv = saved + c.gv; p.sv = saved + c.sv;
+  p.gpart = ws + c.gpart; p.spart = ws + c.spart; p.u = ws + c.u; p.tt = ws + c.tt; p.dA = ws + c.dA;
+  p.dw0part = ws + c.dw0part; p.pch = ws + c.pch;
+  return APA_OK;
+}
+
+#define APA_CUDA(expr)                       \
+  do {                                       \
+    cudaError_t e__ = (expr);                \
+    if (e__ != cudaSuccess) return int(e__); \
+  } while (0)
+
+template <typename Kern>
+cudaError_t big_smem(Kern k, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+}
+
+int check_train(const ApaTrain* t) {
+  if (t == nullptr) return APA_OK;
+  if (!(t->dropout_keep > 0.f) || t->dropout_keep > 1.f || t->reserved0 != 0) return APA_ERR_UNSUPPORTED;
+  return APA_OK;
+}
+
+}  // namespace
+}  // namespace apa
+
+using namespace apa;
+
+extern "C" {
+
+size_t apa_attn_pool_train_saved_bytes(const ApaDesc* desc) {
+  if (train_supported(desc) != APA_OK) return 0;
+  return carve(desc).saved_total * sizeof(float);
+}
+
+size_t apa_attn_pool_train_workspace(const ApaDesc* desc) {
+  if (train_supported(desc) != APA_OK) return 0;
+  return carve(desc).ws_total * sizeof(float);
+}
+
+int apa_attn_pool_fwd_train(const ApaDesc* desc, const float* X, const ApaWeights* weights, const ApaTrain* train,
+                            float* logits, void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                            void* stream_) {
+  int st = train_supported(desc);
+  if (st != APA_OK) return st;
+  if ((st = check_train(train)) != APA_OK) return st;
+  if (!X || !weights || !logits || !saved || !workspace) return APA_ERR_NULL;
+  const Carve c = carve(desc);
+  if (saved_bytes < c.saved_total * 4 || workspace_bytes < c.ws_total * 4) return APA_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(saved) & 255u) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APA_ERR_WORKSPACE;
+  TrainParams p{};
+  if ((st = fill(p, desc, weights, train, X, static_cast<float*>(saved), static_cast<float*>(workspace))) != APA_OK) return st;
+  p.logits = logits;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long rows = long(p.N) * p.HW;
+  const int V = p.N / p.F;
+  {
+    const int grid = int(std::min<long>((rows + 7) / 8, 148 * 8));
+    train_attn_kernel<<<grid, 256, size_t(p.C) * 4, stream>>>(p);
+  }
+  {
+    const size_t smem = (size_t(p.R) * p.HW + 32) * 4;
+    APA_CUDA(big_smem(train_pool_kernel, smem));
+    train_pool_kernel<<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+  }
+  train_reduce_kernel<<<dim3((p.R * (p.C / 4) + 255) / 256, V), 256, 0, stream>>>(p);
+  train_logits_kernel<<<dim3((p.K + 31) / 32, (V + 7) / 8), 256, 0, stream>>>(p);
+  APA_CUDA(cudaGetLastError());
+  return APA_OK;
+}
+
+int apa_attn_pool_bwd(const ApaDesc* desc, const float* X, const ApaWeights* weights, const ApaTrain* train,
+                      const float* dlogits, const void* saved, size_t saved_bytes, const ApaGrads* grads,
+                      void* workspace, size_t workspace_bytes, void* stream_) {
+  int st = train_supported(desc);
+  if (st != APA_OK) return st;
+  if ((st = check_train(train)) != APA_OK) return st;
+  if (!X || !weights || !dlogits || !saved || !grads || !workspace) return APA_ERR_NULL;
+  const Carve c = carve(desc);
+  if (saved_bytes < c.saved_total * 4 || workspace_bytes < c.ws_total * 4) return APA_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(saved) & 255u) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APA_ERR_WORKSPACE;
+  TrainParams p{};
+  if ((st = fill(p, desc, weights, train, X, const_cast<float*>(static_cast<const float*>(saved)),
+                 static_cast<float*>(workspace))) != APA_OK) return st;
+  p.dlogits = dlogits;
+  p.dX = grads->dX;
+  if (p.dX && (reinterpret_cast<uintptr_t>(p.dX) & 15u)) return APA_ERR_ALIGN;
+  for (int r = 0; r < p.R; ++r) {
+    if (!grads->attn_w[r] || !grads->attn_b[r] || !grads->topdown_w[r] || !grads->topdown_b[r]) return APA_ERR_NULL;
+    p.d_aw[r] = grads->attn_w[r]; p.d_ab[r] = grads->attn_b[r]; p.d_tw[r] = grads->topdown_w[r]; p.d_tb[r] = grads->topdown_b[r];
+  }
+  if (reinterpret_cast<uintptr_t>(p.d_aw[0]) & 15u) return APA_ERR_ALIGN;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int V = p.N / p.F;
+  {
+    const size_t smem = size_t(8) * p.K * 4;
+    APA_CUDA(big_smem(bwd_u_kernel, smem));
+    bwd_u_kernel<<<dim3((p.C + 7) / 8, (V + 7) / 8, p.R), 256, smem, stream>>>(p);
+  }
+  {
+    const size_t smem = size_t(p.R) * p.C * 4;
+    APA_CUDA(big_smem(bwd_dattn_kernel, smem));
+    bwd_dattn_kernel<<<dim3(p.J, p.N), 256, smem, stream>>>(p);
+  }
+  {
+    const size_t smem = (size_t(2) * p.R * p.HW + p.HW + 32) * 4;
+    APA_CUDA(big_smem(bwd_dx_kernel, smem));
+    bwd_dx_kernel<<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+  }
+  bwd_wgrad_kernel<<<dim3((p.C + 7) / 8, p.R), 256, 0, stream>>>(p);
+  bwd_finish_kernel<<<(p.C / 4 + 255) / 256, 256, 0, stream>>>(p);
+  APA_CUDA(cudaGetLastError());
+  return APA_OK;
+}
+
+int apa_dropout_mask(const ApaTrain* train, size_t count, float* mask, void* stream) {
+  int st = check_train(train);
+  if (st != APA_OK) return st;
+  if (!mask) return APA_ERR_NULL;
+  if (count % 4 != 0) return APA_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(mask) & 15u) return APA_ERR_ALIGN;
+  const size_t n4 = count / 4;
+  if (n4 == 0) return APA_OK;
+  dropout_mask_kernel<<<unsigned((n4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(make_drop(train), mask, n4);
+  APA_CUDA(cudaGetLastError());
+  return APA_OK;
+}
+
+}  // extern "C"

@@ -48,6 +48,11 @@ ABI_SYMBOLS = (
     "apa_attn_pool_fwd_host",
     "apa_attn_pool_fwd_gather",
     "apa_peer_gather_wait",
+    "apa_attn_pool_train_saved_bytes",
+    "apa_attn_pool_train_workspace",
+    "apa_attn_pool_fwd_train",
+    "apa_attn_pool_bwd",
+    "apa_dropout_mask",
     "apa_gram_fwd",
     "apa_attn_pool_plan",
 )
@@ -122,6 +127,24 @@ class ApaPeerGather(ctypes.Structure):
     ]
 
 
+class ApaTrain(ctypes.Structure):
+    _fields_ = [
+        ("dropout_keep", ctypes.c_float),
+        ("reserved0", ctypes.c_int32),
+        ("dropout_seed", ctypes.c_uint64),
+    ]
+
+
+class ApaGrads(ctypes.Structure):
+    _fields_ = [
+        ("dX", ctypes.c_void_p),
+        ("attn_w", ctypes.c_void_p * APA_MAX_RANK),
+        ("attn_b", ctypes.c_void_p * APA_MAX_RANK),
+        ("topdown_w", ctypes.c_void_p * APA_MAX_RANK),
+        ("topdown_b", ctypes.c_void_p * APA_MAX_RANK),
+    ]
+
+
 class ApaError(RuntimeError):
     def __init__(self, status, where=""):
         self.status = int(status)
@@ -160,6 +183,19 @@ def _load():
                                              c.POINTER(ApaTuning), c.c_void_p]
     lib.apa_peer_gather_wait.restype = c.c_int
     lib.apa_peer_gather_wait.argtypes = [c.POINTER(ApaPeerGather), c.c_int32, c.c_void_p]
+    lib.apa_attn_pool_train_saved_bytes.restype = c.c_size_t
+    lib.apa_attn_pool_train_saved_bytes.argtypes = [c.POINTER(ApaDesc)]
+    lib.apa_attn_pool_train_workspace.restype = c.c_size_t
+    lib.apa_attn_pool_train_workspace.argtypes = [c.POINTER(ApaDesc)]
+    lib.apa_attn_pool_fwd_train.restype = c.c_int
+    lib.apa_attn_pool_fwd_train.argtypes = [c.POINTER(ApaDesc), c.c_void_p, c.POINTER(ApaWeights), c.POINTER(ApaTrain),
+                                            c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.apa_attn_pool_bwd.restype = c.c_int
+    lib.apa_attn_pool_bwd.argtypes = [c.POINTER(ApaDesc), c.c_void_p, c.POINTER(ApaWeights), c.POINTER(ApaTrain),
+                                      c.c_void_p, c.c_void_p, c.c_size_t, c.POINTER(ApaGrads), c.c_void_p,
+                                      c.c_size_t, c.c_void_p]
+    lib.apa_dropout_mask.restype = c.c_int
+    lib.apa_dropout_mask.argtypes = [c.POINTER(ApaTrain), c.c_size_t, c.c_void_p, c.c_void_p]
     lib.apa_gram_fwd.restype = c.c_int
     lib.apa_gram_fwd.argtypes = [c.c_int32, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.apa_attn_pool_plan.restype = c.c_int
@@ -429,6 +465,104 @@ class AttnPoolOp(object):
         if st != APA_OK:
             raise ApaError(st, "apa_attn_pool_fwd_host")
         return logits_host
+
+
+def make_train(dropout_keep=0.2, dropout_seed=0):
+    """ApaTrain: keep probability of slim.dropout(last_conv) (0.2 when cfg.NET.DROPOUT < 0, nets_factory.py:143-146)
+    and the seed of this step's mask."""
+    t = ApaTrain()
+    t.dropout_keep, t.dropout_seed = float(dropout_keep), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+    return t
+
+
+def dropout_mask(train, shape, device):
+    """The mask apa_attn_pool_fwd_train / _bwd apply to X of `shape` (0 or 1/keep), materialised."""
+    import torch
+    n = 1
+    for v in shape:
+        n *= int(v)
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    st = _lib.apa_dropout_mask(ctypes.byref(train), n, _ptr(out),
+                               ctypes.c_void_p(torch.cuda.current_stream(out.device).cuda_stream))
+    if st != APA_OK:
+        raise ApaError(st, "apa_dropout_mask")
+    return out
+
+
+class AttnPoolTrainOp(AttnPoolOp):
+    """The head in training mode (train.py:399-420 builds it with is_training=True; :509-513 differentiates it):
+    `forward(X, train)` -> logits and `backward(dlogits)` -> (dX, {TF variable name: gradient}).  Single-map head
+    that reads X directly (SINGLE_LAYER_ATT, not PER_CLASS); everything else raises ApaError(UNSUPPORTED)."""
+
+    def _train_buffers(self, batch):
+        key = ("train", int(batch))
+        hit = self._ws.get(key)
+        if hit is None:
+            torch = self._torch
+            d = self.desc(batch)
+            st = attn_pool_check(d)
+            if st != APA_OK:
+                raise ApaError(st, "apa_attn_pool_check")
+            nsaved, nws = int(_lib.apa_attn_pool_train_saved_bytes(ctypes.byref(d))), int(
+                _lib.apa_attn_pool_train_workspace(ctypes.byref(d)))
+            if nsaved == 0 or nws == 0:
+                raise ApaError(APA_ERR_UNSUPPORTED, "training mode")
+
+            def aligned(n):
+                raw = torch.empty(n + 256, dtype=torch.uint8, device=self.device)
+                off = (-raw.data_ptr()) % 256
+                return raw[off:off + n], raw
+            hit = (d, aligned(nsaved), aligned(nws))
+            self._ws[key] = hit
+        return hit
+
+    def forward(self, X, train=None, logits=None):
+        torch = self._torch
+        if X.dim() == 4:
+            X = X.reshape(X.shape[0], X.shape[1] * X.shape[2], X.shape[3])
+        X = X.contiguous()
+        d, (saved, _), (ws, _) = self._train_buffers(X.shape[0])
+        if logits is None:
+            logits = torch.empty((X.shape[0] // self.frames, self.num_classes), dtype=torch.float32, device=X.device)
+        st = _lib.apa_attn_pool_fwd_train(ctypes.byref(d), _ptr(X), ctypes.byref(self.weights),
+                                          ctypes.byref(train) if train is not None else None, _ptr(logits),
+                                          _ptr(saved), saved.numel(), _ptr(ws), ws.numel(),
+                                          ctypes.c_void_p(torch.cuda.current_stream(X.device).cuda_stream))
+        if st != APA_OK:
+            raise ApaError(st, "apa_attn_pool_fwd_train")
+        self._last = (X, train)
+        return logits
+
+    def backward(self, dlogits, want_dX=True, grads=None):
+        """Gradients of sum(logits * dlogits) for the last `forward` call.  Returns (dX or None, OrderedDict of
+        TF variable name -> gradient tensor shaped like the variable)."""
+        torch = self._torch
+        X, train = self._last
+        d, (saved, _), (ws, _) = self._train_buffers(X.shape[0])
+        dlogits = dlogits.contiguous()
+        C, K = self.channels, self.num_classes
+        if grads is None:
+            grads = OrderedDict()
+            for r in range(self.rank):
+                grads[attn_scope(r) + "/weights"] = torch.empty((C, 1) if r == 0 else (1, 1), device=X.device)
+                grads[attn_scope(r) + "/biases"] = torch.empty((1,), device=X.device)
+                grads[topdown_scope(r) + "/weights"] = torch.empty((C, K), device=X.device)
+                grads[topdown_scope(r) + "/biases"] = torch.empty((K,), device=X.device)
+        dX = torch.empty_like(X) if want_dX is True else (want_dX if torch.is_tensor(want_dX) else None)
+        g = ApaGrads()
+        g.dX = _ptr(dX).value if dX is not None else None
+        for r in range(self.rank):
+            g.attn_w[r] = _ptr(grads[attn_scope(r) + "/weights"]).value
+            g.attn_b[r] = _ptr(grads[attn_scope(r) + "/biases"]).value
+            g.topdown_w[r] = _ptr(grads[topdown_scope(r) + "/weights"]).value
+            g.topdown_b[r] = _ptr(grads[topdown_scope(r) + "/biases"]).value
+        st = _lib.apa_attn_pool_bwd(ctypes.byref(d), _ptr(X), ctypes.byref(self.weights),
+                                    ctypes.byref(train) if train is not None else None, _ptr(dlogits),
+                                    _ptr(saved), saved.numel(), ctypes.byref(g), _ptr(ws), ws.numel(),
+                                    ctypes.c_void_p(torch.cuda.current_stream(X.device).cuda_stream))
+        if st != APA_OK:
+            raise ApaError(st, "apa_attn_pool_bwd")
+        return dX, grads
 
 
 def peer_gather_wait(gather_struct, lag, stream):

@@ -42,12 +42,29 @@ def get_network_fn(name, num_classes, num_pose_keypoints, cfg, weight_decay=0.0,
         raise NotImplementedError("WITH_POSE_FEAT changes C to 2064 (nets_factory.py:289-295): out of scope")
     if getattr(net, "USE_TEMPORAL_ATT", False):
         raise NotImplementedError("USE_TEMPORAL_ATT (nets_factory.py:361-372) is out of scope")
-    if is_training:
-        raise NotImplementedError("forward/eval only: the training graph (dropout, backward) is a 'next' row")
     if params is None:
         raise ValueError("params (TF variable name -> array) is required: the head has trained variables")
     flags, rank = ops.flags_from_cfg_net(net)
     state = {}
+    if is_training:
+        # nets_factory.py:143-146: the dropout arg-scope of the head
+        drop = float(getattr(net, "DROPOUT", -1.0))
+        keep = 0.2 if drop < 0 else 1.0 - drop
+        counter = [0]
+
+        def network_fn(images, end_point_names=(), dropout_seed=None):
+            """Training graph (train.py:399-420): logits carry a grad_fn; `loss.backward()` fills `.grad` of X and
+            of every variable in `params` on the path (they must be float32 CUDA tensors with requires_grad)."""
+            if end_point_names:
+                raise NotImplementedError("end-points other than Logits are not materialised in training mode")
+            if dropout_seed is None:
+                counter[0] += 1
+                dropout_seed = counter[0]
+            logits = _run_head_train(state, images, params, flags, rank, num_classes, keep, dropout_seed)
+            return logits, {"Logits": logits}
+
+        network_fn.default_image_size = 224
+        return network_fn
 
     def network_fn(images, end_point_names=()):
         return _run_head(state, images, params, flags, rank, num_classes, num_pose_keypoints, end_point_names, tuning)
@@ -88,6 +105,48 @@ def _run_head(state, images, params, flags, rank, num_classes, num_pose_keypoint
     return logits, eps
 
 
+def _run_head_train(state, images, params, flags, rank, num_classes, keep, seed, frames_per_video=1):
+    """Training-mode call: one AttnPoolTrainOp per (HW, C, frames); autograd sees one node for the whole head."""
+    import torch
+    if images.dim() == 5:
+        frames_per_video = images.shape[1]
+        images = images.reshape((-1,) + tuple(images.shape[2:]))
+    X = images if images.dim() == 3 else images.reshape(images.shape[0], -1, images.shape[-1])
+    _, HW, C = X.shape
+    key = ("train", HW, C, frames_per_video)
+    op = state.get(key)
+    if op is None:
+        op = ops.AttnPoolTrainOp(params, num_classes, HW, channels=C, frames=frames_per_video, rank=rank,
+                                 flags=flags, device=X.device)
+        state[key] = op
+    names = []
+    for r in range(rank):
+        names += [ops.attn_scope(r) + "/weights", ops.attn_scope(r) + "/biases",
+                  ops.topdown_scope(r) + "/weights", ops.topdown_scope(r) + "/biases"]
+    variables = [params[n] for n in names]
+    for n, t in zip(names, variables):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError("training mode reads the variables in place: %r must be a contiguous float32 CUDA tensor" % n)
+    train = ops.make_train(keep, seed)
+
+    class _Head(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, *vs):
+            ctx.x_shape = x.shape
+            ctx.need_dx = x.requires_grad
+            return op.forward(x, train)
+
+        @staticmethod
+        def backward(ctx, dlogits):
+            dX, grads = op.backward(dlogits, want_dX=ctx.need_dx)
+            out = [dX.reshape(ctx.x_shape) if dX is not None else None]
+            for n, v in zip(names, variables):
+                out.append(grads[n].reshape(v.shape))
+            return tuple(out)
+
+    return _Head.apply(X.contiguous(), *variables)
+
+
 _HEAD_STATE = {}   # id(params) -> (params, {shape key -> AttnPoolOp}); holds the dict so the id stays unique
 
 
@@ -100,11 +159,12 @@ def attn_pool_head(X, params, cfg_net_flags, num_classes, is_training=False, fra
     `USE_POSE_PRELOGITS_BASED_ATTENTION_*` flags (src/config.py:182-209).  The device-resident copy of the
     variables and the workspace are cached per `params` object, so repeated calls cost one kernel launch.
     """
-    if is_training:
-        raise NotImplementedError("forward/eval only: the training graph (dropout, backward) is a 'next' row")
     if params is None:
         raise ValueError("params (TF variable name -> array) is required: the head has trained variables")
     flags, rank = ops.flags_from_cfg_net(cfg_net_flags)
+    if is_training:
+        raise NotImplementedError("use get_network_fn(..., is_training=True): the training graph needs the dropout "
+                                  "seed and autograd plumbing it sets up")
     entry = _HEAD_STATE.get(id(params))
     if entry is None or entry[0] is not params:
         entry = (params, {})

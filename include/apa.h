@@ -213,6 +213,53 @@ int apa_attn_pool_fwd_gather(const ApaDesc* desc, const float* X, const ApaWeigh
  * own flag array; returns at once when they already have).                                              */
 int apa_peer_gather_wait(const ApaPeerGather* gather, int32_t lag, void* stream);
 
+/* ---- training mode: train.py:399-420 builds the same graph with is_training=True
+ * and train.py:509-513 differentiates it.  Built for the single-map head that reads X directly
+ * (APA_FLAG_SINGLE_LAYER_ATT set, APA_FLAG_PER_CLASS clear; any rank, relu / softmax / plain attention); other
+ * descriptors return APA_ERR_UNSUPPORTED.                                                                   */
+typedef struct ApaTrain {
+  float dropout_keep;     /* keep probability of slim.dropout(last_conv) (nets_factory.py:296): 0.2 when            */
+                          /* cfg.NET.DROPOUT < 0 (:143-146, config.py:231), else 1 - DROPOUT; 1 = no dropout.        */
+                          /* Only the top-down convs read the dropped map; the attention convs read X itself.        */
+  int32_t reserved0;      /* must be 0                                                                               */
+  uint64_t dropout_seed;  /* the mask is a pure function of (seed, element index): 0 or 1/keep, see apa_dropout_mask; */
+                          /* pass the same ApaTrain to the forward and to the backward of a step                      */
+} ApaTrain;
+
+/* Caller-owned device buffers for the gradients; every one is overwritten (not accumulated into), shaped like the
+ * variable it belongs to (ApaWeights).  dX may be NULL when the backbone is frozen.                        */
+typedef struct ApaGrads {
+  float* dX;                        /* [batch, hw, channels]                                                 */
+  float* attn_w[APA_MAX_RANK];      /* r == 0: [channels, 1]; r >= 1: [1, 1]                                  */
+  float* attn_b[APA_MAX_RANK];      /* [1]                                                                   */
+  float* topdown_w[APA_MAX_RANK];   /* [channels, K]                                                         */
+  float* topdown_b[APA_MAX_RANK];   /* [K]                                                                   */
+} ApaGrads;
+
+/* Bytes of the buffer the training forward leaves for the backward (attention pre-activations [batch, hw] and the
+ * pooled features per video), and of the scratch workspace both need (no initialisation required; 256-byte
+ * aligned; calls sharing either must be on one stream).  0 for descriptors the training path does not serve. */
+size_t apa_attn_pool_train_saved_bytes(const ApaDesc* desc);
+size_t apa_attn_pool_train_workspace(const ApaDesc* desc);
+
+/* Forward in training mode: logits of the graph of nets_factory.py:242-374 with the dropout of :296 applied
+ * (train == NULL or dropout_keep == 1: the eval graph).  Two passes over X; writes `saved`.            */
+int apa_attn_pool_fwd_train(const ApaDesc* desc, const float* X, const ApaWeights* weights, const ApaTrain* train,
+                            float* logits, void* saved, size_t saved_bytes, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Backward: given dlogits [batch/frames, K] = dLoss/dlogits, the gradients with respect to X and to every variable
+ * on the path (what optimizer.compute_gradients returns for them, train.py:509-513).  X, weights, train and
+ * `saved` must be those of the forward call.  Two passes over X and one write of dX; bit-reproducible.    */
+int apa_attn_pool_bwd(const ApaDesc* desc, const float* X, const ApaWeights* weights, const ApaTrain* train,
+                      const float* dlogits, const void* saved, size_t saved_bytes, const ApaGrads* grads,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* The dropout mask the two calls above apply, materialised: mask[i] for the first `count` elements of X in
+ * row-major order (count % 4 == 0).  With h = splitmix64(splitmix64(seed) + i / 4), element i is kept iff the
+ * 16-bit field (h >> 16 * (i % 4)) & 0xFFFF is below round(keep * 65536); kept elements carry 1 / keep.    */
+int apa_dropout_mask(const ApaTrain* train, size_t count, float* mask, void* stream);
+
 /* Full second-order pooling G[b] = X[b]^T X[b]  ([batch, C, C], symmetric).  Not present in the
  * reference code; defined from the paper's second-order pooling equation (BASELINE config 5). */
 int apa_gram_fwd(int32_t batch, int32_t hw, int32_t channels, const float* X, float* G,

@@ -17,13 +17,47 @@ be held against:
 
 PARITY PIN STATUS: unpinned against the reference (no TF here, and the reference holds no gradient
 fixtures); the two statements are checked against each other and against finite differences in
-`tests/test_oracle_backward.py`.  No product code uses this file; no CUDA backward exists yet.
+`tests/test_oracle_backward.py`.  No product code uses this file; the CUDA backward
+(`apa_attn_pool_bwd`, csrc/apa_train.cu) is held against `backward_autograd` in `tests/test_gpu_backward.py`.
+
+`dropout_mask` restates the library's counter-based mask (include/apa.h: apa_dropout_mask) in NumPy so that the
+oracle can be given exactly the mask the kernels apply; TF's own mask comes from its Philox stream and cannot be
+reproduced bit for bit by anyone, only its distribution (Bernoulli(keep), kept values scaled by 1/keep).
 """
 from __future__ import annotations
 
 import numpy as np
 
 from . import attn_pool_oracle as orc
+
+
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(z):
+    """Vectorised splitmix64 on uint64 arrays (wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        z = (z + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+        return z ^ (z >> np.uint64(31))
+
+
+def dropout_mask(seed, shape, keep):
+    """mask[i] (row-major element index i) = 1/keep if the 16-bit field (h >> 16*(i%4)) & 0xFFFF of
+    h = splitmix64(splitmix64(seed) + i//4) is below round(keep*65536), else 0.  float32, like the kernels."""
+    n = int(np.prod(shape))
+    if n % 4:
+        raise ValueError("element count must be a multiple of 4")
+    if keep >= 1.0:
+        return np.ones(shape, dtype=np.float32)
+    key = _splitmix64(np.array([int(seed) & _M64], dtype=np.uint64))[0]
+    with np.errstate(over="ignore"):
+        h = _splitmix64((np.arange(n // 4, dtype=np.uint64) + key).astype(np.uint64))
+    thr = np.uint64(int(float(np.float32(keep)) * 65536.0 + 0.5))
+    fields = np.stack([(h >> np.uint64(16 * i)) & np.uint64(0xFFFF) for i in range(4)], axis=1).reshape(-1)
+    scale = np.float32(1.0) / np.float32(keep)
+    return np.where(fields < thr, scale, np.float32(0)).astype(np.float32).reshape(shape)
 
 
 def forward_train_torch(X, params, flags, num_classes, frames_per_video=1, dropout_mask=None):

@@ -38,15 +38,17 @@ def test_struct_layouts_match_header():
     prog = r'''
 #include <stdio.h>
 #include "apa.h"
-int main(void){ printf("%zu %zu %zu %zu %d %d\n", sizeof(ApaDesc), sizeof(ApaWeights), sizeof(ApaTuning),
-                       sizeof(ApaPeerGather), APA_ABI_VERSION, APA_MAX_RANK); return 0; }'''
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %d %d\n", sizeof(ApaDesc), sizeof(ApaWeights), sizeof(ApaTuning),
+                       sizeof(ApaPeerGather), sizeof(ApaTrain), sizeof(ApaGrads), APA_ABI_VERSION, APA_MAX_RANK);
+                return 0; }'''
     exe = "/tmp/apa_sizes_%d" % os.getpid()
     subprocess.run(["gcc", "-x", "c", "-I", os.path.join(ROOT, "include"), "-o", exe, "-"], input=prog,
                    text=True, check=True)
-    d, w, t, g, ver, mr = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
+    d, w, t, g, tr, gr, ver, mr = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
     os.remove(exe)
     assert (d, w, t, g) == (ctypes.sizeof(ops.ApaDesc), ctypes.sizeof(ops.ApaWeights), ctypes.sizeof(ops.ApaTuning),
                             ctypes.sizeof(ops.ApaPeerGather))
+    assert (tr, gr) == (ctypes.sizeof(ops.ApaTrain), ctypes.sizeof(ops.ApaGrads))
     assert ver == ops.APA_ABI_VERSION == ops.attn_pool_lib.apa_abi_version()
     assert mr == ops.APA_MAX_RANK
 
@@ -154,3 +156,23 @@ def test_forward_without_gpu_fails_loudly():
     st = ops.attn_pool_lib.apa_attn_pool_fwd(ctypes.byref(d), aligned, ctypes.byref(w), aligned, None, None,
                                              None, aligned, 0, None, None)
     assert st != ops.APA_OK
+
+
+def test_training_entry_points_validate_without_device():
+    """Sizes and argument checks of the training path (no kernel is launched for a rejected call)."""
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    lib = ops.attn_pool_lib
+    single = ops.APA_FLAG_SINGLE_LAYER_ATT | ops.APA_FLAG_RELU_ATT
+    d = ops.make_desc(32, 196, 2048, 393, flags=single)
+    saved, ws = lib.apa_attn_pool_train_saved_bytes(d), lib.apa_attn_pool_train_workspace(d)
+    # saved: a_0 [32*196] + g [32*2048] + s [32], in 256-byte granules; workspace holds the per-chunk partials
+    assert saved == 4 * (32 * 196 + 32 * 2048 + 64) and ws > 2 * 32 * 7 * 2048 * 4
+    for flags in (single | ops.APA_FLAG_PER_CLASS, ops.APA_FLAG_RELU_ATT):
+        bad = ops.make_desc(32, 196, 2048, 393, flags=flags)
+        assert lib.apa_attn_pool_train_saved_bytes(bad) == 0 and lib.apa_attn_pool_train_workspace(bad) == 0
+        assert lib.apa_attn_pool_fwd_train(bad, None, None, None, None, None, 0, None, 0, None) == ops.APA_ERR_UNSUPPORTED
+    assert lib.apa_attn_pool_fwd_train(d, None, None, None, None, None, 0, None, 0, None) == ops.APA_ERR_NULL
+    assert lib.apa_attn_pool_bwd(d, None, None, None, None, None, 0, None, None, 0, None) == ops.APA_ERR_NULL
+    t = ops.make_train(1.5, 0)
+    assert lib.apa_attn_pool_fwd_train(d, None, None, t, None, None, 0, None, 0, None) == ops.APA_ERR_UNSUPPORTED
+    assert lib.apa_dropout_mask(ops.make_train(0.2, 0), 6, None, None) == ops.APA_ERR_NULL

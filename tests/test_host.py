@@ -60,8 +60,8 @@ def test_get_network_fn_argument_checks():
     cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION = True
     with pytest.raises(ValueError):
         nets_factory.get_network_fn("resnet_v1_101", 393, 16, cfg)            # no variables
-    with pytest.raises(NotImplementedError):
-        nets_factory.get_network_fn("resnet_v1_101", 393, 16, cfg, is_training=True, params={})
+    fn = nets_factory.get_network_fn("resnet_v1_101", 393, 16, cfg, is_training=True, params={})
+    assert callable(fn) and fn.default_image_size == 224   # training graph: built lazily at the first call
     cfg.NET.USE_TEMPORAL_ATT = True
     with pytest.raises(NotImplementedError):
         nets_factory.get_network_fn("resnet_v1_101", 393, 16, cfg, params={})

@@ -32,8 +32,10 @@
 namespace apa {
 namespace {
 
-constexpr int kRowsPerChunk = 28;   // rows of one image per CTA in the passes over X (196 = 7 chunks)
 constexpr int kPoolThreads = 512;   // one float4 of channels per thread: 2048 channels per sweep
+constexpr int kPF = 8;              // rows a thread keeps in flight in the passes over X
+constexpr int kSlices = 16;         // channel slices of the logits contraction
+constexpr int kSlots = 148 * 2;     // CTAs of the X passes resident at once (two per SM)
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -62,7 +64,7 @@ __device__ __forceinline__ float4 drop_mask4(const Drop& d, uint64_t g4) {
 
 struct TrainParams {
   const float* X;
-  int N, HW, C, K, F, R, mode, J;   // N images = videos * F;  J row chunks per image
+  int N, HW, C, K, F, R, mode, J, rows;   // N images = videos * F;  J row chunks of `rows` rows per image
   const float* aw[APA_MAX_RANK];    // aw[0]: [C];  aw[r >= 1]: scalar
   const float* ab[APA_MAX_RANK];    // scalars
   const float* tw[APA_MAX_RANK];    // [C, K]
@@ -75,13 +77,14 @@ struct TrainParams {
   // forward scratch
   float* gpart;  // [N, J, R, C]
   float* spart;  // [N, J, R]
+  float* cpart;  // [kSlices, videos, K]
   float* logits; // [videos, K]
   // backward
   const float* dlogits;  // [videos, K]
   float* u;      // [videos, R, C]
   float* tt;     // [videos, R]
   float* dA;     // [N, R, HW]
-  float* dw0part;// [N, J, C]
+  float* dw0part;// [N, J, C], then [G1, C] (first level of the sum)
   float* pch;    // [N, 2, R]: sum delta_r, sum delta_r a_{r-1}
   float* dX;     // [N, HW, C] or nullptr
   float* d_aw[APA_MAX_RANK];
@@ -134,13 +137,17 @@ __global__ void __launch_bounds__(256) train_attn_kernel(TrainParams p) {
   const long rows = long(p.N) * p.HW;
   for (long row = long(blockIdx.x) * 8 + warp; row < rows; row += long(gridDim.x) * 8) {
     const float4* x = reinterpret_cast<const float4*>(p.X) + row * C4;
-    float acc = 0.f;
+    float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 8
-    for (int c4 = lane; c4 < C4; c4 += 32) {
+    for (int c4 = lane; c4 < C4; c4 += 64) {
       const float4 v = __ldg(x + c4), w = w0s[c4];
-      acc += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+      acc0 += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+      if (c4 + 32 < C4) {
+        const float4 v2 = __ldg(x + c4 + 32), w2 = w0s[c4 + 32];
+        acc1 += v2.x * w2.x + v2.y * w2.y + v2.z * w2.z + v2.w * w2.w;
+      }
     }
-    acc = warp_sum(acc);
+    const float acc = warp_sum(acc0 + acc1);
     if (lane == 0) p.a0[row] = acc + c0;
   }
 }
@@ -150,14 +157,18 @@ __global__ void __launch_bounds__(256) train_attn_kernel(TrainParams p) {
 __device__ __forceinline__ void image_attention(const TrainParams& p, int b, float* A, float* araw, float* red) {
   const int HW = p.HW, R = p.R;
   float wr[APA_MAX_RANK], cr[APA_MAX_RANK];
-  for (int r = 1; r < R; ++r) { wr[r] = __ldg(p.aw[r]); cr[r] = __ldg(p.ab[r]); }
+#pragma unroll
+  for (int r = 1; r < APA_MAX_RANK; ++r)
+    if (r < R) { wr[r] = __ldg(p.aw[r]); cr[r] = __ldg(p.ab[r]); }
   for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) {
     float a = p.a0[size_t(b) * HW + hw];
-    for (int r = 0; r < R; ++r) {
-      if (r > 0) a = wr[r] * a + cr[r];
-      if (araw) araw[r * HW + hw] = a;
-      A[r * HW + hw] = (p.mode == MODE_RELU) ? fmaxf(a, 0.f) : a;
-    }
+#pragma unroll
+    for (int r = 0; r < APA_MAX_RANK; ++r)
+      if (r < R) {
+        if (r > 0) a = wr[r] * a + cr[r];
+        if (araw) araw[r * HW + hw] = a;
+        A[r * HW + hw] = (p.mode == MODE_RELU) ? fmaxf(a, 0.f) : a;
+      }
   }
   __syncthreads();
   if (p.mode == MODE_SOFTMAX) {   // R == 1 (checked on the host)
@@ -173,36 +184,51 @@ __device__ __forceinline__ void image_attention(const TrainParams& p, int b, flo
   }
 }
 
-// partial g_r of (image b, row chunk j): sum over the chunk's rows of A_r[hw] * mask * X[b, hw, :]
-__global__ void __launch_bounds__(kPoolThreads) train_pool_kernel(TrainParams p) {
+// kPF rows of one float4 column, issued together (rows past h1 read as zero)
+__device__ __forceinline__ void load_rows(float4 (&xr)[kPF], const float4* col, int C4, int hb, int h1) {
+#pragma unroll
+  for (int i = 0; i < kPF; ++i)
+    xr[i] = (hb + i < h1) ? __ldg(col + size_t(hb + i) * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// partial g_r of (image b, row chunk j): sum over the chunk's rows of A_r[hw] * mask * X[b, hw, :].  The first rows
+// are in flight while the CTA works out the image's attention values.
+template <int RM>
+__global__ void __launch_bounds__(kPoolThreads, RM == 1 ? 2 : 1) train_pool_kernel(TrainParams p) {
   extern __shared__ float smem[];
   float* A = smem;                       // [R * HW]
   float* red = smem + p.R * p.HW;        // [32]
   const int j = blockIdx.x, b = blockIdx.y, HW = p.HW, R = p.R, C4 = p.C >> 2;
-  image_attention(p, b, A, nullptr, red);
-  const int h0 = j * kRowsPerChunk, h1 = min(HW, h0 + kRowsPerChunk);
+  const int h0 = j * p.rows, h1 = min(HW, h0 + p.rows);
   const float4* Xb = reinterpret_cast<const float4*>(p.X) + size_t(b) * HW * C4;
   const uint64_t g4b = uint64_t(b) * HW * C4;
+  float4 xr[kPF];
+  if (threadIdx.x < C4) load_rows(xr, Xb + threadIdx.x, C4, h0, h1);
+  image_attention(p, b, A, nullptr, red);
   for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
-    float4 acc[APA_MAX_RANK];
+    float4 acc[RM];
 #pragma unroll
-    for (int r = 0; r < APA_MAX_RANK; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int hw = h0; hw < h1; ++hw) {
-      float4 x = __ldg(Xb + size_t(hw) * C4 + c4);
-      if (p.drop.on) {
-        const float4 m = drop_mask4(p.drop, g4b + uint64_t(hw) * C4 + c4);
-        x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
-      }
+    for (int r = 0; r < RM; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int hb = h0; hb < h1; hb += kPF) {
+      if (hb != h0 || c4 != threadIdx.x) load_rows(xr, Xb + c4, C4, hb, h1);
 #pragma unroll
-      for (int r = 0; r < APA_MAX_RANK; ++r)
-        if (r < R) {
-          const float a = A[r * HW + hw];
-          acc[r].x += a * x.x; acc[r].y += a * x.y; acc[r].z += a * x.z; acc[r].w += a * x.w;
+      for (int i = 0; i < kPF; ++i) {
+        const int hw = min(hb + i, HW - 1);   // rows past h1 carry x == 0
+        float4 x = xr[i];
+        if (p.drop.on) {
+          const float4 m = drop_mask4(p.drop, g4b + uint64_t(hw) * C4 + c4);
+          x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
         }
+#pragma unroll
+        for (int r = 0; r < RM; ++r)
+          if (r < R) {
+            const float a = A[r * HW + hw];
+            acc[r].x += a * x.x; acc[r].y += a * x.y; acc[r].z += a * x.z; acc[r].w += a * x.w;
+          }
+      }
     }
 #pragma unroll
-    for (int r = 0; r < APA_MAX_RANK; ++r)
+    for (int r = 0; r < RM; ++r)
       if (r < R)
         reinterpret_cast<float4*>(p.gpart)[((size_t(b) * p.J + j) * R + r) * C4 + c4] = acc[r];
   }
@@ -223,6 +249,7 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(TrainParams p) {
   if (i < RC4) {
     const float4* src = reinterpret_cast<const float4*>(p.gpart) + size_t(v) * parts * RC4 + i;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
     for (int q = 0; q < parts; ++q) {
       const float4 t = src[size_t(q) * RC4];
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
@@ -236,94 +263,118 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(TrainParams p) {
   }
 }
 
-// logits[v, k] = (sum_r g_r[v].B_r[:, k] + d_r[k] s_r[v]) / (HW F): 8 videos x 32 classes per CTA, one channel
-// slice per warp, the slices summed in warp order
-__global__ void __launch_bounds__(256) train_logits_kernel(TrainParams p) {
-  __shared__ float red[8][8][33];
+// logits[v, k] = (sum_r g_r[v].B_r[:, k] + d_r[k] s_r[v]) / (HW F) in two steps: CONTRACT forms the partial products of
+// one channel slice (kSlices of them) for 32 videos x 32 classes per CTA out of shared memory, FINISH adds the slices in
+// order, the bias term and the scale.
+__global__ void __launch_bounds__(256) train_contract_kernel(TrainParams p) {
+  extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = blockIdx.x * 32 + lane, v0 = blockIdx.y * 8, V = p.N / p.F, C = p.C, K = p.K, R = p.R;
-  const int cs = (C + 7) / 8, clo = warp * cs, chi = min(C, clo + cs);
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const int kk = min(k, K - 1);
+  const int V = p.N / p.F, C = p.C, K = p.K, R = p.R;
+  const int k0 = blockIdx.x * 32, sl = blockIdx.y, v0 = blockIdx.z * 32;
+  const int cs = (((C + kSlices - 1) / kSlices) + 3) & ~3;
+  const int c0 = sl * cs, cn = max(0, min(cs, C - c0));
+  float* tws = sm;              // [cs][32]
+  float* gs = sm + cs * 32;     // [32][cs]
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool kok = k0 + lane < K;
   for (int r = 0; r < R; ++r) {
-    const float* tw = p.tw[r];
-    for (int c = clo; c < chi; ++c) {
-      const float w = __ldg(tw + size_t(c) * K + kk);
+    __syncthreads();
+    const float* tw = p.tw[r] + size_t(c0) * K + k0 + lane;
+#pragma unroll 8
+    for (int c = warp; c < cn; c += 8) tws[c * 32 + lane] = kok ? __ldg(tw + size_t(c) * K) : 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int v = min(v0 + i, V - 1);
-        acc[i] += p.gv[(size_t(v) * R + r) * C + c] * w;
-      }
+    for (int vv = 0; vv < 4; ++vv) {
+      const int v = warp * 4 + vv;
+      const float* g = p.gv + (size_t(min(v0 + v, V - 1)) * R + r) * C + c0;
+#pragma unroll 4
+      for (int c = lane; c < cn; c += 32) gs[v * cs + c] = g[c];
+    }
+    __syncthreads();
+    const float* g0 = gs + (warp * 4) * cs;
+#pragma unroll 4
+    for (int c = 0; c < cn; ++c) {
+      const float w = tws[c * 32 + lane];
+      acc[0] += g0[c] * w;
+      acc[1] += g0[cs + c] * w;
+      acc[2] += g0[2 * cs + c] * w;
+      acc[3] += g0[3 * cs + c] * w;
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) red[warp][i][lane] = acc[i];
-  __syncthreads();
-  const int v = v0 + warp;   // warp i finishes video i of the tile
-  if (v < V && k < K) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][warp][lane];
-    for (int r = 0; r < R; ++r) t += __ldg(p.tb[r] + k) * p.sv[size_t(v) * R + r];
-    p.logits[size_t(v) * K + k] = t / (float(p.HW) * float(p.F));
+  for (int i = 0; i < 4; ++i) {
+    const int v = v0 + warp * 4 + i;
+    if (v < V && kok) p.cpart[(size_t(sl) * V + v) * K + k0 + lane] = acc[i];
   }
+}
+__global__ void __launch_bounds__(256) train_finish_kernel(TrainParams p) {
+  const int V = p.N / p.F, K = p.K, R = p.R;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V * K) return;
+  const int v = i / K, k = i % K;
+  float t = 0.f;
+#pragma unroll
+  for (int s = 0; s < kSlices; ++s) t += p.cpart[size_t(s) * V * K + i];
+  for (int r = 0; r < R; ++r) t += __ldg(p.tb[r] + k) * p.sv[size_t(v) * R + r];
+  p.logits[i] = t / (float(p.HW) * float(p.F));
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// u_r[v, c] = B_r[c, :].G[v],  t_r[v] = d_r.G[v]  with G = dlogits / (HW F): warp per channel, 8 videos per CTA
+// u_r[v, c] = B_r[c, :].G[v],  t_r[v] = d_r.G[v]  with G = dlogits / (HW F): 32 channels x 8 videos per CTA, the 32 rows
+// of B_r (contiguous in memory) and the 8 rows of G in shared memory; warp = video, lane = channel
 __global__ void __launch_bounds__(256) bwd_u_kernel(TrainParams p) {
-  extern __shared__ float Gs[];   // [8][K]
+  extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r = blockIdx.z, v0 = blockIdx.y * 8, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
+  const int r = blockIdx.z, v0 = blockIdx.y * 8, c0 = blockIdx.x * 32, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
+  const int Kp = K | 1;             // odd row stride: lanes (channels) fall into distinct banks
+  float* tws = sm;                  // [32][Kp]
+  float* Gs = sm + 32 * Kp;         // [8][K]
   const float scale = 1.f / (float(p.HW) * float(p.F));
-  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
-    const int v = v0 + i / K;
-    Gs[i] = (v < V) ? p.dlogits[size_t(v) * K + (i % K)] * scale : 0.f;
+  const int nc = min(32, C - c0);
+#pragma unroll 4
+  for (int c = warp; c < nc; c += 8) {
+    const float* src = p.tw[r] + size_t(c0 + c) * K;
+#pragma unroll 4
+    for (int k = lane; k < K; k += 32) tws[c * Kp + k] = __ldg(src + k);
+  }
+  {
+    const int v = min(v0 + warp, V - 1);
+#pragma unroll 4
+    for (int k = lane; k < K; k += 32) Gs[warp * K + k] = p.dlogits[size_t(v) * K + k] * scale;
   }
   __syncthreads();
-  const int c = blockIdx.x * 8 + warp;
-  if (c < C) {
-    const float* tw = p.tw[r] + size_t(c) * K;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float w = __ldg(tw + k);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += Gs[i * K + k] * w;
+  if (v0 + warp < V) {
+    const float* g = Gs + warp * K;
+    if (lane < nc) {
+      const float* t = tws + lane * Kp;
+      float a0 = 0.f, a1 = 0.f;
+      int k = 0;
+#pragma unroll 4
+      for (; k + 1 < K; k += 2) { a0 += g[k] * t[k]; a1 += g[k + 1] * t[k + 1]; }
+      if (k < K) a0 += g[k] * t[k];
+      p.u[(size_t(v0 + warp) * R + r) * C + c0 + lane] = a0 + a1;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t = warp_sum(acc[i]);
-      if (lane == 0 && v0 + i < V) p.u[(size_t(v0 + i) * R + r) * C + c] = t;
+    if (blockIdx.x == 0) {
+      float t = 0.f;
+      for (int k = lane; k < K; k += 32) t += g[k] * __ldg(p.tb[r] + k);
+      t = warp_sum(t);
+      if (lane == 0) p.tt[size_t(v0 + warp) * R + r] = t;
     }
-  }
-  if (blockIdx.x == 0 && v0 + warp < V) {
-    float t = 0.f;
-    for (int k = lane; k < K; k += 32) t += Gs[warp * K + k] * __ldg(p.tb[r] + k);
-    t = warp_sum(t);
-    if (lane == 0) p.tt[size_t(v0 + warp) * R + r] = t;
   }
 }
 
-// pass 1 over X: dA_r[b, hw] = (mask * X[b, hw]).u_r[v] + t_r[v]; warp per row, u_r[v] in shared memory
+// pass 1 over X: dA_r[b, hw] = (mask * X[b, hw]).u_r[v] + t_r[v]; warp per row, u_r[v] through L1
 __global__ void __launch_bounds__(256) bwd_dattn_kernel(TrainParams p) {
-  extern __shared__ float4 us[];   // [R][C/4]
   const int j = blockIdx.x, b = blockIdx.y, v = b / p.F, HW = p.HW, R = p.R, C4 = p.C >> 2;
-  for (int i = threadIdx.x; i < R * C4; i += blockDim.x)
-    us[i] = reinterpret_cast<const float4*>(p.u)[size_t(v) * R * C4 + i];
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int h0 = j * kRowsPerChunk, h1 = min(HW, h0 + kRowsPerChunk);
+  const int h0 = j * p.rows, h1 = min(HW, h0 + p.rows);
   const float4* Xb = reinterpret_cast<const float4*>(p.X) + size_t(b) * HW * C4;
+  const float4* uv = reinterpret_cast<const float4*>(p.u) + size_t(v) * R * C4;
   const uint64_t g4b = uint64_t(b) * HW * C4;
   for (int hw = h0 + warp; hw < h1; hw += 8) {
     float acc[APA_MAX_RANK];
 #pragma unroll
     for (int r = 0; r < APA_MAX_RANK; ++r) acc[r] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int c4 = lane; c4 < C4; c4 += 32) {
       float4 x = __ldg(Xb + size_t(hw) * C4 + c4);
       if (p.drop.on) {
@@ -333,7 +384,7 @@ __global__ void __launch_bounds__(256) bwd_dattn_kernel(TrainParams p) {
 #pragma unroll
       for (int r = 0; r < APA_MAX_RANK; ++r)
         if (r < R) {
-          const float4 w = us[r * C4 + c4];
+          const float4 w = uv[r * C4 + c4];
           acc[r] += x.x * w.x + x.y * w.y + x.z * w.z + x.w * w.w;
         }
     }
@@ -348,7 +399,8 @@ __global__ void __launch_bounds__(256) bwd_dattn_kernel(TrainParams p) {
 
 // pass 2 over X: per image the chain / relu / softmax backward (tiny, recomputed by each of the image's CTAs), then
 //   dX[b, hw, :] = mask * sum_r A_r[hw] u_r[v] + delta_0[hw] w_0      and the CTA's part of dw_0 = sum delta_0 X
-__global__ void __launch_bounds__(kPoolThreads) bwd_dx_kernel(TrainParams p) {
+template <int RM>
+__global__ void __launch_bounds__(kPoolThreads, RM == 1 ? 2 : 1) bwd_dx_kernel(TrainParams p) {
   extern __shared__ float smem[];
   const int HW = p.HW, R = p.R, C4 = p.C >> 2;
   float* A = smem;                 // [R * HW]
@@ -356,133 +408,181 @@ __global__ void __launch_bounds__(kPoolThreads) bwd_dx_kernel(TrainParams p) {
   float* d0 = araw + R * HW;       // [HW]
   float* red = d0 + HW;            // [32]
   const int j = blockIdx.x, b = blockIdx.y, v = b / p.F;
+  const int h0 = j * p.rows, h1 = min(HW, h0 + p.rows);
+  const float4* Xb = reinterpret_cast<const float4*>(p.X) + size_t(b) * HW * C4;
+  float4 xr[kPF];
+  if (threadIdx.x < C4) load_rows(xr, Xb + threadIdx.x, C4, h0, h1);
   image_attention(p, b, A, araw, red);
-  float wr[APA_MAX_RANK];
-  for (int r = 1; r < R; ++r) wr[r] = __ldg(p.aw[r]);
+  float wr[4];
+#pragma unroll
+  for (int r = 1; r < 4; ++r) wr[r] = (r < R) ? __ldg(p.aw[r]) : 0.f;
   float sAd = 0.f;
   if (p.mode == MODE_SOFTMAX) {
     float t = 0.f;
     for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) t += A[hw] * p.dA[size_t(b) * HW + hw];
     sAd = block_sum(t, red);
   }
-  float sd[APA_MAX_RANK], sda[APA_MAX_RANK];
+  float sd[RM], sda[RM];
 #pragma unroll
-  for (int r = 0; r < APA_MAX_RANK; ++r) sd[r] = sda[r] = 0.f;
+  for (int r = 0; r < RM; ++r) sd[r] = sda[r] = 0.f;
   for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) {
-    float da[APA_MAX_RANK];
+    float da[RM];
 #pragma unroll
-    for (int r = 0; r < APA_MAX_RANK; ++r)
+    for (int r = 0; r < RM; ++r) {
+      da[r] = 0.f;
       if (r < R) {
         float d = p.dA[(size_t(b) * R + r) * HW + hw];
         if (p.mode == MODE_RELU) d = araw[r * HW + hw] > 0.f ? d : 0.f;
         if (p.mode == MODE_SOFTMAX) d = A[hw] * (d - sAd);
         da[r] = d;
       }
+    }
     float delta = 0.f;
 #pragma unroll
-    for (int r = APA_MAX_RANK - 1; r >= 0; --r)
+    for (int r = RM - 1; r >= 0; --r)
       if (r < R) {
-        delta = da[r] + ((r + 1 < R) ? wr[(r + 1) & (APA_MAX_RANK - 1)] * delta : 0.f);
+        delta = da[r] + ((r + 1 < R) ? wr[(r + 1) & 3] * delta : 0.f);
         sd[r] += delta;
         if (r > 0) sda[r] += delta * araw[(r - 1) * HW + hw];
       }
     d0[hw] = delta;
   }
-  // the image's sums for dc_r and dw_r (r >= 1); chunk 0 writes them
-  for (int r = 0; r < R; ++r) {
-    const float s1 = block_sum(sd[r], red);
-    const float s2 = (r > 0) ? block_sum(sda[r], red) : 0.f;
-    if (j == 0 && threadIdx.x == 0) {
-      p.pch[(size_t(b) * 2 + 0) * R + r] = s1;
-      p.pch[(size_t(b) * 2 + 1) * R + r] = s2;
-    }
+  if (j == 0) {   // the image's sums for dc_r and dw_r (r >= 1)
+#pragma unroll
+    for (int r = 0; r < RM; ++r)
+      if (r < R) {
+        const float s1 = block_sum(sd[r], red);
+        const float s2 = (r > 0) ? block_sum(sda[r], red) : 0.f;
+        if (threadIdx.x == 0) {
+          p.pch[(size_t(b) * 2 + 0) * R + r] = s1;
+          p.pch[(size_t(b) * 2 + 1) * R + r] = s2;
+        }
+      }
   }
   __syncthreads();
-  const int h0 = j * kRowsPerChunk, h1 = min(HW, h0 + kRowsPerChunk);
-  const float4* Xb = reinterpret_cast<const float4*>(p.X) + size_t(b) * HW * C4;
   float4* dXb = p.dX ? reinterpret_cast<float4*>(p.dX) + size_t(b) * HW * C4 : nullptr;
   const uint64_t g4b = uint64_t(b) * HW * C4;
   for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
-    float4 u4[APA_MAX_RANK];
+    float4 u4[RM];
 #pragma unroll
-    for (int r = 0; r < APA_MAX_RANK; ++r)
+    for (int r = 0; r < RM; ++r)
       if (r < R) u4[r] = reinterpret_cast<const float4*>(p.u)[(size_t(v) * R + r) * C4 + c4];
     const float4 w04 = __ldg(reinterpret_cast<const float4*>(p.aw[0]) + c4);
     float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int hw = h0; hw < h1; ++hw) {
-      const float4 x = __ldg(Xb + size_t(hw) * C4 + c4);
-      const float d = d0[hw];
-      dw.x += d * x.x; dw.y += d * x.y; dw.z += d * x.z; dw.w += d * x.w;
-      if (dXb) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int hb = h0; hb < h1; hb += kPF) {
+      if (hb != h0 || c4 != threadIdx.x) load_rows(xr, Xb + c4, C4, hb, h1);
 #pragma unroll
-        for (int r = 0; r < APA_MAX_RANK; ++r)
-          if (r < R) {
-            const float a = A[r * HW + hw];
-            t.x += a * u4[r].x; t.y += a * u4[r].y; t.z += a * u4[r].z; t.w += a * u4[r].w;
+      for (int i = 0; i < kPF; ++i) {
+        const int hw = hb + i;
+        if (hw < h1) {
+          const float4 x = xr[i];
+          const float d = d0[hw];
+          dw.x += d * x.x; dw.y += d * x.y; dw.z += d * x.z; dw.w += d * x.w;
+          if (dXb) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+              if (r < R) {
+                const float a = A[r * HW + hw];
+                t.x += a * u4[r].x; t.y += a * u4[r].y; t.z += a * u4[r].z; t.w += a * u4[r].w;
+              }
+            if (p.drop.on) {
+              const float4 m = drop_mask4(p.drop, g4b + uint64_t(hw) * C4 + c4);
+              t.x *= m.x; t.y *= m.y; t.z *= m.z; t.w *= m.w;
+            }
+            t.x += d * w04.x; t.y += d * w04.y; t.z += d * w04.z; t.w += d * w04.w;
+            __stcs(dXb + size_t(hw) * C4 + c4, t);
           }
-        if (p.drop.on) {
-          const float4 m = drop_mask4(p.drop, g4b + uint64_t(hw) * C4 + c4);
-          t.x *= m.x; t.y *= m.y; t.z *= m.z; t.w *= m.w;
         }
-        t.x += d * w04.x; t.y += d * w04.y; t.z += d * w04.z; t.w += d * w04.w;
-        __stcs(dXb + size_t(hw) * C4 + c4, t);
       }
     }
     reinterpret_cast<float4*>(p.dw0part)[(size_t(b) * p.J + j) * C4 + c4] = dw;
   }
 }
 
-// dB_r[c, k] = sum_v g_r[v, c] G[v, k];  dd_r[k] = sum_v s_r[v] G[v, k]: warp per channel
+// dB_r[c, k] = sum_v g_r[v, c] G[v, k];  dd_r[k] = sum_v s_r[v] G[v, k]: 32 channels x 256 classes per CTA pass, 32
+// videos at a time in shared memory; thread = class, 32 channel accumulators
 __global__ void __launch_bounds__(256) bwd_wgrad_kernel(TrainParams p) {
+  __shared__ float Gs[32][256];
+  __shared__ float4 gvs[32][8];
+  const int r = blockIdx.y, c0 = blockIdx.x * 32, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r = blockIdx.y, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
   const float scale = 1.f / (float(p.HW) * float(p.F));
-  const int c = blockIdx.x * 8 + warp;
-  if (c < C) {
-    for (int k0 = 0; k0 < K; k0 += 128) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int v = 0; v < V; ++v) {
-        const float g = p.gv[(size_t(v) * R + r) * C + c];
+  const int nc = min(32, C - c0);   // a multiple of 4
+  for (int kb = 0; kb < K; kb += 256) {
+    const int k = kb + threadIdx.x;
+    float acc[32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = k0 + i * 32 + lane;
-          acc[i] += g * (k < K ? __ldg(p.dlogits + size_t(v) * K + k) : 0.f);
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int vt = 0; vt < V; vt += 32) {
+      __syncthreads();
+#pragma unroll 8
+      for (int vv = 0; vv < 32; ++vv)
+        Gs[vv][threadIdx.x] = (vt + vv < V && k < K) ? __ldg(p.dlogits + size_t(vt + vv) * K + k) : 0.f;
+      {  // 32 videos x 8 float4 of channels: one float4 per thread
+        const int vv = threadIdx.x >> 3, c4 = threadIdx.x & 7;
+        gvs[vv][c4] = (vt + vv < V && c4 * 4 < nc)
+                          ? *reinterpret_cast<const float4*>(p.gv + (size_t(vt + vv) * R + r) * C + c0 + c4 * 4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int vv = 0; vv < 32; ++vv) {
+        const float g = Gs[vv][threadIdx.x];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 q = gvs[vv][c4];
+          acc[c4 * 4 + 0] += q.x * g; acc[c4 * 4 + 1] += q.y * g; acc[c4 * 4 + 2] += q.z * g; acc[c4 * 4 + 3] += q.w * g;
         }
       }
+    }
+    if (k < K) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = k0 + i * 32 + lane;
-        if (k < K) p.d_tw[r][size_t(c) * K + k] = acc[i] * scale;
+      for (int c = 0; c < 32; ++c)
+        if (c < nc) p.d_tw[r][size_t(c0 + c) * K + k] = acc[c] * scale;
+      if (blockIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll 8
+        for (int v = 0; v < V; ++v) t += p.sv[size_t(v) * R + r] * __ldg(p.dlogits + size_t(v) * K + k);
+        p.d_tb[r][k] = t * scale;
       }
     }
   }
-  if (blockIdx.x == 0)
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      float t = 0.f;
-      for (int v = 0; v < V; ++v) t += p.sv[size_t(v) * R + r] * __ldg(p.dlogits + size_t(v) * K + k);
-      p.d_tb[r][k] = t * scale;
-    }
+  (void)lane; (void)warp;
 }
 
-// dw_0[c] = sum of the CTAs' parts (fixed order); dc_r, dw_r (r >= 1) = sums over the images
-__global__ void __launch_bounds__(256) bwd_finish_kernel(TrainParams p) {
-  const int C4 = p.C >> 2, parts = p.N * p.J;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Sum of `parts` rows of C floats in a fixed order: CTA (x, y) adds the parts of group y (`per` of them) for 32 float4
+// columns, the group's parts split over the 8 warps, the warps' sums added in order.  Two launches: parts -> groups -> 1.
+// The second one also adds the images' sums for dc_r and dw_r (r >= 1).
+__global__ void __launch_bounds__(256) bwd_sum_kernel(TrainParams p, const float* __restrict__ src, float* __restrict__ dst,
+                                                      int parts, int per, int final) {
+  __shared__ float4 red[8][32];
+  const int C4 = p.C >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int g0 = blockIdx.y * per, g1 = min(parts, g0 + per);
+  const int pw = (per + 7) / 8, q0 = g0 + warp * pw, q1 = min(g1, q0 + pw);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < C4) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* src = reinterpret_cast<const float4*>(p.dw0part) + i;
+    const float4* s4 = reinterpret_cast<const float4*>(src) + i;
 #pragma unroll 8
-    for (int q = 0; q < parts; ++q) {
-      const float4 t = src[size_t(q) * C4];
+    for (int q = q0; q < q1; ++q) {
+      const float4 t = s4[size_t(q) * C4];
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
-    reinterpret_cast<float4*>(p.d_aw[0])[i] = acc;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 2 * p.R) {
-    const int which = threadIdx.x / p.R, r = threadIdx.x % p.R;
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && i < C4) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { t.x += red[w][lane].x; t.y += red[w][lane].y; t.z += red[w][lane].z; t.w += red[w][lane].w; }
+    reinterpret_cast<float4*>(dst)[size_t(blockIdx.y) * C4 + i] = t;
+  }
+  if (final && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + 2 * p.R) {
+    const int jj = threadIdx.x - 32, which = jj / p.R, r = jj % p.R;
     float t = 0.f;
+#pragma unroll 8
     for (int b = 0; b < p.N; ++b) t += p.pch[(size_t(b) * 2 + which) * p.R + r];
     if (which == 0) p.d_ab[r][0] = t;
     else if (r > 0) p.d_aw[r][0] = t;
@@ -516,18 +616,34 @@ int train_supported(const ApaDesc* d) {
   if (st != APA_OK) return st;
   if ((d->flags & APA_FLAG_PER_CLASS) || !(d->flags & APA_FLAG_SINGLE_LAYER_ATT)) return APA_ERR_UNSUPPORTED;
   if (size_t(d->rank) * d->hw * 2 + d->hw + 64 > 40000) return APA_ERR_SHAPE;   // per-image attention lives in smem
-  if (size_t(d->rank) * d->channels * 4 > 200 * 1024 || size_t(d->num_classes) * 32 > 200 * 1024) return APA_ERR_SHAPE;
+  if (size_t(d->num_classes) * 164 > 220 * 1024) return APA_ERR_SHAPE;   // bwd_u keeps 40 rows of K floats in smem
   return APA_OK;
 }
 
+// Row chunks per image for the passes over X: the (image, chunk) CTAs should fill whole waves of kSlots resident CTAs
+// with as little left over as possible; each chunk costs a prologue worth a few rows.
+int chunks_per_image(int N, int HW) {
+  int best = 1;
+  double best_cost = 1e300;
+  for (int J = 1; J <= std::min(HW, 64); ++J) {
+    const int rows = (HW + J - 1) / J;
+    if ((HW + rows - 1) / rows != J) continue;   // J must be the chunk count its row count produces
+    const double waves = double((long(N) * J + kSlots - 1) / kSlots);
+    const double cost = waves * (rows + 4.0);
+    if (cost < best_cost) { best_cost = cost; best = J; }
+  }
+  return best;
+}
+int sum_groups(size_t parts) { return int(std::min<size_t>(32, (parts + 31) / 32)); }
+
 struct Carve {
   size_t a0, gv, sv, saved_total;                       // saved
-  size_t gpart, spart, u, tt, dA, dw0part, pch, ws_total;   // workspace (floats)
+  size_t gpart, spart, cpart, u, tt, dA, dw0part, pch, ws_total;   // workspace (floats)
 };
 Carve carve(const ApaDesc* d) {
   Carve c;
   const size_t N = d->batch, V = d->batch / d->frames, R = d->rank, C = d->channels, HW = d->hw;
-  const size_t J = (HW + kRowsPerChunk - 1) / kRowsPerChunk;
+  const size_t J = chunks_per_image(d->batch, d->hw);
   size_t o = 0;
   c.a0 = o; o += al(N * HW);
   c.gv = o; o += al(V * R * C);
@@ -536,10 +652,11 @@ Carve carve(const ApaDesc* d) {
   o = 0;
   c.gpart = o; o += al(N * J * R * C);
   c.spart = o; o += al(N * J * R);
+  c.cpart = o; o += al(size_t(kSlices) * V * d->num_classes);
   c.u = o; o += al(V * R * C);
   c.tt = o; o += al(V * R);
   c.dA = o; o += al(N * R * HW);
-  c.dw0part = o; o += al(N * J * C);
+  c.dw0part = o; o += al(N * J * C + size_t(sum_groups(N * J)) * C);
   c.pch = o; o += al(N * 2 * R);
   c.ws_total = o;
   return c;
@@ -551,7 +668,8 @@ int fill(TrainParams& p, const ApaDesc* d, const ApaWeights* w, const ApaTrain* 
   p.X = X;
   p.N = d->batch; p.HW = d->hw; p.C = d->channels; p.K = d->num_classes; p.F = d->frames; p.R = d->rank;
   p.mode = (d->flags & APA_FLAG_SOFTMAX_ATT) ? MODE_SOFTMAX : ((d->flags & APA_FLAG_RELU_ATT) ? MODE_RELU : MODE_PLAIN);
-  p.J = (d->hw + kRowsPerChunk - 1) / kRowsPerChunk;
+  p.J = chunks_per_image(d->batch, d->hw);
+  p.rows = (d->hw + p.J - 1) / p.J;
   for (int r = 0; r < d->rank; ++r) {
     if (!w->attn_w[r] || !w->attn_b[r] || !w->topdown_w[r] || !w->topdown_b[r]) return APA_ERR_NULL;
     p.aw[r] = w->attn_w[r]; p.ab[r] = w->attn_b[r]; p.tw[r] = w->topdown_w[r]; p.tb[r] = w->topdown_b[r];
@@ -559,7 +677,7 @@ int fill(TrainParams& p, const ApaDesc* d, const ApaWeights* w, const ApaTrain* 
   if ((reinterpret_cast<uintptr_t>(X) & 15u) || (reinterpret_cast<uintptr_t>(w->attn_w[0]) & 15u)) return APA_ERR_ALIGN;
   p.drop = make_drop(t);
   p.a0 = saved + c.a0; p.gv = saved + c.gv; p.sv = saved + c.sv;
-  p.gpart = ws + c.gpart; p.spart = ws + c.spart; p.u = ws + c.u; p.tt = ws + c.tt; p.dA = ws + c.dA;
+  p.gpart = ws + c.gpart; p.spart = ws + c.spart; p.cpart = ws + c.cpart; p.u = ws + c.u; p.tt = ws + c.tt; p.dA = ws + c.dA;
   p.dw0part = ws + c.dw0part; p.pch = ws + c.pch;
   return APA_OK;
 }
@@ -621,11 +739,22 @@ int apa_attn_pool_fwd_train(const ApaDesc* desc, const float* X, const ApaWeight
   }
   {
     const size_t smem = (size_t(p.R) * p.HW + 32) * 4;
-    APA_CUDA(big_smem(train_pool_kernel, smem));
-    train_pool_kernel<<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+    if (p.R == 1) {
+      APA_CUDA(big_smem(train_pool_kernel<1>, smem));
+      train_pool_kernel<1><<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+    } else {
+      APA_CUDA(big_smem(train_pool_kernel<APA_MAX_RANK>, smem));
+      train_pool_kernel<APA_MAX_RANK><<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+    }
   }
   train_reduce_kernel<<<dim3((p.R * (p.C / 4) + 255) / 256, V), 256, 0, stream>>>(p);
-  train_logits_kernel<<<dim3((p.K + 31) / 32, (V + 7) / 8), 256, 0, stream>>>(p);
+  {
+    const int cs = (((p.C + kSlices - 1) / kSlices) + 3) & ~3;
+    const size_t smem = size_t(cs) * 64 * 4;
+    APA_CUDA(big_smem(train_contract_kernel, smem));
+    train_contract_kernel<<<dim3((p.K + 31) / 32, kSlices, (V + 31) / 32), 256, smem, stream>>>(p);
+    train_finish_kernel<<<(V * p.K + 255) / 256, 256, 0, stream>>>(p);
+  }
   APA_CUDA(cudaGetLastError());
   return APA_OK;
 }
@@ -654,22 +783,28 @@ int apa_attn_pool_bwd(const ApaDesc* desc, const float* X, const ApaWeights* wei
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int V = p.N / p.F;
   {
-    const size_t smem = size_t(8) * p.K * 4;
+    const size_t smem = (size_t(32) * (p.K | 1) + size_t(8) * p.K) * 4;
     APA_CUDA(big_smem(bwd_u_kernel, smem));
-    bwd_u_kernel<<<dim3((p.C + 7) / 8, (V + 7) / 8, p.R), 256, smem, stream>>>(p);
+    bwd_u_kernel<<<dim3((p.C + 31) / 32, (V + 7) / 8, p.R), 256, smem, stream>>>(p);
   }
-  {
-    const size_t smem = size_t(p.R) * p.C * 4;
-    APA_CUDA(big_smem(bwd_dattn_kernel, smem));
-    bwd_dattn_kernel<<<dim3(p.J, p.N), 256, smem, stream>>>(p);
-  }
+  bwd_dattn_kernel<<<dim3(p.J, p.N), 256, 0, stream>>>(p);
   {
     const size_t smem = (size_t(2) * p.R * p.HW + p.HW + 32) * 4;
-    APA_CUDA(big_smem(bwd_dx_kernel, smem));
-    bwd_dx_kernel<<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+    if (p.R == 1) {
+      APA_CUDA(big_smem(bwd_dx_kernel<1>, smem));
+      bwd_dx_kernel<1><<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+    } else {
+      APA_CUDA(big_smem(bwd_dx_kernel<APA_MAX_RANK>, smem));
+      bwd_dx_kernel<APA_MAX_RANK><<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+    }
   }
-  bwd_wgrad_kernel<<<dim3((p.C + 7) / 8, p.R), 256, 0, stream>>>(p);
-  bwd_finish_kernel<<<(p.C / 4 + 255) / 256, 256, 0, stream>>>(p);
+  bwd_wgrad_kernel<<<dim3((p.C + 31) / 32, p.R), 256, 0, stream>>>(p);
+  {
+    const int parts = p.N * p.J, groups = sum_groups(parts), per = (parts + groups - 1) / groups;
+    float* tmp = p.dw0part + size_t(parts) * p.C;
+    bwd_sum_kernel<<<dim3((p.C / 4 + 31) / 32, groups), 256, 0, stream>>>(p, p.dw0part, tmp, parts, per, 0);
+    bwd_sum_kernel<<<dim3((p.C / 4 + 31) / 32, 1), 256, 0, stream>>>(p, tmp, p.d_aw[0], groups, groups, 1);
+  }
   APA_CUDA(cudaGetLastError());
   return APA_OK;
 }

@@ -8,9 +8,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _rel(a, b):
+def _rel(a, b, floor=1e-30):
+    """max |a - b| relative to max |b| (or to `floor`, for gradients that are zero by construction: the sum of a
+    softmax's input gradients, for one)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
 
 
 CASES = [
@@ -57,9 +59,10 @@ def test_forward_train_and_backward_match_autograd(case):
     ref_dX, ref_g = bwd.backward_autograd(X, params, fl, K, dl, frames_per_video=F, dropout_mask=mask)
     assert _rel(dX.cpu().numpy(), ref_dX) <= 1e-4, "dX"
     assert set(grads) == set(ref_g)
+    gscale = max(float(np.abs(v).max()) for v in ref_g.values())
     for n, g in grads.items():
         assert tuple(g.shape) == tuple(np.asarray(params[n]).reshape(g.shape).shape)
-        assert _rel(g.cpu().numpy().reshape(ref_g[n].shape), ref_g[n]) <= 1e-4, n
+        assert _rel(g.cpu().numpy().reshape(ref_g[n].shape), ref_g[n], floor=1e-2 * gscale) <= 1e-4, n
     # bit-reproducible: all reductions have a fixed order
     logits2 = op.forward(Xd, train).clone()
     dX2, grads2 = op.backward(torch.from_numpy(dl).to(dev))

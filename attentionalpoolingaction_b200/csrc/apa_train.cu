@@ -34,8 +34,10 @@ namespace {
 
 constexpr int kPoolThreads = 512;   // one float4 of channels per thread: 2048 channels per sweep
 constexpr int kPF = 8;              // rows a thread keeps in flight in the passes over X
+static_assert(kPF == 8, "bwd_fused_kernel packs 4 mask bits per row into one 32-bit word");
 constexpr int kSlices = 16;         // channel slices of the logits contraction
-constexpr int kSlots = 148 * 2;     // CTAs of the X passes resident at once (two per SM)
+constexpr int kSMs = 148;
+constexpr int kSlots = kSMs;        // CTAs of the X passes resident at once: the fused kernels run one (persistent) per SM
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -44,27 +46,36 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 
+// murmur3's 32-bit finaliser: a bijection of 32-bit words with full avalanche; two of them (two keys) give the 64 bits a
+// group of four elements needs.  ~12 integer instructions per float4 of X.
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+
 struct Drop {
-  uint64_t key;     // splitmix64(seed)
-  uint32_t thr;     // keep iff 16-bit lane < thr;  thr = round(keep * 65536)
-  float scale;      // 1 / keep
-  int on;           // 0: keep == 1, no hashing at all
+  uint32_t key0, key1;  // low / high word of splitmix64(seed)
+  uint32_t thr;         // keep iff 16-bit field < thr;  thr = round(keep * 65536)
+  float scale;          // 1 / keep
+  int on;               // 0: keep == 1, no hashing at all
 };
 
-// mask of the four consecutive elements 4*g4 .. 4*g4+3 of X (row-major [batch, hw, channels], channels % 4 == 0)
-__device__ __forceinline__ float4 drop_mask4(const Drop& d, uint64_t g4) {
-  const uint64_t h = splitmix64(d.key + g4);
-  float4 m;
-  m.x = (uint32_t(h) & 0xFFFFu) < d.thr ? d.scale : 0.f;
-  m.y = (uint32_t(h >> 16) & 0xFFFFu) < d.thr ? d.scale : 0.f;
-  m.z = (uint32_t(h >> 32) & 0xFFFFu) < d.thr ? d.scale : 0.f;
-  m.w = (uint32_t(h >> 48) & 0xFFFFu) < d.thr ? d.scale : 0.f;
-  return m;
+// mask of the four consecutive elements 4*g4 .. 4*g4+3 of X (row-major [batch, hw, channels], channels % 4 == 0;
+// g4 < 2^32 is checked on the host)
+__device__ __forceinline__ uint32_t drop_bits4(const Drop& d, uint64_t g4) {
+  const uint32_t a = fmix32(uint32_t(g4) ^ d.key0), b = fmix32(uint32_t(g4) ^ d.key1);
+  return ((a & 0xFFFFu) < d.thr ? 1u : 0u) | ((a >> 16) < d.thr ? 2u : 0u) | ((b & 0xFFFFu) < d.thr ? 4u : 0u) |
+         ((b >> 16) < d.thr ? 8u : 0u);
 }
+__device__ __forceinline__ float4 bits_mask4(uint32_t bits, float scale) {
+  return make_float4((bits & 1u) ? scale : 0.f, (bits & 2u) ? scale : 0.f, (bits & 4u) ? scale : 0.f, (bits & 8u) ? scale : 0.f);
+}
+__device__ __forceinline__ float4 drop_mask4(const Drop& d, uint64_t g4) { return bits_mask4(drop_bits4(d, g4), d.scale); }
 
 struct TrainParams {
   const float* X;
   int N, HW, C, K, F, R, mode, J, rows;   // N images = videos * F;  J row chunks of `rows` rows per image
+  int parts;                              // backward: rows of dw0part / pch that were written (CTAs or chunks)
   const float* aw[APA_MAX_RANK];    // aw[0]: [C];  aw[r >= 1]: scalar
   const float* ab[APA_MAX_RANK];    // scalars
   const float* tw[APA_MAX_RANK];    // [C, K]
@@ -85,7 +96,7 @@ struct TrainParams {
   float* tt;     // [videos, R]
   float* dA;     // [N, R, HW]
   float* dw0part;// [N, J, C], then [G1, C] (first level of the sum)
-  float* pch;    // [N, 2, R]: sum delta_r, sum delta_r a_{r-1}
+  float* pch;    // [N * J, 2, R]: per chunk, sum delta_r and sum delta_r a_{r-1}
   float* dX;     // [N, HW, C] or nullptr
   float* d_aw[APA_MAX_RANK];
   float* d_ab[APA_MAX_RANK];
@@ -128,6 +139,8 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // ------------------------------------------------------------------------------------------------ forward
 // a_0[row] = X[row].w_0 + c_0 (un-dropped features, nets_factory.py:259-270): one warp per row.
 __global__ void __launch_bounds__(256) train_attn_kernel(TrainParams p) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
   extern __shared__ float4 w0s[];
   const int C4 = p.C >> 2;
   for (int i = threadIdx.x; i < C4; i += blockDim.x) w0s[i] = __ldg(reinterpret_cast<const float4*>(p.aw[0]) + i);
@@ -195,6 +208,8 @@ __device__ __forceinline__ void load_rows(float4 (&xr)[kPF], const float4* col, 
 // are in flight while the CTA works out the image's attention values.
 template <int RM>
 __global__ void __launch_bounds__(kPoolThreads, RM == 1 ? 2 : 1) train_pool_kernel(TrainParams p) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
   extern __shared__ float smem[];
   float* A = smem;                       // [R * HW]
   float* red = smem + p.R * p.HW;        // [32]
@@ -243,6 +258,8 @@ __global__ void __launch_bounds__(kPoolThreads, RM == 1 ? 2 : 1) train_pool_kern
 
 // g_r[v] = sum over the video's frames and row chunks (fixed order); s_r[v] likewise
 __global__ void __launch_bounds__(256) train_reduce_kernel(TrainParams p) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
   const int v = blockIdx.y, RC4 = p.R * (p.C >> 2);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int parts = p.F * p.J;
@@ -267,6 +284,8 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(TrainParams p) {
 // one channel slice (kSlices of them) for 32 videos x 32 classes per CTA out of shared memory, FINISH adds the slices in
 // order, the bias term and the scale.
 __global__ void __launch_bounds__(256) train_contract_kernel(TrainParams p) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int V = p.N / p.F, C = p.C, K = p.K, R = p.R;
@@ -291,13 +310,15 @@ __global__ void __launch_bounds__(256) train_contract_kernel(TrainParams p) {
     }
     __syncthreads();
     const float* g0 = gs + (warp * 4) * cs;
-#pragma unroll 4
-    for (int c = 0; c < cn; ++c) {
-      const float w = tws[c * 32 + lane];
-      acc[0] += g0[c] * w;
-      acc[1] += g0[cs + c] * w;
-      acc[2] += g0[2 * cs + c] * w;
-      acc[3] += g0[3 * cs + c] * w;
+#pragma unroll 2
+    for (int c = 0; c < cn; c += 4) {   // cn % 4 == 0
+      const float w0 = tws[c * 32 + lane], w1 = tws[(c + 1) * 32 + lane], w2 = tws[(c + 2) * 32 + lane],
+                  w3 = tws[(c + 3) * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 g = *reinterpret_cast<const float4*>(g0 + i * cs + c);
+        acc[i] += g.x * w0 + g.y * w1 + g.z * w2 + g.w * w3;
+      }
     }
   }
 #pragma unroll
@@ -307,6 +328,8 @@ __global__ void __launch_bounds__(256) train_contract_kernel(TrainParams p) {
   }
 }
 __global__ void __launch_bounds__(256) train_finish_kernel(TrainParams p) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
   const int V = p.N / p.F, K = p.K, R = p.R;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V * K) return;
@@ -318,16 +341,253 @@ __global__ void __launch_bounds__(256) train_finish_kernel(TrainParams p) {
   p.logits[i] = t / (float(p.HW) * float(p.F));
 }
 
+// kPF per-thread partial sums -> kPF block-wide sums in every thread (fixed order: xor butterfly inside a warp, then
+// the warps in order).  red: [17][kPF] floats.
+__device__ __forceinline__ void block_sum_rows(float (&v)[kPF], float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // 8 values over 32 lanes in 4 + 2 + 1 + 1 + 1 exchanges: each step halves the values a lane still carries
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  if ((lane & 3) == 0) red[warp * kPF + (lane >> 2)] = v[0];   // lane 4m carries value m
+  __syncthreads();
+  if (warp == 0 && lane < kPF) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += red[w * kPF + lane];
+    red[16 * kPF + lane] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kPF; ++i) v[i] = red[16 * kPF + i];
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// ---- One pass over X when the attention is local to a row (rank 1, relu / plain attention, channels <= 4 * blockDim).
+// Persistent CTAs (one per SM) walk items = (image, row chunk); thread = one float4 column, kPF rows per batch, and the
+// next batch's rows are in flight while the current batch is reduced and consumed (two register sets, ping-pong).
+struct Walk {
+  int item, hb;   // current item (b * J + j) and first row of the current batch
+};
+__device__ __forceinline__ bool walk_valid(const TrainParams& p, const Walk& w) { return w.item < p.N * p.J; }
+__device__ __forceinline__ int walk_h1(const TrainParams& p, const Walk& w) { return min(p.HW, (w.item % p.J + 1) * p.rows); }
+__device__ __forceinline__ Walk walk_next(const TrainParams& p, Walk w) {
+  w.hb += kPF;
+  if (w.hb >= walk_h1(p, w)) {
+    w.item += gridDim.x;
+    w.hb = (w.item % p.J) * p.rows;
+  }
+  return w;
+}
+// kPF rows of the thread's column for batch w.  No predicates: rows past the chunk re-read its last row and columns
+// past C re-read the last column; the consumers give those zero weight.
+__device__ __forceinline__ void walk_load(const TrainParams& p, const Walk& w, float4 (&xr)[kPF]) {
+  const int C4 = p.C >> 2;
+  if (walk_valid(p, w)) {
+    const int hl = walk_h1(p, w) - 1;
+    const float4* col = reinterpret_cast<const float4*>(p.X) + size_t(w.item / p.J) * p.HW * C4 + min(int(threadIdx.x), C4 - 1);
+#pragma unroll
+    for (int i = 0; i < kPF; ++i) xr[i] = __ldg(col + size_t(min(w.hb + i, hl)) * C4);
+  }
+}
+
+struct FwdState {
+  float4 w04, acc;
+  float c0, ssum;
+};
+// forward: the rows' dot products with w_0 are summed across the CTA, then the same registers feed the masked pooling.
+__device__ __forceinline__ void fwd_batch(const TrainParams& p, const Walk& w, bool act, const float4 (&xr)[kPF], FwdState& st,
+                                          float* red, bool item_ends) {
+  const int C4 = p.C >> 2, b = w.item / p.J, nr = walk_h1(p, w) - w.hb;   // rows of this batch that count
+  float part[kPF];
+#pragma unroll
+  for (int i = 0; i < kPF; ++i) part[i] = dot4(xr[i], st.w04);   // w04 == 0 in the columns past C
+  block_sum_rows(part, red);
+  const uint32_t g0 = uint32_t(b) * p.HW * C4 + uint32_t(w.hb) * C4 + threadIdx.x;   // group index of row hb (< 2^32, host check)
+#pragma unroll
+  for (int i = 0; i < kPF; ++i) {
+    const float a = part[i] + st.c0;
+    if (int(threadIdx.x) == i && i < nr) p.a0[size_t(b) * p.HW + w.hb + i] = a;
+    float A = (p.mode == MODE_RELU) ? fmaxf(a, 0.f) : a;
+    A = (i < nr) ? A : 0.f;
+    st.ssum += A;
+    const float4 x = xr[i];
+    if (p.drop.on) {
+      const uint32_t g = g0 + uint32_t(i) * C4;
+      const uint32_t ha = fmix32(g ^ p.drop.key0), hb2 = fmix32(g ^ p.drop.key1);
+      const float As = A * p.drop.scale;
+      st.acc.x = fmaf((ha & 0xFFFFu) < p.drop.thr ? As : 0.f, x.x, st.acc.x);
+      st.acc.y = fmaf((ha >> 16) < p.drop.thr ? As : 0.f, x.y, st.acc.y);
+      st.acc.z = fmaf((hb2 & 0xFFFFu) < p.drop.thr ? As : 0.f, x.z, st.acc.z);
+      st.acc.w = fmaf((hb2 >> 16) < p.drop.thr ? As : 0.f, x.w, st.acc.w);
+    } else {
+      st.acc.x = fmaf(A, x.x, st.acc.x); st.acc.y = fmaf(A, x.y, st.acc.y);
+      st.acc.z = fmaf(A, x.z, st.acc.z); st.acc.w = fmaf(A, x.w, st.acc.w);
+    }
+  }
+  if (item_ends) {
+    if (act) reinterpret_cast<float4*>(p.gpart)[size_t(w.item) * C4 + threadIdx.x] = st.acc;
+    if (threadIdx.x == 0) p.spart[w.item] = st.ssum;
+    st.acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    st.ssum = 0.f;
+  }
+}
+__global__ void __launch_bounds__(kPoolThreads, 1) train_fused_fwd_kernel(TrainParams p) {
+  __shared__ float red[17 * kPF];
+  griddep_launch_dependents();
+  griddep_wait();
+  const bool act = int(threadIdx.x) < (p.C >> 2);
+  FwdState st;
+  st.w04 = act ? __ldg(reinterpret_cast<const float4*>(p.aw[0]) + threadIdx.x) : make_float4(0.f, 0.f, 0.f, 0.f);
+  st.c0 = __ldg(p.ab[0]);
+  st.acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  st.ssum = 0.f;
+  Walk cur;
+  cur.item = blockIdx.x;
+  cur.hb = (cur.item % p.J) * p.rows;
+  float4 xa[kPF], xb[kPF];
+  walk_load(p, cur, xa);
+  while (walk_valid(p, cur)) {
+    Walk nxt = walk_next(p, cur);
+    walk_load(p, nxt, xb);
+    fwd_batch(p, cur, act, xa, st, red, nxt.item != cur.item);
+    cur = nxt;
+    if (!walk_valid(p, cur)) break;
+    nxt = walk_next(p, cur);
+    walk_load(p, nxt, xa);
+    fwd_batch(p, cur, act, xb, st, red, nxt.item != cur.item);
+    cur = nxt;
+  }
+}
+
+struct BwdState {
+  float4 w04, u4, dw;
+  float tt0, sd;
+  int par, v;
+};
+// backward: the rows' dot products with u[v] give dA, the row's delta follows locally (relu / plain), and the registers
+// that hold the rows produce dX and the CTA's part of dw_0.
+__device__ __forceinline__ void bwd_batch(const TrainParams& p, const Walk& w, bool act, const float4 (&xr)[kPF], BwdState& st,
+                                          float* red) {
+  const int C4 = p.C >> 2, HW = p.HW, b = w.item / p.J, nr = walk_h1(p, w) - w.hb;
+  if (b / p.F != st.v) {   // a new video: its u and t (u == 0 in the columns past C)
+    st.v = b / p.F;
+    st.u4 = act ? reinterpret_cast<const float4*>(p.u)[size_t(st.v) * C4 + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+    st.tt0 = p.tt[st.v];
+  }
+  float* avs = red + (17 + (st.par & 1)) * kPF;   // the rows' a_0, read after the barriers inside block_sum_rows
+  st.par ^= 1;
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kPF)
+    avs[threadIdx.x - 32] = (int(threadIdx.x) - 32 < nr) ? p.a0[size_t(b) * HW + w.hb + threadIdx.x - 32] : 0.f;
+  const uint32_t g0 = uint32_t(b) * HW * C4 + uint32_t(w.hb) * C4 + threadIdx.x;
+  uint32_t bits = 0xFFFFFFFFu;
+  float part[kPF];
+#pragma unroll
+  for (int i = 0; i < kPF; ++i) {
+    const float4 x = xr[i];
+    if (p.drop.on) {
+      const uint32_t g = g0 + uint32_t(i) * C4;
+      const uint32_t ha = fmix32(g ^ p.drop.key0), hb2 = fmix32(g ^ p.drop.key1);
+      const bool k0 = (ha & 0xFFFFu) < p.drop.thr, k1 = (ha >> 16) < p.drop.thr, k2 = (hb2 & 0xFFFFu) < p.drop.thr,
+                 k3 = (hb2 >> 16) < p.drop.thr;
+      bits = (bits << 4) | (k0 ? 1u : 0u) | (k1 ? 2u : 0u) | (k2 ? 4u : 0u) | (k3 ? 8u : 0u);   // row i ends up at nibble kPF-1-i
+      part[i] = ((k0 ? x.x * st.u4.x : 0.f) + (k1 ? x.y * st.u4.y : 0.f) + (k2 ? x.z * st.u4.z : 0.f) +
+                 (k3 ? x.w * st.u4.w : 0.f)) * p.drop.scale;
+    } else {
+      part[i] = dot4(x, st.u4);
+    }
+  }
+  block_sum_rows(part, red);
+  float4* dcol = (p.dX && act) ? reinterpret_cast<float4*>(p.dX) + size_t(b) * HW * C4 + size_t(w.hb) * C4 + threadIdx.x : nullptr;
+#pragma unroll
+  for (int i = 0; i < kPF; ++i) {
+    const float a = avs[i];
+    float d = part[i] + st.tt0;
+    if (p.mode == MODE_RELU) d = a > 0.f ? d : 0.f;
+    d = (i < nr) ? d : 0.f;
+    const float A = (p.mode == MODE_RELU) ? fmaxf(a, 0.f) : a;
+    st.sd += d;
+    const float4 x = xr[i];
+    st.dw.x = fmaf(d, x.x, st.dw.x); st.dw.y = fmaf(d, x.y, st.dw.y);
+    st.dw.z = fmaf(d, x.z, st.dw.z); st.dw.w = fmaf(d, x.w, st.dw.w);
+    if (dcol && i < nr) {
+      const float As = p.drop.on ? A * p.drop.scale : A;
+      const uint32_t nib = bits >> (4 * (kPF - 1 - i));
+      float4 t;
+      t.x = fmaf((nib & 1u) ? As : 0.f, st.u4.x, d * st.w04.x);
+      t.y = fmaf((nib & 2u) ? As : 0.f, st.u4.y, d * st.w04.y);
+      t.z = fmaf((nib & 4u) ? As : 0.f, st.u4.z, d * st.w04.z);
+      t.w = fmaf((nib & 8u) ? As : 0.f, st.u4.w, d * st.w04.w);
+      __stcs(dcol + size_t(i) * C4, t);
+    }
+  }
+}
+__global__ void __launch_bounds__(kPoolThreads, 1) bwd_fused_kernel(TrainParams p) {
+  __shared__ float red[19 * kPF];   // [17] block_sum_rows, [2] the rows' a_0 (double-buffered)
+  griddep_launch_dependents();
+  griddep_wait();
+  const int C4 = p.C >> 2;
+  const bool act = int(threadIdx.x) < C4;
+  BwdState st;
+  st.w04 = act ? __ldg(reinterpret_cast<const float4*>(p.aw[0]) + threadIdx.x) : make_float4(0.f, 0.f, 0.f, 0.f);
+  st.u4 = st.dw = make_float4(0.f, 0.f, 0.f, 0.f);
+  st.tt0 = st.sd = 0.f;
+  st.par = 0;
+  st.v = -1;
+  Walk cur;
+  cur.item = blockIdx.x;
+  cur.hb = (cur.item % p.J) * p.rows;
+  float4 xa[kPF], xb[kPF];
+  walk_load(p, cur, xa);
+  while (walk_valid(p, cur)) {
+    Walk nxt = walk_next(p, cur);
+    walk_load(p, nxt, xb);
+    bwd_batch(p, cur, act, xa, st, red);
+    cur = nxt;
+    if (!walk_valid(p, cur)) break;
+    nxt = walk_next(p, cur);
+    walk_load(p, nxt, xa);
+    bwd_batch(p, cur, act, xb, st, red);
+    cur = nxt;
+  }
+  // the CTA's parts of dw_0 and of dc_0 (one part per CTA)
+  if (act) reinterpret_cast<float4*>(p.dw0part)[size_t(blockIdx.x) * C4 + threadIdx.x] = st.dw;
+  if (threadIdx.x == 0) {
+    p.pch[size_t(blockIdx.x) * 2 + 0] = st.sd;
+    p.pch[size_t(blockIdx.x) * 2 + 1] = 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 // u_r[v, c] = B_r[c, :].G[v],  t_r[v] = d_r.G[v]  with G = dlogits / (HW F): 32 channels x 8 videos per CTA, the 32 rows
 // of B_r (contiguous in memory) and the 8 rows of G in shared memory; warp = video, lane = channel
-__global__ void __launch_bounds__(256) bwd_u_kernel(TrainParams p) {
-  extern __shared__ float sm[];
+__device__ __forceinline__ void bwd_u_block(const TrainParams& p, float* sm, int bx, int by, int r) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r = blockIdx.z, v0 = blockIdx.y * 8, c0 = blockIdx.x * 32, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
+  const int v0 = by * 8, c0 = bx * 32, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
   const int Kp = K | 1;             // odd row stride: lanes (channels) fall into distinct banks
+  const int K4 = (K + 3) & ~3;      // 16-byte aligned rows of G
   float* tws = sm;                  // [32][Kp]
-  float* Gs = sm + 32 * Kp;         // [8][K]
+  float* Gs = sm + 32 * Kp;         // [8][K4]
   const float scale = 1.f / (float(p.HW) * float(p.F));
   const int nc = min(32, C - c0);
 #pragma unroll 4
@@ -339,21 +599,25 @@ __global__ void __launch_bounds__(256) bwd_u_kernel(TrainParams p) {
   {
     const int v = min(v0 + warp, V - 1);
 #pragma unroll 4
-    for (int k = lane; k < K; k += 32) Gs[warp * K + k] = p.dlogits[size_t(v) * K + k] * scale;
+    for (int k = lane; k < K; k += 32) Gs[warp * K4 + k] = p.dlogits[size_t(v) * K + k] * scale;
   }
   __syncthreads();
   if (v0 + warp < V) {
-    const float* g = Gs + warp * K;
+    const float* g = Gs + warp * K4;
     if (lane < nc) {
       const float* t = tws + lane * Kp;
       float a0 = 0.f, a1 = 0.f;
       int k = 0;
-#pragma unroll 4
-      for (; k + 1 < K; k += 2) { a0 += g[k] * t[k]; a1 += g[k + 1] * t[k + 1]; }
-      if (k < K) a0 += g[k] * t[k];
+#pragma unroll 2
+      for (; k + 3 < K; k += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(g + k);
+        a0 += g4.x * t[k] + g4.z * t[k + 2];
+        a1 += g4.y * t[k + 1] + g4.w * t[k + 3];
+      }
+      for (; k < K; ++k) a0 += g[k] * t[k];
       p.u[(size_t(v0 + warp) * R + r) * C + c0 + lane] = a0 + a1;
     }
-    if (blockIdx.x == 0) {
+    if (bx == 0) {
       float t = 0.f;
       for (int k = lane; k < K; k += 32) t += g[k] * __ldg(p.tb[r] + k);
       t = warp_sum(t);
@@ -364,6 +628,8 @@ __global__ void __launch_bounds__(256) bwd_u_kernel(TrainParams p) {
 
 // pass 1 over X: dA_r[b, hw] = (mask * X[b, hw]).u_r[v] + t_r[v]; warp per row, u_r[v] through L1
 __global__ void __launch_bounds__(256) bwd_dattn_kernel(TrainParams p) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
   const int j = blockIdx.x, b = blockIdx.y, v = b / p.F, HW = p.HW, R = p.R, C4 = p.C >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h0 = j * p.rows, h1 = min(HW, h0 + p.rows);
@@ -401,6 +667,8 @@ __global__ void __launch_bounds__(256) bwd_dattn_kernel(TrainParams p) {
 //   dX[b, hw, :] = mask * sum_r A_r[hw] u_r[v] + delta_0[hw] w_0      and the CTA's part of dw_0 = sum delta_0 X
 template <int RM>
 __global__ void __launch_bounds__(kPoolThreads, RM == 1 ? 2 : 1) bwd_dx_kernel(TrainParams p) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
   extern __shared__ float smem[];
   const int HW = p.HW, R = p.R, C4 = p.C >> 2;
   float* A = smem;                 // [R * HW]
@@ -425,7 +693,8 @@ __global__ void __launch_bounds__(kPoolThreads, RM == 1 ? 2 : 1) bwd_dx_kernel(T
   float sd[RM], sda[RM];
 #pragma unroll
   for (int r = 0; r < RM; ++r) sd[r] = sda[r] = 0.f;
-  for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) {
+  const int h0c = j * p.rows, h1c = min(HW, h0c + p.rows);
+  for (int hw = h0c + threadIdx.x; hw < h1c; hw += blockDim.x) {   // delta of the CTA's own rows
     float da[RM];
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
@@ -447,18 +716,17 @@ __global__ void __launch_bounds__(kPoolThreads, RM == 1 ? 2 : 1) bwd_dx_kernel(T
       }
     d0[hw] = delta;
   }
-  if (j == 0) {   // the image's sums for dc_r and dw_r (r >= 1)
+  // the chunk's sums for dc_r and dw_r (r >= 1)
 #pragma unroll
-    for (int r = 0; r < RM; ++r)
-      if (r < R) {
-        const float s1 = block_sum(sd[r], red);
-        const float s2 = (r > 0) ? block_sum(sda[r], red) : 0.f;
-        if (threadIdx.x == 0) {
-          p.pch[(size_t(b) * 2 + 0) * R + r] = s1;
-          p.pch[(size_t(b) * 2 + 1) * R + r] = s2;
-        }
+  for (int r = 0; r < RM; ++r)
+    if (r < R) {
+      const float s1 = block_sum(sd[r], red);
+      const float s2 = (r > 0) ? block_sum(sda[r], red) : 0.f;
+      if (threadIdx.x == 0) {
+        p.pch[((size_t(b) * p.J + j) * 2 + 0) * R + r] = s1;
+        p.pch[((size_t(b) * p.J + j) * 2 + 1) * R + r] = s2;
       }
-  }
+    }
   __syncthreads();
   float4* dXb = p.dX ? reinterpret_cast<float4*>(p.dX) + size_t(b) * HW * C4 : nullptr;
   const uint64_t g4b = uint64_t(b) * HW * C4;
@@ -502,11 +770,10 @@ __global__ void __launch_bounds__(kPoolThreads, RM == 1 ? 2 : 1) bwd_dx_kernel(T
 
 // dB_r[c, k] = sum_v g_r[v, c] G[v, k];  dd_r[k] = sum_v s_r[v] G[v, k]: 32 channels x 256 classes per CTA pass, 32
 // videos at a time in shared memory; thread = class, 32 channel accumulators
-__global__ void __launch_bounds__(256) bwd_wgrad_kernel(TrainParams p) {
-  __shared__ float Gs[32][256];
-  __shared__ float4 gvs[32][8];
-  const int r = blockIdx.y, c0 = blockIdx.x * 32, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void bwd_wgrad_block(const TrainParams& p, float* sm, int bx, int r) {
+  float4(*gvs)[8] = reinterpret_cast<float4(*)[8]>(sm);            // [32][8] float4
+  float(*Gs)[256] = reinterpret_cast<float(*)[256]>(sm + 32 * 32);  // [32][256]
+  const int c0 = bx * 32, V = p.N / p.F, K = p.K, C = p.C, R = p.R;
   const float scale = 1.f / (float(p.HW) * float(p.F));
   const int nc = min(32, C - c0);   // a multiple of 4
   for (int kb = 0; kb < K; kb += 256) {
@@ -540,7 +807,7 @@ __global__ void __launch_bounds__(256) bwd_wgrad_kernel(TrainParams p) {
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (c < nc) p.d_tw[r][size_t(c0 + c) * K + k] = acc[c] * scale;
-      if (blockIdx.x == 0) {
+      if (bx == 0) {
         float t = 0.f;
 #pragma unroll 8
         for (int v = 0; v < V; ++v) t += p.sv[size_t(v) * R + r] * __ldg(p.dlogits + size_t(v) * K + k);
@@ -548,7 +815,17 @@ __global__ void __launch_bounds__(256) bwd_wgrad_kernel(TrainParams p) {
       }
     }
   }
-  (void)lane; (void)warp;
+}
+
+// Both need only dlogits and what the forward saved, and neither is bound by HBM: one launch, the CTAs of the two roles
+// side by side (first nW CTAs: the top-down convs' gradients, the longer role; the rest: u / t).
+__global__ void __launch_bounds__(256) bwd_small_kernel(TrainParams p, int nW, int cx, int vy) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
+  extern __shared__ __align__(16) float sm_small[];
+  const int i = blockIdx.x;
+  if (i < nW) bwd_wgrad_block(p, sm_small, i % cx, i / cx);
+  else bwd_u_block(p, sm_small, (i - nW) % cx, ((i - nW) / cx) % vy, (i - nW) / (cx * vy));
 }
 
 // Sum of `parts` rows of C floats in a fixed order: CTA (x, y) adds the parts of group y (`per` of them) for 32 float4
@@ -556,6 +833,8 @@ __global__ void __launch_bounds__(256) bwd_wgrad_kernel(TrainParams p) {
 // The second one also adds the images' sums for dc_r and dw_r (r >= 1).
 __global__ void __launch_bounds__(256) bwd_sum_kernel(TrainParams p, const float* __restrict__ src, float* __restrict__ dst,
                                                       int parts, int per, int final) {
+  griddep_launch_dependents();   // the next kernel of the call may be scheduled; it waits for this one to finish
+  griddep_wait();
   __shared__ float4 red[8][32];
   const int C4 = p.C >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -579,13 +858,16 @@ __global__ void __launch_bounds__(256) bwd_sum_kernel(TrainParams p, const float
     for (int w = 1; w < 8; ++w) { t.x += red[w][lane].x; t.y += red[w][lane].y; t.z += red[w][lane].z; t.w += red[w][lane].w; }
     reinterpret_cast<float4*>(dst)[size_t(blockIdx.y) * C4 + i] = t;
   }
-  if (final && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + 2 * p.R) {
-    const int jj = threadIdx.x - 32, which = jj / p.R, r = jj % p.R;
+  if (final && blockIdx.x == 0 && warp >= 1 && warp < 1 + 2 * p.R) {   // one warp per sum: lanes stride the chunks
+    const int jj = warp - 1, which = jj / p.R, r = jj % p.R;
     float t = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < p.N; ++b) t += p.pch[(size_t(b) * 2 + which) * p.R + r];
-    if (which == 0) p.d_ab[r][0] = t;
-    else if (r > 0) p.d_aw[r][0] = t;
+#pragma unroll 4
+    for (int q = lane; q < p.parts; q += 32) t += p.pch[(size_t(q) * 2 + which) * p.R + r];
+    t = warp_sum(t);
+    if (lane == 0) {
+      if (which == 0) p.d_ab[r][0] = t;
+      else if (r > 0) p.d_aw[r][0] = t;
+    }
   }
 }
 
@@ -604,7 +886,9 @@ Drop make_drop(const ApaTrain* t) {
   Drop d;
   const float keep = t ? t->dropout_keep : 1.f;
   d.on = keep < 1.f;
-  d.key = splitmix64(t ? t->dropout_seed : 0ull);
+  const uint64_t key = splitmix64(t ? t->dropout_seed : 0ull);
+  d.key0 = uint32_t(key);
+  d.key1 = uint32_t(key >> 32);
   double th = double(keep) * 65536.0 + 0.5;
   d.thr = th < 0 ? 0u : (th > 65536.0 ? 65536u : uint32_t(th));
   d.scale = 1.f / keep;
@@ -615,6 +899,7 @@ int train_supported(const ApaDesc* d) {
   int st = apa_attn_pool_check(d);
   if (st != APA_OK) return st;
   if ((d->flags & APA_FLAG_PER_CLASS) || !(d->flags & APA_FLAG_SINGLE_LAYER_ATT)) return APA_ERR_UNSUPPORTED;
+  if (double(d->batch) * d->hw * d->channels / 4.0 >= 4294967296.0) return APA_ERR_SHAPE;   // dropout counter is 32-bit
   if (size_t(d->rank) * d->hw * 2 + d->hw + 64 > 40000) return APA_ERR_SHAPE;   // per-image attention lives in smem
   if (size_t(d->num_classes) * 164 > 220 * 1024) return APA_ERR_SHAPE;   // bwd_u keeps 40 rows of K floats in smem
   return APA_OK;
@@ -657,7 +942,7 @@ Carve carve(const ApaDesc* d) {
   c.tt = o; o += al(V * R);
   c.dA = o; o += al(N * R * HW);
   c.dw0part = o; o += al(N * J * C + size_t(sum_groups(N * J)) * C);
-  c.pch = o; o += al(N * 2 * R);
+  c.pch = o; o += al(N * J * 2 * R);
   c.ws_total = o;
   return c;
 }
@@ -687,6 +972,19 @@ int fill(TrainParams& p, const ApaDesc* d, const ApaWeights* w, const ApaTrain* 
     cudaError_t e__ = (expr);                \
     if (e__ != cudaSuccess) return int(e__); \
   } while (0)
+
+// every kernel here starts with griddepcontrol.launch_dependents + griddepcontrol.wait: launched as programmatic
+// dependents, the launch latency of kernel n+1 hides behind kernel n
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 template <typename Kern>
 cudaError_t big_smem(Kern k, size_t bytes) {
@@ -733,27 +1031,28 @@ int apa_attn_pool_fwd_train(const ApaDesc* desc, const float* X, const ApaWeight
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long rows = long(p.N) * p.HW;
   const int V = p.N / p.F;
-  {
+  const bool fused = p.R == 1 && p.mode != MODE_SOFTMAX && (p.C / 4) <= kPoolThreads;
+  if (fused) {
+    APA_CUDA(launch_pdl(train_fused_fwd_kernel, dim3(std::min(p.N * p.J, kSMs)), dim3(kPoolThreads), 0, stream, p));
+  } else {
     const int grid = int(std::min<long>((rows + 7) / 8, 148 * 8));
-    train_attn_kernel<<<grid, 256, size_t(p.C) * 4, stream>>>(p);
-  }
-  {
+    APA_CUDA(launch_pdl(train_attn_kernel, dim3(grid), dim3(256), size_t(p.C) * 4, stream, p));
     const size_t smem = (size_t(p.R) * p.HW + 32) * 4;
     if (p.R == 1) {
       APA_CUDA(big_smem(train_pool_kernel<1>, smem));
-      train_pool_kernel<1><<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+      APA_CUDA(launch_pdl(train_pool_kernel<1>, dim3(p.J, p.N), dim3(kPoolThreads), smem, stream, p));
     } else {
       APA_CUDA(big_smem(train_pool_kernel<APA_MAX_RANK>, smem));
-      train_pool_kernel<APA_MAX_RANK><<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+      APA_CUDA(launch_pdl(train_pool_kernel<APA_MAX_RANK>, dim3(p.J, p.N), dim3(kPoolThreads), smem, stream, p));
     }
   }
-  train_reduce_kernel<<<dim3((p.R * (p.C / 4) + 255) / 256, V), 256, 0, stream>>>(p);
+  APA_CUDA(launch_pdl(train_reduce_kernel, dim3((p.R * (p.C / 4) + 255) / 256, V), dim3(256), 0, stream, p));
   {
     const int cs = (((p.C + kSlices - 1) / kSlices) + 3) & ~3;
     const size_t smem = size_t(cs) * 64 * 4;
     APA_CUDA(big_smem(train_contract_kernel, smem));
-    train_contract_kernel<<<dim3((p.K + 31) / 32, kSlices, (V + 31) / 32), 256, smem, stream>>>(p);
-    train_finish_kernel<<<(V * p.K + 255) / 256, 256, 0, stream>>>(p);
+    APA_CUDA(launch_pdl(train_contract_kernel, dim3((p.K + 31) / 32, kSlices, (V + 31) / 32), dim3(256), smem, stream, p));
+    APA_CUDA(launch_pdl(train_finish_kernel, dim3((V * p.K + 255) / 256), dim3(256), 0, stream, p));
   }
   APA_CUDA(cudaGetLastError());
   return APA_OK;
@@ -782,28 +1081,34 @@ int apa_attn_pool_bwd(const ApaDesc* desc, const float* X, const ApaWeights* wei
   if (reinterpret_cast<uintptr_t>(p.d_aw[0]) & 15u) return APA_ERR_ALIGN;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int V = p.N / p.F;
+  const bool fused = p.R == 1 && p.mode != MODE_SOFTMAX && (p.C / 4) <= kPoolThreads;
+  p.parts = fused ? std::min(p.N * p.J, kSMs) : p.N * p.J;
   {
-    const size_t smem = (size_t(32) * (p.K | 1) + size_t(8) * p.K) * 4;
-    APA_CUDA(big_smem(bwd_u_kernel, smem));
-    bwd_u_kernel<<<dim3((p.C + 31) / 32, (V + 7) / 8, p.R), 256, smem, stream>>>(p);
+    const int cx = (p.C + 31) / 32, vy = (V + 7) / 8, nU = cx * vy * p.R, nW = cx * p.R;
+    const size_t smem = std::max((size_t(32) * (p.K | 1) + size_t(8) * ((p.K + 3) & ~3)) * 4, size_t(36) * 1024);
+    APA_CUDA(big_smem(bwd_small_kernel, smem));
+    APA_CUDA(launch_pdl(bwd_small_kernel, dim3(nU + nW), dim3(256), smem, stream, p, nW, cx, vy));
   }
-  bwd_dattn_kernel<<<dim3(p.J, p.N), 256, 0, stream>>>(p);
-  {
+  if (fused) {
+    APA_CUDA(launch_pdl(bwd_fused_kernel, dim3(p.parts), dim3(kPoolThreads), 0, stream, p));
+  } else {
+    APA_CUDA(launch_pdl(bwd_dattn_kernel, dim3(p.J, p.N), dim3(256), 0, stream, p));
     const size_t smem = (size_t(2) * p.R * p.HW + p.HW + 32) * 4;
     if (p.R == 1) {
       APA_CUDA(big_smem(bwd_dx_kernel<1>, smem));
-      bwd_dx_kernel<1><<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+      APA_CUDA(launch_pdl(bwd_dx_kernel<1>, dim3(p.J, p.N), dim3(kPoolThreads), smem, stream, p));
     } else {
       APA_CUDA(big_smem(bwd_dx_kernel<APA_MAX_RANK>, smem));
-      bwd_dx_kernel<APA_MAX_RANK><<<dim3(p.J, p.N), kPoolThreads, smem, stream>>>(p);
+      APA_CUDA(launch_pdl(bwd_dx_kernel<APA_MAX_RANK>, dim3(p.J, p.N), dim3(kPoolThreads), smem, stream, p));
     }
   }
-  bwd_wgrad_kernel<<<dim3((p.C + 31) / 32, p.R), 256, 0, stream>>>(p);
   {
-    const int parts = p.N * p.J, groups = sum_groups(parts), per = (parts + groups - 1) / groups;
-    float* tmp = p.dw0part + size_t(parts) * p.C;
-    bwd_sum_kernel<<<dim3((p.C / 4 + 31) / 32, groups), 256, 0, stream>>>(p, p.dw0part, tmp, parts, per, 0);
-    bwd_sum_kernel<<<dim3((p.C / 4 + 31) / 32, 1), 256, 0, stream>>>(p, tmp, p.d_aw[0], groups, groups, 1);
+    const int parts = p.parts, groups = sum_groups(parts), per = (parts + groups - 1) / groups;
+    float* tmp = p.dw0part + size_t(p.N) * p.J * p.C;
+    const float* src = p.dw0part;
+    APA_CUDA(launch_pdl(bwd_sum_kernel, dim3((p.C / 4 + 31) / 32, groups), dim3(256), 0, stream, p, src, tmp, parts, per, 0));
+    const float* tmpc = tmp;
+    APA_CUDA(launch_pdl(bwd_sum_kernel, dim3((p.C / 4 + 31) / 32, 1), dim3(256), 0, stream, p, tmpc, p.d_aw[0], groups, groups, 1));
   }
   APA_CUDA(cudaGetLastError());
   return APA_OK;

@@ -256,8 +256,10 @@ int apa_attn_pool_bwd(const ApaDesc* desc, const float* X, const ApaWeights* wei
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* The dropout mask the two calls above apply, materialised: mask[i] for the first `count` elements of X in
- * row-major order (count % 4 == 0).  With h = splitmix64(splitmix64(seed) + i / 4), element i is kept iff the
- * 16-bit field (h >> 16 * (i % 4)) & 0xFFFF is below round(keep * 65536); kept elements carry 1 / keep.    */
+ * row-major order (count % 4 == 0, count / 4 < 2^32).  With key = splitmix64(seed), g = i / 4,
+ * a = fmix32(g ^ low32(key)), b = fmix32(g ^ high32(key)) (fmix32 = murmur3's 32-bit finaliser), the four elements
+ * of group g take the 16-bit fields a & 0xFFFF, a >> 16, b & 0xFFFF, b >> 16; an element is kept iff its field is
+ * below round(keep * 65536); kept elements carry 1 / keep.                                                  */
 int apa_dropout_mask(const ApaTrain* train, size_t count, float* mask, void* stream);
 
 /* Full second-order pooling G[b] = X[b]^T X[b]  ([batch, C, C], symmetric).  Not present in the

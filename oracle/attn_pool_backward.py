@@ -43,19 +43,32 @@ def _splitmix64(z):
         return z ^ (z >> np.uint64(31))
 
 
+def _fmix32(h):
+    """murmur3's 32-bit finaliser on uint32 arrays."""
+    with np.errstate(over="ignore"):
+        h = h ^ (h >> np.uint32(16))
+        h = (h * np.uint32(0x85EBCA6B)).astype(np.uint32)
+        h = h ^ (h >> np.uint32(13))
+        h = (h * np.uint32(0xC2B2AE35)).astype(np.uint32)
+        return h ^ (h >> np.uint32(16))
+
+
 def dropout_mask(seed, shape, keep):
-    """mask[i] (row-major element index i) = 1/keep if the 16-bit field (h >> 16*(i%4)) & 0xFFFF of
-    h = splitmix64(splitmix64(seed) + i//4) is below round(keep*65536), else 0.  float32, like the kernels."""
+    """include/apa.h apa_dropout_mask restated: key = splitmix64(seed); for group g = i // 4,
+    a = fmix32(g ^ low32(key)), b = fmix32(g ^ high32(key)); the group's four elements take the 16-bit fields
+    a & 0xFFFF, a >> 16, b & 0xFFFF, b >> 16 and are kept (value 1/keep) iff the field < round(keep * 65536)."""
     n = int(np.prod(shape))
     if n % 4:
         raise ValueError("element count must be a multiple of 4")
     if keep >= 1.0:
         return np.ones(shape, dtype=np.float32)
-    key = _splitmix64(np.array([int(seed) & _M64], dtype=np.uint64))[0]
-    with np.errstate(over="ignore"):
-        h = _splitmix64((np.arange(n // 4, dtype=np.uint64) + key).astype(np.uint64))
-    thr = np.uint64(int(float(np.float32(keep)) * 65536.0 + 0.5))
-    fields = np.stack([(h >> np.uint64(16 * i)) & np.uint64(0xFFFF) for i in range(4)], axis=1).reshape(-1)
+    key = int(_splitmix64(np.array([int(seed) & _M64], dtype=np.uint64))[0])
+    g = np.arange(n // 4, dtype=np.uint32)
+    a = _fmix32(g ^ np.uint32(key & 0xFFFFFFFF))
+    b = _fmix32(g ^ np.uint32(key >> 32))
+    fields = np.stack([a & np.uint32(0xFFFF), a >> np.uint32(16), b & np.uint32(0xFFFF), b >> np.uint32(16)],
+                      axis=1).reshape(-1)
+    thr = np.uint32(int(float(np.float32(keep)) * 65536.0 + 0.5))
     scale = np.float32(1.0) / np.float32(keep)
     return np.where(fields < thr, scale, np.float32(0)).astype(np.float32).reshape(shape)
 

@@ -80,3 +80,20 @@ def test_forward_train_without_mask_is_the_eval_forward():
     got = bwd.forward_train_torch(torch.tensor(X), Pt, fl, 7, 2).numpy()
     ref, _ = orc.attn_pool_head(X, params, fl, 7, frames_per_video=2, want_pose=False)
     np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-13)
+
+
+def test_dropout_mask_restatement_is_a_fair_bernoulli():
+    """oracle.dropout_mask (the NumPy restatement of include/apa.h apa_dropout_mask): keep rate, scale, independence
+    between the four fields of a group, between neighbouring groups and between seeds."""
+    from oracle import attn_pool_backward as bwd
+    m = bwd.dropout_mask(77, (8, 196, 2048), 0.2)
+    k = m > 0
+    assert set(np.unique(m)) == {np.float32(0), np.float32(5)}
+    assert abs(k.mean() - 0.2) < 2e-3 and abs(m.mean() - 1.0) < 1e-2
+    g = k.reshape(-1, 4)
+    for i in range(4):
+        for j in range(i + 1, 4):
+            assert abs((g[:, i] & g[:, j]).mean() - 0.04) < 2e-3
+    assert abs((k[:, :, :-4] & k[:, :, 4:]).mean() - 0.04) < 2e-3          # neighbouring groups
+    assert abs((k & (bwd.dropout_mask(78, (8, 196, 2048), 0.2) > 0)).mean() - 0.04) < 2e-3   # another step's seed
+    assert np.array_equal(bwd.dropout_mask(77, (8, 196, 2048), 1.0), np.ones((8, 196, 2048), np.float32))

@@ -53,6 +53,8 @@ ABI_SYMBOLS = (
     "apa_attn_pool_fwd_train",
     "apa_attn_pool_bwd",
     "apa_dropout_mask",
+    "apa_eval_tail",
+    "apa_mean_ap",
     "apa_gram_fwd",
     "apa_attn_pool_plan",
 )
@@ -196,6 +198,11 @@ def _load():
                                       c.c_size_t, c.c_void_p]
     lib.apa_dropout_mask.restype = c.c_int
     lib.apa_dropout_mask.argtypes = [c.POINTER(ApaTrain), c.c_size_t, c.c_void_p, c.c_void_p]
+    lib.apa_eval_tail.restype = c.c_int
+    lib.apa_eval_tail.argtypes = [c.c_int32, c.c_int32, c.c_void_p, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p,
+                                  c.c_void_p, c.c_void_p]
+    lib.apa_mean_ap.restype = c.c_int
+    lib.apa_mean_ap.argtypes = [c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.apa_gram_fwd.restype = c.c_int
     lib.apa_gram_fwd.argtypes = [c.c_int32, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.apa_attn_pool_plan.restype = c.c_int
@@ -563,6 +570,51 @@ class AttnPoolTrainOp(AttnPoolOp):
         if st != APA_OK:
             raise ApaError(st, "apa_attn_pool_bwd")
         return dX, grads
+
+
+APA_EVAL_SOFTMAX = 0
+APA_EVAL_SIGMOID = 1
+APA_AP_MAX_SAMPLES = 16384
+
+
+def eval_tail(logits, labels=None, counts=None, multi_label=False, want_probs=True):
+    """What eval.py:193-203 does with a batch of logits: returns (predictions int32 [rows], probs [rows, K] or None).
+    With `labels` (int32 [rows]) the hits and the rows seen are added to `counts` (uint64 [2], zeroed by the caller
+    before the first batch): counts[0] / counts[1] is the streaming accuracy."""
+    import torch
+    logits = logits.contiguous()
+    rows, K = logits.shape
+    pred = torch.empty((rows,), dtype=torch.int32, device=logits.device)
+    probs = torch.empty_like(logits) if want_probs else None
+    if (labels is None) != (counts is None):
+        raise ValueError("labels and counts go together")
+    if labels is not None:
+        if labels.dtype != torch.int32 or counts.dtype not in (torch.int64, torch.uint64) or counts.numel() < 2:
+            raise TypeError("labels must be int32 and counts a 64-bit integer tensor of 2 words")
+        labels = labels.contiguous()
+    st = _lib.apa_eval_tail(rows, K, _ptr(logits), APA_EVAL_SIGMOID if multi_label else APA_EVAL_SOFTMAX,
+                            _ptr(probs), _ptr(pred), _ptr(labels), _ptr(counts),
+                            ctypes.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream))
+    if st != APA_OK:
+        raise ApaError(st, "apa_eval_tail")
+    return pred, probs
+
+
+def mean_ap(scores, labels):
+    """compute_map of the reference (eval.py:305 -> eval/utils.py:4-16) on the GPU: returns (mAP, class APs float64
+    [K] with -1 for classes without positives) as tensors; scores float32 [samples, K], labels int32 [samples]."""
+    import torch
+    scores, labels = scores.contiguous(), labels.contiguous()
+    if scores.dtype != torch.float32 or labels.dtype != torch.int32:
+        raise TypeError("scores must be float32 and labels int32")
+    n, K = scores.shape
+    aps = torch.empty((K,), dtype=torch.float64, device=scores.device)
+    out = torch.empty((2,), dtype=torch.float64, device=scores.device)
+    st = _lib.apa_mean_ap(n, K, _ptr(scores), _ptr(labels), _ptr(aps), _ptr(out),
+                          ctypes.c_void_p(torch.cuda.current_stream(scores.device).cuda_stream))
+    if st != APA_OK:
+        raise ApaError(st, "apa_mean_ap")
+    return out[0], aps
 
 
 def peer_gather_wait(gather_struct, lag, stream):

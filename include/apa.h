@@ -262,6 +262,24 @@ int apa_attn_pool_bwd(const ApaDesc* desc, const float* X, const ApaWeights* wei
  * below round(keep * 65536); kept elements carry 1 / keep.                                                  */
 int apa_dropout_mask(const ApaTrain* train, size_t count, float* mask, void* stream);
 
+/* ---- evaluation tail: what eval.py does with the logits.
+ * apa_eval_tail: per row, predictions = argmax(logits) (first maximum, eval.py:193) and probs = softmax(logits)
+ * (eval.py:197) or sigmoid(logits) for the multi-label losses (:195); with labels, counts[0] += hits and
+ * counts[1] += rows (the streaming accuracy of :200-203; zero the two words before the first batch).
+ * probs / predictions / labels+counts are each optional (NULL).                                            */
+enum { APA_EVAL_SOFTMAX = 0, APA_EVAL_SIGMOID = 1 };
+int apa_eval_tail(int32_t rows, int32_t num_classes, const float* logits, int32_t activation, float* probs,
+                  int32_t* predictions, const int32_t* labels, unsigned long long* counts, void* stream);
+
+/* Mean average precision over all collected scores (eval.py:303-306 -> eval/utils.py:4-16 compute_map ->
+ * eval/cap_eval_utils.py:55-109): scores [samples, K], labels [samples] (class index); class_ap [K] receives the
+ * one-vs-rest VOC AP of each class in float64 (-1 for a class without positives, which the mean skips);
+ * mean_ap[0] = mAP, mean_ap[1] = number of classes averaged.  samples <= APA_AP_MAX_SAMPLES (the scores of one
+ * class are sorted in shared memory; MPII's validation split has 6988).                                     */
+#define APA_AP_MAX_SAMPLES 16384
+int apa_mean_ap(int32_t samples, int32_t num_classes, const float* scores, const int32_t* labels, double* class_ap,
+                double* mean_ap, void* stream);
+
 /* Full second-order pooling G[b] = X[b]^T X[b]  ([batch, C, C], symmetric).  Not present in the
  * reference code; defined from the paper's second-order pooling equation (BASELINE config 5). */
 int apa_gram_fwd(int32_t batch, int32_t hw, int32_t channels, const float* X, float* G,

@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over small shapes of every kernel family (scripts/sanitize_cases.py); summaries -> gpurun_out/
-# usage: gpu_sanitize.sh [flow|cluster|dense|all] [tools...]      (default: all memcheck racecheck synccheck)
+# usage: gpu_sanitize.sh [flow|cluster|dense|train|all] [tools...]      (default: all memcheck racecheck synccheck)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 which=${1:-all}; shift

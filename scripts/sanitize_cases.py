@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small shapes of every kernel family, for compute-sanitizer (scripts/gpu_sanitize.sh): each form of the single-map
-head, the fused all-gather on one rank, the dense path on the tcgen05 GEMM, the Gram.  Each case is checked against
+head, the fused all-gather on one rank, the dense path on the tcgen05 GEMM, the Gram, the training path, the eval tail.  Each case is checked against
 the oracle so a sanitizer-clean run is also a correct one."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -65,4 +65,43 @@ if which in ("all", "dense"):
     err = orc.rel_err(G.cpu().numpy(), orc.gram(Xg.cpu().numpy()))
     print("%-36s rel err %.2e" % ("gram 2 x 64 x 256", err), flush=True)
     assert err <= 1e-4
+if which in ("all", "train"):
+    from oracle import attn_pool_backward as bwd, eval_tail as et
+
+    def train(name, B, HW, C, K, flags, F=1, keep=0.2):
+        fl = dict(orc.DEFAULT_FLAGS, **flags)
+        params = orc.make_params(K, C, flags=fl, seed=3)
+        bits, rank = ops.flags_from_cfg_net(fl)
+        rng = np.random.RandomState(1)
+        X = np.maximum(rng.randn(B, HW, C), 0).astype(np.float32)
+        dl = rng.randn(B // F, K).astype(np.float32)
+        op = ops.AttnPoolTrainOp({k: torch.from_numpy(v) for k, v in params.items()}, K, HW, channels=C, frames=F,
+                                 rank=rank, flags=bits, device="cuda:0")
+        tr = ops.make_train(keep, 9)
+        for _ in range(2):
+            op.forward(torch.from_numpy(X).cuda(), tr)
+            dX, grads = op.backward(torch.from_numpy(dl).cuda())
+        torch.cuda.synchronize()
+        mask = bwd.dropout_mask(9, X.shape, keep)
+        ref_dX, ref_g = bwd.backward_autograd(X, params, fl, K, dl, frames_per_video=F, dropout_mask=mask)
+        err = max([orc.rel_err(dX.cpu().numpy(), ref_dX)] +
+                  [float(np.abs(grads[n].cpu().numpy().reshape(g.shape) - g).max() / max(np.abs(g).max(), 1e-3))
+                   for n, g in ref_g.items()])
+        print("%-36s rel err %.2e %s" % (name, err, "OK" if err <= 1e-4 else "MISMATCH"), flush=True)
+        assert err <= 1e-4
+
+    train("train one-pass relu b6", 6, 49, 2048, 37, S)
+    train("train one-pass plain c512 frames2", 4, 30, 512, 33, dict(S, RELU_ATT=False), F=2, keep=0.5)
+    train("train two-pass softmax", 3, 25, 2048, 37, dict(S, SOFTMAX_ATT=True))
+    train("train two-pass rank 3", 3, 25, 1024, 37, dict(S, RANK=3))
+    x = torch.randn((19, 37), device="cuda")
+    lab = torch.randint(0, 37, (19,), device="cuda", dtype=torch.int32)
+    cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    pred, probs = ops.eval_tail(x, lab, cnt)
+    mAP, aps = ops.mean_ap(x, lab)
+    torch.cuda.synchronize()
+    ref_map, ref_aps = et.compute_map(x.cpu().numpy(), lab.cpu().numpy())
+    err = float(np.abs(aps.cpu().numpy() - ref_aps).max())
+    print("%-36s rel err %.2e" % ("eval tail + mAP 19 x 37", err), flush=True)
+    assert err <= 1e-12 and np.array_equal(pred.cpu().numpy(), et.predictions(x.cpu().numpy()))
 print("SANITIZE_CASES_DONE", flush=True)

@@ -399,22 +399,32 @@ apa_flow_reduce_kernel(const FusedParams p) {
   int lo, hi;
   flow_image_ctas(N, G, HW, b, &lo, &hi);
   const int n = p.fl_ng * (hi - lo + 1), s0 = p.fl_ng * (lo + b);   // partials of image b (runs x consumer groups), first slot
+  // the image's statistics: lanes stride the partials (all loads of a lane in flight together), butterfly in a fixed
+  // order; a serial loop here would cost one L2 round trip per partial
+  const int lane = tid & 31, warp = tid >> 5;
   if (SOFTMAX) {
     float M = -INFINITY;
-    for (int e = 0; e < n; ++e) M = fmaxf(M, __ldcg(gstat + size_t(s0 + e) * 8 + 4));
+    for (int e = lane; e < n; e += 32) M = fmaxf(M, __ldcg(gstat + size_t(s0 + e) * 8 + 4));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
     float S = 0.f;
-    for (int e = 0; e < n; ++e) S += expf(__ldcg(gstat + size_t(s0 + e) * 8 + 4) - M) * __ldcg(gstat + size_t(s0 + e) * 8);
+    for (int e = lane; e < n; e += 32)
+      S += expf(__ldcg(gstat + size_t(s0 + e) * 8 + 4) - M) * __ldcg(gstat + size_t(s0 + e) * 8);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
     for (int e = tid; e < n; e += kRThreads) scl[e] = expf(__ldcg(gstat + size_t(s0 + e) * 8 + 4) - M) / S;
     if (tid == 0 && blockIdx.y == 0) {
       gsum[size_t(b) * 4] = 1.f;
       if (p.smx != nullptr) { p.smx[2 * b] = M; p.smx[2 * b + 1] = S; }
     }
     __syncthreads();
-  } else if (tid < 4 && blockIdx.y == 0) {
+  } else if (warp < 4 && blockIdx.y == 0) {
     float mass = 0.f;
-    if (tid < R)
-      for (int e = 0; e < n; ++e) mass += __ldcg(gstat + size_t(s0 + e) * 8 + tid);
-    gsum[size_t(b) * 4 + tid] = mass;
+    if (warp < R)
+      for (int e = lane; e < n; e += 32) mass += __ldcg(gstat + size_t(s0 + e) * 8 + warp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mass += __shfl_xor_sync(0xffffffffu, mass, o);
+    if (lane == 0) gsum[size_t(b) * 4 + warp] = mass;
   }
   if (c < C) {
     for (int j = 0; j < R; ++j) {
@@ -479,6 +489,7 @@ apa_flow_contract_kernel(const FusedParams p) {
   }
   auto load_w = [&](int j) {
     const float* W = p.td_w[j];
+#pragma unroll 8
     for (int idx = tid; idx < CH * kKW; idx += kCThreads) {
       const int c = idx / kKW, kk = idx - c * kKW;
       Ws[idx] = (kk < width) ? __ldg(W + size_t(c_base + c) * K + k_lo + kk) : 0.f;

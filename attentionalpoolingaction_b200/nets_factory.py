@@ -93,10 +93,27 @@ def _run_head(state, images, params, flags, rank, num_classes, num_pose_keypoint
                             device=images.device)
         state[key] = op
     want = set(end_point_names)
+    per_frame = frames_per_video > 1 and (want & {"Logits", "logits_beforePool"})
+    if per_frame:
+        # nets_factory.py:352,357: with several frames per video the reference's end_points['Logits'] and
+        # ['logits_beforePool'] are the UN-pooled [B*F, K] logits and only the returned tensor is the frame mean
+        # (:354-374).  The fast path pools inside the kernel, so these two end-points cost a frames=1 call and the
+        # mean is taken from its result (same numbers up to fp32 rounding).
+        key1 = (HW, C, 1)
+        op1 = state.get(key1)
+        if op1 is None:
+            op1 = ops.AttnPoolOp(params, num_classes, HW, channels=C, frames=1, rank=rank, flags=flags,
+                                 num_pose_keypoints=num_pose_keypoints, tuning=tuning, device=images.device)
+            state[key1] = op1
+        op = op1
     logits, eps = op(images.reshape(B, HW, C),
                      want_attn="PosePrelogitsBasedAttention" in want,
                      want_topdown="TopDownAttention" in want,
                      want_pose="PoseLogits" in want)
+    if per_frame:
+        eps["Logits"] = logits
+        eps["logits_beforePool"] = logits
+        logits = logits.reshape(B // frames_per_video, frames_per_video, -1).mean(dim=1)
     if H is not None:   # restore the spatial axes the reference's end-points carry
         for k in ("PosePrelogitsBasedAttention", "TopDownAttention", "PoseLogits"):
             if k in eps:
@@ -148,6 +165,16 @@ def _run_head_train(state, images, params, flags, rank, num_classes, keep, seed,
 
 
 _HEAD_STATE = {}   # id(params) -> (params, {shape key -> AttnPoolOp}); holds the dict so the id stays unique
+_HEAD_STATE_MAX = 8
+
+
+def invalidate_head_cache(params=None):
+    """Drop the device copies `attn_pool_head` keeps: of one `params` object (after its arrays were reloaded or
+    updated in place) or of all of them."""
+    if params is None:
+        _HEAD_STATE.clear()
+    else:
+        _HEAD_STATE.pop(id(params), None)
 
 
 def attn_pool_head(X, params, cfg_net_flags, num_classes, is_training=False, frames_per_video=1,
@@ -157,7 +184,8 @@ def attn_pool_head(X, params, cfg_net_flags, num_classes, is_training=False, fra
     X: float32 CUDA tensor `[B*F, H, W, C]` or `[B*F, HW, C]`; `params`: TF variable name -> array/tensor
     (nets_factory.py:260-269, :300-303, :151-159); `cfg_net_flags`: `cfg.NET`-like object or dict with the
     `USE_POSE_PRELOGITS_BASED_ATTENTION_*` flags (src/config.py:182-209).  The device-resident copy of the
-    variables and the workspace are cached per `params` object, so repeated calls cost one kernel launch.
+    variables and the workspace are cached per (`params` object, flags, tuning) — at most 8 `params` objects; call
+    `invalidate_head_cache(params)` after updating the arrays of a `params` dict in place.
     """
     if params is None:
         raise ValueError("params (TF variable name -> array) is required: the head has trained variables")
@@ -167,8 +195,11 @@ def attn_pool_head(X, params, cfg_net_flags, num_classes, is_training=False, fra
                                   "seed and autograd plumbing it sets up")
     entry = _HEAD_STATE.get(id(params))
     if entry is None or entry[0] is not params:
+        while len(_HEAD_STATE) >= _HEAD_STATE_MAX:       # bounded: the oldest entry goes first
+            _HEAD_STATE.pop(next(iter(_HEAD_STATE)))
         entry = (params, {})
         _HEAD_STATE[id(params)] = entry
-    state = entry[1].setdefault((flags, rank, int(num_classes), int(num_pose_keypoints)), {})
+    tkey = bytes(tuning) if tuning is not None else None   # ApaTuning is a ctypes struct: its bytes are its value
+    state = entry[1].setdefault((flags, rank, int(num_classes), int(num_pose_keypoints), tkey), {})
     return _run_head(state, X, params, flags, rank, num_classes, num_pose_keypoints, end_point_names, tuning,
                      frames_per_video=frames_per_video)

@@ -335,6 +335,11 @@ def test_network_fn_shim():
                                                frames_per_video=3)
     orc.assert_parity(logits2.cpu().numpy(), ref, TOL)
     assert list(ep2) == ["Logits"]
+    # the reference's per-frame end-points (nets_factory.py:352,357): un-pooled logits on request
+    logits3, ep3 = fn(images, end_point_names=("logits_beforePool",))
+    assert tuple(ep3["logits_beforePool"].shape) == (6, 393) and ep3["Logits"] is ep3["logits_beforePool"]
+    orc.assert_parity(ep3["logits_beforePool"].cpu().numpy(), ref_ep["logits_beforePool"], TOL)
+    orc.assert_parity(logits3.cpu().numpy(), ref, TOL)
 
 
 def test_gram_matches_oracle():

@@ -126,6 +126,21 @@ def test_head_call_logic_with_a_stand_in_op(monkeypatch):
         nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), params, flags, 600, is_training=True)
     with pytest.raises(ValueError):
         nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), None, flags, 600)
+    # per-frame end-points (nets_factory.py:352,357): 'Logits' / 'logits_beforePool' are the UN-pooled logits
+    logits, eps = nets_factory.attn_pool_head(torch.zeros(20, 7, 7, 2048), params, flags, 600, frames_per_video=10,
+                                              end_point_names=("logits_beforePool",))
+    assert logits.shape == (2, 600) and eps["logits_beforePool"].shape == (20, 600) and eps["Logits"].shape == (20, 600)
+    assert built[-1].args["F"] == 1                                         # ... served by a frames=1 op
+    # a different tuning is a different cache entry; invalidation drops the device copies of one params object
+    n1 = len(built)
+    nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), params, flags, 600, tuning=ops.make_tuning(stream_ctas=37))
+    assert len(built) == n1 + 1
+    nets_factory.invalidate_head_cache(params)
+    nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), params, flags, 600)
+    assert len(built) == n1 + 2
+    for i in range(12):                                                     # bounded: at most 8 params objects kept
+        nets_factory.attn_pool_head(torch.zeros(8, 49, 2048), {"dummy": i}, flags, 600)
+    assert len(nets_factory._HEAD_STATE) <= 8
 
 
 def test_shard_bounds_cover_batch_exactly():

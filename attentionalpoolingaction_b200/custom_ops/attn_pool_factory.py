@@ -53,6 +53,8 @@ ABI_SYMBOLS = (
     "apa_attn_pool_fwd_train",
     "apa_attn_pool_bwd",
     "apa_dropout_mask",
+    "apa_softmax_xent_loss",
+    "apa_pose_l2_loss",
     "apa_eval_tail",
     "apa_mean_ap",
     "apa_gram_fwd",
@@ -198,6 +200,12 @@ def _load():
                                       c.c_size_t, c.c_void_p]
     lib.apa_dropout_mask.restype = c.c_int
     lib.apa_dropout_mask.argtypes = [c.POINTER(ApaTrain), c.c_size_t, c.c_void_p, c.c_void_p]
+    lib.apa_softmax_xent_loss.restype = c.c_int
+    lib.apa_softmax_xent_loss.argtypes = [c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_float, c.c_void_p, c.c_void_p,
+                                          c.c_void_p, c.c_void_p]
+    lib.apa_pose_l2_loss.restype = c.c_int
+    lib.apa_pose_l2_loss.argtypes = [c.c_int32, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_float,
+                                     c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.apa_eval_tail.restype = c.c_int
     lib.apa_eval_tail.argtypes = [c.c_int32, c.c_int32, c.c_void_p, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p,
                                   c.c_void_p, c.c_void_p]
@@ -570,6 +578,45 @@ class AttnPoolTrainOp(AttnPoolOp):
         if st != APA_OK:
             raise ApaError(st, "apa_attn_pool_bwd")
         return dX, grads
+
+
+def softmax_xent_loss(logits, labels, weight=1.0, want_grad=True):
+    """loss.py:72-79 (softmax-xentropy action loss): returns (loss 0-d tensor, dlogits or None).  `dlogits` is what
+    AttnPoolTrainOp.backward takes."""
+    import torch
+    logits, labels = logits.contiguous(), labels.contiguous()
+    if labels.dtype != torch.int32:
+        raise TypeError("labels must be int32")
+    rows, K = logits.shape
+    row_loss = torch.empty((rows,), dtype=torch.float32, device=logits.device)
+    loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
+    grad = torch.empty_like(logits) if want_grad else None
+    st = _lib.apa_softmax_xent_loss(rows, K, _ptr(logits), _ptr(labels), float(weight), _ptr(row_loss), _ptr(loss),
+                                    _ptr(grad), ctypes.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream))
+    if st != APA_OK:
+        raise ApaError(st, "apa_softmax_xent_loss")
+    return loss[0], grad
+
+
+def pose_l2_loss(pose_logits, pose_labels, valid, weight=1.0, want_grad=True):
+    """loss.py:29-70 (masked L2 heat-map loss, un-sampled): pose_logits / pose_labels [B, HW, Kp] (or [B, H, W, Kp]),
+    valid [B, Kp] bool / uint8.  Returns (loss 0-d tensor, d loss / d pose_logits or None)."""
+    import torch
+    shape = pose_logits.shape
+    x = pose_logits.reshape(shape[0], -1, shape[-1]).contiguous()
+    y = pose_labels.reshape(shape[0], -1, shape[-1]).contiguous()
+    if x.shape != y.shape:
+        raise ValueError("labels must have the logits' size (the reference resizes them otherwise, loss.py:14-22)")
+    v = valid.to(torch.uint8).contiguous()
+    B, HW, Kp = x.shape
+    row_loss = torch.empty((B,), dtype=torch.float32, device=x.device)
+    loss = torch.empty((1,), dtype=torch.float32, device=x.device)
+    grad = torch.empty_like(x) if want_grad else None
+    st = _lib.apa_pose_l2_loss(B, HW, Kp, _ptr(x), _ptr(y), _ptr(v), float(weight), _ptr(row_loss), _ptr(loss), _ptr(grad),
+                               ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if st != APA_OK:
+        raise ApaError(st, "apa_pose_l2_loss")
+    return loss[0], (grad.reshape(shape) if grad is not None else None)
 
 
 APA_EVAL_SOFTMAX = 0

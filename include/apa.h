@@ -262,6 +262,20 @@ int apa_attn_pool_bwd(const ApaDesc* desc, const float* X, const ApaWeights* wei
  * below round(keep * 65536); kept elements carry 1 / keep.                                                  */
 int apa_dropout_mask(const ApaTrain* train, size_t count, float* mask, void* stream);
 
+/* ---- the losses behind the head in training (train.py:404-411 -> loss.py).
+ * apa_softmax_xent_loss: loss.py:72-79, tf.losses.softmax_cross_entropy(onehot(labels), logits, weights=weight):
+ *   loss[0] = weight / rows * sum_i (logsumexp(logits[i]) - logits[i, labels[i]]);  dlogits (optional) = d loss / d logits
+ *   -- what apa_attn_pool_bwd takes.  row_loss [rows] is a caller scratch that receives the per-row losses.
+ * apa_pose_l2_loss: loss.py:29-70 with cfg.TRAIN.LOSS_FN_POSE_SAMPLED off: pose_logits / pose_labels
+ *   [batch, hw, keypoints] (end_points['PoseLogits'], nets_factory.py:158-160, and the heat-map labels of the same size),
+ *   valid [batch, keypoints] bytes (labels_pose_valid);  loss[0] = weight * sum_c mean_b ( valid[b,c] * 0.5 *
+ *   sum_hw (logit - label)^2 / hw );  dpose (optional) = d loss / d pose_logits.  row_loss [batch] scratch.
+ * Both add the per-row values in index order (bit-reproducible).                                              */
+int apa_softmax_xent_loss(int32_t rows, int32_t num_classes, const float* logits, const int32_t* labels, float weight,
+                          float* row_loss, float* loss, float* dlogits, void* stream);
+int apa_pose_l2_loss(int32_t batch, int32_t hw, int32_t keypoints, const float* pose_logits, const float* pose_labels,
+                     const uint8_t* valid, float weight, float* row_loss, float* loss, float* dpose, void* stream);
+
 /* ---- evaluation tail: what eval.py does with the logits.
  * apa_eval_tail: per row, predictions = argmax(logits) (first maximum, eval.py:193) and probs = softmax(logits)
  * (eval.py:197) or sigmoid(logits) for the multi-label losses (:195); with labels, counts[0] += hits and

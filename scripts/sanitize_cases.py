@@ -104,4 +104,12 @@ if which in ("all", "train"):
     err = float(np.abs(aps.cpu().numpy() - ref_aps).max())
     print("%-36s rel err %.2e" % ("eval tail + mAP 19 x 37", err), flush=True)
     assert err <= 1e-12 and np.array_equal(pred.cpu().numpy(), et.predictions(x.cpu().numpy()))
+    from oracle import losses
+    loss, dl = ops.softmax_xent_loss(x, lab, 0.5)
+    pl, dp = ops.pose_l2_loss(torch.randn((3, 25, 5), device="cuda"), torch.zeros((3, 25, 5), device="cuda"),
+                              torch.ones((3, 5), dtype=torch.bool, device="cuda"))
+    torch.cuda.synchronize()
+    ref, _ = losses.softmax_xent(x.cpu().numpy(), lab.cpu().numpy(), 0.5)
+    print("%-36s rel err %.2e" % ("losses", abs(float(loss) - ref) / abs(ref)), flush=True)
+    assert abs(float(loss) - ref) <= 1e-5 * abs(ref)
 print("SANITIZE_CASES_DONE", flush=True)

@@ -10,7 +10,7 @@ if ROOT not in sys.path:
 
 LIB = os.path.join(ROOT, "attentionalpoolingaction_b200", "custom_ops", "libapa_attn_pool.so")
 # test modules that never load the library: the NumPy oracle against the golden vectors and against itself
-PURE_ORACLE = {"test_oracle.py", "test_oracle_backward.py"}
+PURE_ORACLE = {"test_oracle.py", "test_oracle_backward.py"}   # (test_losses / test_eval_tail also hold GPU cases)
 
 
 def pytest_configure(config):

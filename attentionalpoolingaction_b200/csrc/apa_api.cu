@@ -103,7 +103,8 @@ int check_tuning(const ApaTuning* t) {
   if (t->form != APA_FORM_AUTO && t->form != APA_FORM_FLOW && t->form != APA_FORM_CLUSTER) return APA_ERR_UNSUPPORTED;
   if (t->stream_ctas < 0 || t->stream_shape < 0 || t->stream_shape > 2 || t->cluster_shape < 0 || t->cluster_shape > 3)
     return APA_ERR_UNSUPPORTED;
-  for (int i = 0; i < 6; ++i)
+  if (t->tail_smem_kb < 0 || t->tail_smem_kb > 200) return APA_ERR_UNSUPPORTED;
+  for (int i = 0; i < 5; ++i)
     if (t->reserved[i] != 0) return APA_ERR_UNSUPPORTED;
   return APA_OK;
 }

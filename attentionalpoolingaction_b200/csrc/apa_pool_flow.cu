@@ -34,6 +34,7 @@
 #include "apa_common.cuh"
 #include "apa_kernels.h"
 
+#include <algorithm>
 #include <mutex>
 
 namespace apa {
@@ -789,10 +790,15 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   p.fl_ng = ng;
   FKernelFn rfn = (mode == MODE_SOFTMAX) ? &apa_flow_reduce_kernel<true> : &apa_flow_reduce_kernel<false>;
   if (sfn == nullptr || cfn == nullptr) return cudaErrorInvalidValue;
-  const size_t smem1 = stream_smem_bytes(p.C, stages), smem2 = contract_smem_bytes(p.C);
+  const size_t pad = (tuning && tuning->tail_smem_kb > 0) ? size_t(tuning->tail_smem_kb) * 1024 : 0;
+  const size_t smem1 = stream_smem_bytes(p.C, stages), smem2 = std::max(contract_smem_bytes(p.C), pad);
   cudaError_t err = flow_prepare(reinterpret_cast<const void*>(sfn), smem1);
   if (err != cudaSuccess) return err;
-  err = flow_prepare(reinterpret_cast<const void*>(cfn), smem2);
+  err = flow_prepare(reinterpret_cast<const void*>(cfn), size_t(200) * 1024);   // room for any tail_smem_kb
+  if (err != cudaSuccess) return err;
+  err = flow_prepare(reinterpret_cast<const void*>(rfn), size_t(200) * 1024);
+  if (err != cudaSuccess) return err;
+  err = flow_prepare(reinterpret_cast<const void*>(&apa_flow_finish_kernel), size_t(200) * 1024);
   if (err != cudaSuccess) return err;
   p.fl_G = flow_stream_ctas(p.B, p.HW, tuning);
   {
@@ -827,6 +833,7 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   cudaLaunchConfig_t cfgr = {};
   cfgr.gridDim = dim3(p.B, (p.C / 4 + kRThreads - 1) / kRThreads, 1);
   cfgr.blockDim = dim3(kRThreads, 1, 1);
+  cfgr.dynamicSmemBytes = pad;
   cfgr.stream = stream;
   cfgr.attrs = at;
   cfgr.numAttrs = na;
@@ -846,6 +853,7 @@ cudaError_t flow_launch(const FusedParams& p_in, int mode, const ApaTuning* tuni
   cudaLaunchConfig_t cfg3 = {};
   cfg3.gridDim = dim3(unsigned(flow_slices(p.B, p.K, p.F)), 1, 1);
   cfg3.blockDim = dim3(kCThreads, 1, 1);
+  cfg3.dynamicSmemBytes = pad;
   cfg3.stream = stream;
   cfg3.attrs = at;
   cfg3.numAttrs = na;

@@ -106,7 +106,8 @@ class ApaTuning(ctypes.Structure):
         ("gather_wait_lag", ctypes.c_int32),
         ("debug_timestamps", ctypes.c_int32),
         ("debug_cut_tail", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 6),
+        ("tail_smem_kb", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 5),
     ]
 
 
@@ -270,13 +271,14 @@ def make_desc(batch, hw, channels, num_classes, frames=1, rank=1, flags=APA_FLAG
 
 
 def make_tuning(form=APA_FORM_AUTO, stream_ctas=0, stream_shape=0, cluster_shape=0, no_pdl=0, inputs_stable=0,
-                pdl_trigger_lead=0, gather_wait_lag=0, debug_timestamps=0, debug_cut_tail=0):
+                pdl_trigger_lead=0, gather_wait_lag=0, debug_timestamps=0, debug_cut_tail=0, tail_smem_kb=0):
     """ApaTuning (include/apa.h).  `inputs_stable=1` is a promise by the caller: X and the weights were completely
     written before the previous kernel in the stream was launched (lets back-to-back calls overlap)."""
     t = ApaTuning()
     t.form, t.stream_ctas, t.stream_shape, t.cluster_shape = int(form), int(stream_ctas), int(stream_shape), int(cluster_shape)
     t.no_pdl, t.inputs_stable, t.pdl_trigger_lead = int(no_pdl), int(inputs_stable), int(pdl_trigger_lead)
     t.gather_wait_lag, t.debug_timestamps, t.debug_cut_tail = int(gather_wait_lag), int(debug_timestamps), int(debug_cut_tail)
+    t.tail_smem_kb = int(tail_smem_kb)
     return t
 
 

@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--stream-ctas", type=int, default=-1,
                     help="ApaTuning.stream_ctas: STREAM CTAs per call (-1 = this bench's throughput setting, 37 for "
                          "the 32-map batches; 0 = library default, 148 = one per SM = shortest single call)")
+    ap.add_argument("--tail-smem-kb", type=int, default=0, help="ApaTuning.tail_smem_kb (0 = library default)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--streams", type=int, default=6, help="independent batches in flight (1..8)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch")
@@ -345,7 +346,7 @@ def main():
         fl = dict(orc.DEFAULT_FLAGS, **cfg["flags"])
         params = orc.make_params(K, C, flags=fl, seed=42)
         bits, rnk = ops.flags_from_cfg_net(fl)
-        tuning = ops.make_tuning(no_pdl=int(args.no_pdl), form=args.form, stream_ctas=stream_ctas,
+        tuning = ops.make_tuning(no_pdl=int(args.no_pdl), form=args.form, stream_ctas=stream_ctas, tail_smem_kb=args.tail_smem_kb,
                                  inputs_stable=args.inputs_stable, gather_wait_lag=lag)
         P = {k: torch.from_numpy(v) for k, v in params.items()}
         # one op (= one workspace) per in-flight batch: consecutive steps are independent batches

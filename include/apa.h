@@ -130,7 +130,10 @@ typedef struct ApaTuning {
   int32_t debug_timestamps; /* 1 = kernels write a per-CTA clock64 / globaltimer timeline into the workspace     */
   int32_t debug_cut_tail;   /* measurement only (results are then wrong): flow form launches only its first 1, 2 */
                         /*   or 3 kernels (STREAM / + REDUCE / + CONTRACT)                                      */
-  int32_t reserved[6];  /* must be 0                                                                           */
+  int32_t tail_smem_kb; /* flow form: pad the shared memory of the REDUCE / CONTRACT / FINISH CTAs to this many KB so   */
+                        /*   that fewer of them share an SM (they are placed SM by SM and an SM that holds three or    */
+                        /*   more cannot take the next call's STREAM CTA); 0 = library default                        */
+  int32_t reserved[5];  /* must be 0                                                                           */
 } ApaTuning;
 
 /* Library/ABI version (APA_ABI_VERSION of the build). */

@@ -55,6 +55,10 @@ CONFIGS = {
     4: dict(name="configs[4]: full-rank bilinear X^T X (2048^2), synthetic 28x28x2048, 64 images per GPU "
                  "(512 on 8 GPUs), outputs stay local",
             kind="gram", B=64, F=1, HW=HW28, K=0, flags={}, bound="tensor"),
+    # not a BASELINE config: the training caller SURVEY.md section 8(f) row 1 names (train.py:399-420,509-513)
+    5: dict(name="training step of configs[1]'s head (forward with dropout keep 0.2, softmax cross-entropy, backward), "
+                 "batch=32 per GPU",
+            kind="train", B=32, F=1, HW=HW14, K=393, flags={"SINGLE_LAYER_ATT": True}, bound="hbm"),
 }
 
 
@@ -148,6 +152,19 @@ def _cpu_step_fn(cfg, images):
     if cfg["kind"] == "gram":
         X = torch.from_numpy(orc.make_features(images, cfg["HW"], C, seed=42))
         return lambda: torch.matmul(X.transpose(1, 2), X)
+    if cfg["kind"] == "train":
+        from oracle import attn_pool_backward as bwd
+        fl = dict(orc.DEFAULT_FLAGS, **cfg["flags"])
+        P = {k: torch.from_numpy(v).requires_grad_(True) for k, v in orc.make_params(cfg["K"], C, flags=fl, seed=42).items()}
+        X = torch.from_numpy(orc.make_features(images, cfg["HW"], C, seed=42)).requires_grad_(True)
+        mask = torch.from_numpy(bwd.dropout_mask(1, X.shape, 0.2))
+        lab = torch.arange(images) % cfg["K"]
+
+        def step():
+            with torch.enable_grad():
+                logits = bwd.forward_train_torch(X, P, fl, cfg["K"], 1, mask)
+                torch.nn.functional.cross_entropy(logits, lab).backward()
+        return step
     fl = dict(orc.DEFAULT_FLAGS, **cfg["flags"])
     params = {k: torch.from_numpy(v) for k, v in orc.make_params(cfg["K"], C, flags=fl, seed=42).items()}
     X = torch.from_numpy(orc.make_features(images * cfg["F"], cfg["HW"], C, seed=42))   # built ONCE
@@ -177,7 +194,7 @@ def _best_thread_count(fn):
 
 def cpu_sample_images(cfg):
     """Images per CPU call: the whole per-GPU batch for config 1, a bounded slice of it for the heavy ones."""
-    return {1: 32, 2: 16, 3: 4, 4: 2}.get(cfg["id"], cfg["B"] // cfg["F"])
+    return {1: 32, 2: 16, 3: 4, 4: 2, 5: 8}.get(cfg["id"], cfg["B"] // cfg["F"])
 
 
 def cpu_port_rate(cfg, seconds):
@@ -235,6 +252,151 @@ def run_reference(args, cfg, rank):
     }
     print(json.dumps(line), flush=True)
 
+
+
+# ------------------------------------------------------------------------------------------------ training step
+def run_train(args, cfg, rank, world, local_rank, dev, placement):
+    """--config 5: one training step of the head per GPU per step -- apa_attn_pool_fwd_train (dropout keep 0.2),
+    apa_softmax_xent_loss, apa_attn_pool_bwd (dX + every variable's gradient); with N > 1 the variables' gradients
+    are all-reduced (one NCCL all_reduce of 3.2 MB per step: data-parallel SGD, train.py:393-422 clones).  Bytes-based
+    roofline: X read once forward, once backward, dX written once = 3 |X| per step."""
+    import torch
+    import torch.distributed as dist
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    from oracle import attn_pool_oracle as orc, attn_pool_backward as bwd, losses
+    B, HW, K = cfg["B"], cfg["HW"], cfg["K"]
+    x_bytes = B * HW * C * 4
+    hbm_peak, _, peak_src = _peaks()
+    fl = dict(orc.DEFAULT_FLAGS, **cfg["flags"])
+    params = orc.make_params(K, C, flags=fl, seed=42)
+    bits, rnk = ops.flags_from_cfg_net(fl)
+    P = {k: torch.from_numpy(v) for k, v in params.items()}
+    op = ops.AttnPoolTrainOp(P, K, HW, channels=C, rank=rnk, flags=bits, device=dev)
+    nbuf = max(3, -(-2 * L2_BYTES // x_bytes) + 1)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    ring = [torch.relu(torch.randn((B, HW, C), device=dev, generator=g)) for _ in range(nbuf)]
+    labels = (torch.arange(B, device=dev, dtype=torch.int32) * 7) % K
+    dX = torch.empty_like(ring[0])
+    # the variables' gradients live in one flat buffer so that the data-parallel exchange is ONE all_reduce
+    names = [ops.attn_scope(0) + "/weights", ops.attn_scope(0) + "/biases", ops.topdown_scope(0) + "/weights",
+             ops.topdown_scope(0) + "/biases"]
+    shapes = [(C, 1), (1,), (C, K), (K,)]
+    offs, tot = [], 0
+    for sh in shapes:
+        offs.append(tot)
+        tot += (int(torch.tensor(sh).prod()) + 63) // 64 * 64
+    flat = torch.zeros((tot,), device=dev)
+    grads = {n: flat[o:o + int(torch.tensor(sh).prod())].view(sh) for n, o, sh in zip(names, offs, shapes)}
+    logits = torch.empty((B, K), device=dev)
+    state = {"loss": None}
+
+    def step(i):
+        x = ring[i % nbuf]
+        op.forward(x, ops.make_train(0.2, i + 1), logits=logits)
+        state["loss"], dl = ops.softmax_xent_loss(logits, labels)
+        op.backward(dl, want_dX=dX, grads=grads)
+        if world > 1:
+            dist.all_reduce(flat)
+
+    # parity spot-check of what is being timed (4 images, float64 autograd with the same mask)
+    nchk = 4
+    opc = ops.AttnPoolTrainOp(P, K, HW, channels=C, rank=rnk, flags=bits, device=dev)
+    lg = opc.forward(ring[0][:nchk], ops.make_train(0.2, 1))
+    _, dlc = ops.softmax_xent_loss(lg, labels[:nchk])
+    dXc, gc = opc.backward(dlc)
+    torch.cuda.synchronize()
+    Xn = ring[0][:nchk].cpu().numpy()
+    mask = bwd.dropout_mask(1, Xn.shape, 0.2)
+    import numpy as np
+    ref_lg = bwd.forward_train_torch(torch.from_numpy(Xn.astype(np.float64)),
+                                     {k: torch.from_numpy(v.astype(np.float64)) for k, v in params.items()}, fl, K, 1,
+                                     torch.from_numpy(mask.astype(np.float64))).numpy()
+    _, ref_dl = losses.softmax_xent(ref_lg, labels[:nchk].cpu().numpy())
+    ref_dX, ref_g = bwd.backward_autograd(Xn, params, fl, K, ref_dl, dropout_mask=mask)
+    parity = max([orc.rel_err(dXc.cpu().numpy(), ref_dX)] +
+                 [float(np.abs(gc[n].cpu().numpy().reshape(v.shape) - v).max() / max(np.abs(v).max(), 1e-6))
+                  for n, v in ref_g.items()])
+    assert parity <= 1e-4, "bench parity check failed (training): %.3e" % parity
+
+    def timed(n, first=0):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            step(first + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        step(i)
+    ms_total = timed(args.steps, args.warmup)
+    ms_per_step = ms_total / args.steps
+    n_roof = int(min(20000, max(200, 1.0e3 / max(ms_per_step, 1e-3))))
+    ms_roof = timed(n_roof) / n_roof
+    # e2e: pinned host X -> HBM, the step, the loss back to the host
+    xh = torch.relu(torch.randn((B, HW, C), generator=torch.Generator().manual_seed(rank))).pin_memory()
+    stage = torch.empty_like(ring[0])
+    lh = torch.empty((1,)).pin_memory()
+
+    def e2e_step(i):
+        stage.copy_(xh, non_blocking=True)
+        op.forward(stage, ops.make_train(0.2, i + 1), logits=logits)
+        loss, dl = ops.softmax_xent_loss(logits, labels)
+        op.backward(dl, want_dX=dX, grads=grads)
+        if world > 1:
+            dist.all_reduce(flat)
+        lh.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+    for i in range(3):
+        e2e_step(i)
+    t0 = time.perf_counter()
+    for i in range(args.e2e_steps):
+        e2e_step(i)
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    cpu_v, cores, ncalls, cpu_dt, cpu_img = cpu_port_rate(cfg, args.cpu_seconds)
+    achieved = 3 * x_bytes / (ms_roof * 1e-3) / 1e9
+    line = {
+        "metric": "imgs/sec attn-pool head training step 14x14x2048->393 (forward + loss + backward)",
+        "value": world * B * args.steps / (ms_total * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "per_gpu_batch": B, "global_batch": world * B,
+                   "parallelism": ("data-parallel x%d: one NCCL all_reduce of the variables' gradients (%.1f MB) per step"
+                                   % (world, tot * 4 / 1e6)) if world > 1 else "single GPU",
+                   "l2": "inputs rotate over %d buffers x %.1f MB: every step reads HBM" % (nbuf, x_bytes / 1e6),
+                   "launch": "stream launches (12 kernels per step, programmatic dependent launch)",
+                   "dropout": "keep 0.2 on the top-down branch, counter-based mask, a new seed every step",
+                   "parity_rel_err_vs_fp64_autograd": parity},
+        "e2e": {"value": world * B * args.e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": x_bytes,
+                "d2h_bytes_per_step": 4, "steps": args.e2e_steps,
+                "api": "pinned host X -> HBM, apa_attn_pool_fwd_train, apa_softmax_xent_loss, apa_attn_pool_bwd, "
+                       "loss -> host, sync", "host_placement": placement},
+        "gpu_launches": args.steps * 12,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src + ": hbm_gbs",
+                     "kernel": "train_fused_fwd_kernel + bwd_fused_kernel (+ 10 small kernels)",
+                     "us_per_step": ms_roof * 1e3, "algorithmic_bytes_per_step": 3 * x_bytes,
+                     "note": "X read forward, X read backward, dX written: 3 |X| per step", "steps_timed": n_roof},
+        "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "%d images per call, %d calls in %.1f s: PyTorch-CPU fp32 autograd through the "
+                                   "reference graph port, %d threads (best of a sweep)" % (cpu_img, ncalls, cpu_dt, cores)},
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
 
 # ------------------------------------------------------------------------------------------------ host placement
 def bind_to_gpu_numa_node(local_rank):
@@ -313,6 +475,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d" % (args.gpus, world)
+
+    if cfg["kind"] == "train":
+        run_train(args, cfg, rank, world, local_rank, dev, placement)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     B, F, HW, K = cfg["B"], cfg["F"], cfg["HW"], cfg["K"]
     Bv = B // F
@@ -439,10 +608,16 @@ def main():
             torch.cuda.synchronize()
             return (lambda: enqueue(nsteps, with_collective)), "stream"
 
+    align = torch.zeros(1, device=dev)
+
     def timed(run):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            # the host-side barrier releases the ranks tens of microseconds apart; a stream-ordered all_reduce in front
+            # of the start event lines the GPUs up, so that the timed region is not one rank waiting for another's start
+            dist.all_reduce(align)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         run()
@@ -464,6 +639,11 @@ def main():
     run_k, launch_mode = make_runner(args.steps, True)
     run_w()
     torch.cuda.synchronize()
+    warm_extra = 0
+    if launch_mode.startswith("cuda-graph"):      # more warm-up: the first launch of an instantiated graph uploads it
+        run_k()
+        torch.cuda.synchronize()
+        warm_extra = args.steps
     ms_total = timed(run_k)                       # <- the K timed steps
     ms_per_step = ms_total / args.steps
     value = world * Bv * args.steps / (ms_total * 1e-3)
@@ -600,7 +780,7 @@ def main():
                     if world > 1 else "single GPU",
                 "l2": "inputs rotate over %d buffers x %.1f MB (%.0f MB > 2x 126 MB L2): every step reads HBM"
                       % (nbuf, x_bytes / 1e6, nbuf * x_bytes / 1e6),
-                "launch": launch_mode, "plan": plan, "batches_in_flight": nstreams, "stream_ctas_per_call": stream_ctas or 148,
+                "launch": launch_mode, "warmup_steps_run": args.warmup + warm_extra, "plan": plan, "batches_in_flight": nstreams, "stream_ctas_per_call": stream_ctas or 148,
                 "inputs_stable": args.inputs_stable, "parity_rel_err_vs_fp64_oracle": parity,
                 "clock_sampling": "nvidia-smi every 100 ms across warm-up, the K timed steps, the "
                                   "roofline loop (%d steps), the latency and e2e loops" % n_roof,

@@ -104,6 +104,13 @@ struct TrainParams {
   float* d_tb[APA_MAX_RANK];
 };
 
+// 4-byte asynchronous global -> shared copies: a thread issues all of its tile loads back to back (no registers, one
+// round trip) and waits once
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -299,15 +306,17 @@ __global__ void __launch_bounds__(256) train_contract_kernel(TrainParams p) {
   for (int r = 0; r < R; ++r) {
     __syncthreads();
     const float* tw = p.tw[r] + size_t(c0) * K + k0 + lane;
-#pragma unroll 8
-    for (int c = warp; c < cn; c += 8) tws[c * 32 + lane] = kok ? __ldg(tw + size_t(c) * K) : 0.f;
+    for (int c = warp; c < cn; c += 8) {
+      if (kok) cp_async4(tws + c * 32 + lane, tw + size_t(c) * K);
+      else tws[c * 32 + lane] = 0.f;
+    }
 #pragma unroll
     for (int vv = 0; vv < 4; ++vv) {
       const int v = warp * 4 + vv;
       const float* g = p.gv + (size_t(min(v0 + v, V - 1)) * R + r) * C + c0;
-#pragma unroll 4
-      for (int c = lane; c < cn; c += 32) gs[v * cs + c] = g[c];
+      for (int c = lane; c < cn; c += 32) cp_async4(gs + v * cs + c, g + c);
     }
+    cp_async_wait_all();
     __syncthreads();
     const float* g0 = gs + (warp * 4) * cs;
 #pragma unroll 2
@@ -590,17 +599,15 @@ __device__ __forceinline__ void bwd_u_block(const TrainParams& p, float* sm, int
   float* Gs = sm + 32 * Kp;         // [8][K4]
   const float scale = 1.f / (float(p.HW) * float(p.F));
   const int nc = min(32, C - c0);
-#pragma unroll 4
   for (int c = warp; c < nc; c += 8) {
     const float* src = p.tw[r] + size_t(c0 + c) * K;
-#pragma unroll 4
-    for (int k = lane; k < K; k += 32) tws[c * Kp + k] = __ldg(src + k);
+    for (int k = lane; k < K; k += 32) cp_async4(tws + c * Kp + k, src + k);
   }
   {
     const int v = min(v0 + warp, V - 1);
-#pragma unroll 4
-    for (int k = lane; k < K; k += 32) Gs[warp * K4 + k] = p.dlogits[size_t(v) * K + k] * scale;
+    for (int k = lane; k < K; k += 32) cp_async4(Gs + warp * K4 + k, p.dlogits + size_t(v) * K + k);   // scaled at the end
   }
+  cp_async_wait_all();
   __syncthreads();
   if (v0 + warp < V) {
     const float* g = Gs + warp * K4;
@@ -615,13 +622,13 @@ __device__ __forceinline__ void bwd_u_block(const TrainParams& p, float* sm, int
         a1 += g4.y * t[k + 1] + g4.w * t[k + 3];
       }
       for (; k < K; ++k) a0 += g[k] * t[k];
-      p.u[(size_t(v0 + warp) * R + r) * C + c0 + lane] = a0 + a1;
+      p.u[(size_t(v0 + warp) * R + r) * C + c0 + lane] = (a0 + a1) * scale;
     }
     if (bx == 0) {
       float t = 0.f;
       for (int k = lane; k < K; k += 32) t += g[k] * __ldg(p.tb[r] + k);
       t = warp_sum(t);
-      if (lane == 0) p.tt[size_t(v0 + warp) * R + r] = t;
+      if (lane == 0) p.tt[size_t(v0 + warp) * R + r] = t * scale;
     }
   }
 }
@@ -784,14 +791,17 @@ __device__ __forceinline__ void bwd_wgrad_block(const TrainParams& p, float* sm,
     for (int vt = 0; vt < V; vt += 32) {
       __syncthreads();
 #pragma unroll 8
-      for (int vv = 0; vv < 32; ++vv)
-        Gs[vv][threadIdx.x] = (vt + vv < V && k < K) ? __ldg(p.dlogits + size_t(vt + vv) * K + k) : 0.f;
+      for (int vv = 0; vv < 32; ++vv) {
+        if (vt + vv < V && k < K) cp_async4(&Gs[vv][threadIdx.x], p.dlogits + size_t(vt + vv) * K + k);
+        else Gs[vv][threadIdx.x] = 0.f;
+      }
       {  // 32 videos x 8 float4 of channels: one float4 per thread
         const int vv = threadIdx.x >> 3, c4 = threadIdx.x & 7;
         gvs[vv][c4] = (vt + vv < V && c4 * 4 < nc)
                           ? *reinterpret_cast<const float4*>(p.gv + (size_t(vt + vv) * R + r) * C + c0 + c4 * 4)
                           : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      cp_async_wait_all();
       __syncthreads();
 #pragma unroll 4
       for (int vv = 0; vv < 32; ++vv) {

@@ -15,7 +15,7 @@ def test_oracle_losses_match_autograd():
     ref = 0.3 * torch.nn.functional.cross_entropy(xt, torch.tensor(lab), reduction="sum") / 7
     ref.backward()
     loss, grad = losses.softmax_xent(x, lab, 0.3)
-    assert abs(loss - float(ref)) <= 1e-12 and np.abs(grad - xt.grad.numpy()).max() <= 1e-12
+    assert abs(loss - float(ref.detach())) <= 1e-12 and np.abs(grad - xt.grad.numpy()).max() <= 1e-12
     p, h = rng.randn(3, 5, 5, 4), np.maximum(rng.randn(3, 5, 5, 4), 0)
     valid = rng.rand(3, 4) > 0.4
     pt = torch.tensor(p, dtype=torch.float64, requires_grad=True)
@@ -24,7 +24,7 @@ def test_oracle_losses_match_autograd():
     ref = 2.5 * torch.where(torch.tensor(valid), lv, torch.zeros_like(lv)).mean(dim=0).sum()
     ref.backward()
     loss, grad = losses.pose_l2(p, h, valid, 2.5)
-    assert abs(loss - float(ref)) <= 1e-12 and np.abs(grad - pt.grad.numpy()).max() <= 1e-12
+    assert abs(loss - float(ref.detach())) <= 1e-12 and np.abs(grad - pt.grad.numpy()).max() <= 1e-12
 
 
 @pytest.mark.gpu

@@ -164,3 +164,62 @@ def test_shard_features_keeps_videos_whole():
     assert [p.shape[0] for p in parts] == [20, 10]
     with pytest.raises(ValueError):
         dist.shard_features(X, 7, 0, 2)
+
+
+def test_training_network_fn_host_logic(monkeypatch):
+    """get_network_fn(is_training=True) with the CUDA op replaced by a recorder: keep probability from cfg.NET.DROPOUT
+    (nets_factory.py:143-146), a new dropout seed per call, the autograd node hands every variable its gradient."""
+    import torch
+    from attentionalpoolingaction_b200 import config, nets_factory
+    from attentionalpoolingaction_b200.custom_ops import attn_pool_factory as ops
+    seen = []
+
+    class FakeTrainOp(object):
+        def __init__(self, params, num_classes, hw, channels=2048, frames=1, rank=1, flags=0, device=None, **kw):
+            self.K, self.F, self.rank, self.C = num_classes, frames, rank, channels
+
+        def forward(self, X, train=None, logits=None):
+            seen.append((float(train.dropout_keep), int(train.dropout_seed), tuple(X.shape)))
+            self.X = X
+            return torch.zeros(X.shape[0] // self.F, self.K)
+
+        def backward(self, dlogits, want_dX=True, grads=None):
+            g = {}
+            for r in range(self.rank):
+                g[ops.attn_scope(r) + "/weights"] = torch.full((self.C, 1) if r == 0 else (1, 1), 1.0 + r)
+                g[ops.attn_scope(r) + "/biases"] = torch.full((1,), 2.0 + r)
+                g[ops.topdown_scope(r) + "/weights"] = torch.full((self.C, self.K), 3.0 + r)
+                g[ops.topdown_scope(r) + "/biases"] = torch.full((self.K,), 4.0 + r)
+            return (torch.full_like(self.X, 5.0) if want_dX else None), g
+
+    monkeypatch.setattr(ops, "AttnPoolTrainOp", FakeTrainOp)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))   # the shim insists on CUDA variables
+    cfg = config.default_cfg()
+    cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION = True
+    cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION_SINGLE_LAYER_ATT = True
+    cfg.NET.USE_POSE_PRELOGITS_BASED_ATTENTION_RANK = 2
+    C, K = 8, 5
+    params = {}
+    for r in range(2):
+        params[ops.attn_scope(r) + "/weights"] = torch.zeros((C, 1) if r == 0 else (1, 1), requires_grad=True)
+        params[ops.attn_scope(r) + "/biases"] = torch.zeros(1, requires_grad=True)
+        params[ops.topdown_scope(r) + "/weights"] = torch.zeros(C, K, requires_grad=True)
+        params[ops.topdown_scope(r) + "/biases"] = torch.zeros(K, requires_grad=True)
+    fn = nets_factory.get_network_fn("resnet_v1_101", K, 16, cfg, is_training=True, params=params)
+    X = torch.zeros(4, 3, 3, C, requires_grad=True)
+    logits, eps = fn(X)
+    logits.sum().backward()
+    assert seen[-1] == (pytest.approx(0.2), 1, (4, 9, C))                   # DROPOUT = -1 -> keep 0.2; first seed 1
+    assert X.grad.shape == X.shape and float(X.grad[0, 0, 0, 0]) == 5.0
+    assert float(params[ops.topdown_scope(1) + "/weights"].grad[0, 0]) == 4.0
+    assert float(params[ops.attn_scope(1) + "/biases"].grad[0]) == 3.0
+    fn(X)
+    assert seen[-1][1] == 2                                                  # a new mask every call
+    fn(X, dropout_seed=77)
+    assert seen[-1][1] == 77
+    cfg.NET.DROPOUT = 0.3                                                    # keep = 1 - DROPOUT (:145-146)
+    fn2 = nets_factory.get_network_fn("resnet_v1_101", K, 16, cfg, is_training=True, params=params)
+    fn2(X.detach())                                                          # frozen backbone: no dX requested
+    assert seen[-1][0] == pytest.approx(0.7)
+    with pytest.raises(NotImplementedError):
+        fn(X, end_point_names=("PoseLogits",))

@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py — images/s through the attentional-pooling head on synthetic conv5 features.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A *step* is one pass of the hot path over one batch per GPU (weak scaling: every rank owns the same batch).
 `--config` indexes BASELINE.json `configs` (default 1, the configuration the metric is quoted on):
-  1  rank-1 attn pool, 14x14x2048, K=393, batch 32 per GPU                     HBM-bound   (one kernel launch)
+  1  rank-1 attn pool, 14x14x2048, K=393, batch 32 per GPU                     HBM-bound   (4 small launches)
   2  config-003 flags + RANK=2 (chained attention), batch 128 per GPU          tensor-bound (pose GEMM on tcgen05)
   3  HICO K=600, 10-crop: 32 videos x 10 crop maps = 320 maps per GPU          HBM-bound
   4  full second-order X^T X, 28x28x2048, 64 images per GPU, outputs local     tensor-bound
+  5  (not in BASELINE) training step of config 1's head: forward with dropout,  HBM-bound (3 |X| per step)
+     softmax cross-entropy, backward; N>1 all-reduces the gradients
 At N>1 the single all-gather of the logits is fused into the head kernel (NVLink peer stores into a ring of
 gathered buffers + step flags; the consumer is pipelined `--gather-lag` steps behind, `--collective nccl` for a NCCL
 all_gather per step instead).  Consecutive steps are independent batches: `--streams` of them are kept in flight
 (each lane its own workspace) and back-to-back launches on a lane overlap through programmatic dependent launch
-(the inputs are resident in HBM before the timed region, ApaTuning.inputs_stable).  Prints ONE JSON line on rank 0:
+(the inputs are resident in HBM before the timed region, ApaTuning.inputs_stable).  The K timed steps are one CUDA-graph
+replay; the graph is replayed once untimed first (its upload is warm-up) and at N>1 a stream-ordered all_reduce lines
+the ranks up in front of the start event.  Prints ONE JSON line on rank 0:
   value        whole-job images/s with X resident in HBM (CUDA events, max over ranks)
   e2e          same metric through the C-ABI host-buffer entry (apa_attn_pool_fwd_host): pinned host X -> device,
                head, logits -> host, inside the timed region (PCIe-bound: e2e.roofline compares it with a bare copy)

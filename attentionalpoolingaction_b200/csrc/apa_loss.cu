@@ -4,8 +4,8 @@
 // Reference sites: loss.py:72-79 (`tf.losses.softmax_cross_entropy(onehot(labels), logits, weights=action_loss_wt)`:
 // TF 1.1's compute_weighted_loss = sum(w * loss_i) / number of rows for a scalar w != 0) and loss.py:29-70, the
 // un-sampled branch (cfg.TRAIN.LOSS_FN_POSE_SAMPLED = False): per key-point channel c,
-// 0.5 * sum_hw (label - logit)^2 / HW per image, kept where labels_pose_valid[b, c], mean over the batch, summed over
-// the channels, times pose_loss_wt.  (The sampled branch draws a random mask and a differing label size is resized
+// 0.5 * sum_hw (label - logit)^2 / reduce_sum(ones([B, H, W])) per image (the divisor counts the batch too, :55-57), kept
+// where labels_pose_valid[b, c], mean over the batch, summed over the channels, times pose_loss_wt.  (The sampled branch draws a random mask and a differing label size is resized
 // there: both are outside this entry point -- pass labels of the logits' size.)
 //
 // Per-row losses go to a caller-provided buffer and a single CTA adds them in index order: bit-reproducible.
@@ -115,8 +115,9 @@ int apa_pose_l2_loss(int32_t batch, int32_t hw, int32_t keypoints, const float* 
   if (batch <= 0 || hw <= 0 || keypoints <= 0) return APA_ERR_SHAPE;
   if (!pose_logits || !pose_labels || !valid || !row_loss || !loss) return APA_ERR_NULL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // 0.5 * sum / HW per (image, channel), mean over the batch, sum over the channels, times the weight
-  const float scale = 0.5f * weight / (float(hw) * float(batch));
+  // loss.py:56-57 divides the per-image sum by tf.reduce_sum(mask) with mask = ones([B, H, W]) -- B*HW, not HW -- and
+  // :60-64 then takes the mean over the batch: the divisor is B * B * HW (reproduced, not corrected)
+  const float scale = 0.5f * weight / (float(hw) * float(batch) * float(batch));
   pose_rows_kernel<<<batch, 256, 0, st>>>(hw, keypoints, pose_logits, pose_labels, valid, 2.f * scale, row_loss, dpose);
   sum_rows_kernel<<<1, 256, 0, st>>>(batch, row_loss, scale, loss);
   APA_CUDA(cudaGetLastError());

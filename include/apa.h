@@ -272,7 +272,8 @@ int apa_dropout_mask(const ApaTrain* train, size_t count, float* mask, void* str
  * apa_pose_l2_loss: loss.py:29-70 with cfg.TRAIN.LOSS_FN_POSE_SAMPLED off: pose_logits / pose_labels
  *   [batch, hw, keypoints] (end_points['PoseLogits'], nets_factory.py:158-160, and the heat-map labels of the same size),
  *   valid [batch, keypoints] bytes (labels_pose_valid);  loss[0] = weight * sum_c mean_b ( valid[b,c] * 0.5 *
- *   sum_hw (logit - label)^2 / hw );  dpose (optional) = d loss / d pose_logits.  row_loss [batch] scratch.
+ *   sum_hw (logit - label)^2 / (batch * hw) ) -- the reference divides by reduce_sum(ones([B, H, W])), so the batch
+ *   size enters twice (loss.py:55-57,60-64); dpose (optional) = d loss / d pose_logits.  row_loss [batch] scratch.
  * Both add the per-row values in index order (bit-reproducible).                                              */
 int apa_softmax_xent_loss(int32_t rows, int32_t num_classes, const float* logits, const int32_t* labels, float weight,
                           float* row_loss, float* loss, float* dlogits, void* stream);

@@ -19,8 +19,8 @@ def test_oracle_losses_match_autograd():
     p, h = rng.randn(3, 5, 5, 4), np.maximum(rng.randn(3, 5, 5, 4), 0)
     valid = rng.rand(3, 4) > 0.4
     pt = torch.tensor(p, dtype=torch.float64, requires_grad=True)
-    # loss.py:56-64,69-70 written out: per channel, 0.5 * sum / HW, where(valid), mean over the batch, sum, weight
-    lv = 0.5 * ((torch.tensor(h) - pt) ** 2).sum(dim=(1, 2)) / 25
+    # loss.py:55-64,69-70 written out: per channel, 0.5 * sum / (B*HW), where(valid), mean over the batch, sum, weight
+    lv = 0.5 * ((torch.tensor(h) - pt) ** 2).sum(dim=(1, 2)) / (3 * 25)    # reduce_sum(ones([B, H, W])) = 75
     ref = 2.5 * torch.where(torch.tensor(valid), lv, torch.zeros_like(lv)).mean(dim=0).sum()
     ref.backward()
     loss, grad = losses.pose_l2(p, h, valid, 2.5)
@@ -91,3 +91,26 @@ def test_train_step_chain_head_loss_backward():
     assert np.abs(dX.cpu().numpy() - ref_dX).max() <= 1e-4 * np.abs(ref_dX).max()
     for n, g in ref_g.items():
         assert np.abs(grads[n].cpu().numpy().reshape(g.shape) - g).max() <= 1e-4 * max(np.abs(g).max(), 1e-6), n
+
+
+def test_pose_loss_restatement_equals_the_channel_loop_of_the_reference():
+    """loss.py:31-69 walked channel by channel the way the reference writes it (unstack on the last axis, zip,
+    0.5 * reduce_sum(square(.)) / reduce_sum(ones), tf.where(valid, ., 0), reduce_mean, sum of the channel losses),
+    against the vectorised restatement in oracle/losses.py."""
+    from oracle import losses
+    rng = np.random.RandomState(4)
+    B, H, W, Kp = 5, 6, 7, 9
+    logits_pose = rng.randn(B, H, W, Kp)
+    labels_pose = np.maximum(rng.randn(B, H, W, Kp), 0)
+    labels_pose_valid = rng.rand(B, Kp) > 0.5
+    loss_elements = []
+    for c in range(Kp):                                              # :35 zip(channels_valid, channels_logits, channels_labels)
+        v, lbl, lgt = labels_pose_valid[:, c], logits_pose[..., c], labels_pose[..., c]   # (names bound as the reference binds them)
+        mask = np.ones_like(lgt)                                     # :55
+        loss_val = 0.5 * np.square(lbl - lgt).sum(axis=(1, 2)) / mask.sum()   # :56-57 -- NB: mask.sum() counts the BATCH too
+        loss_elements.append(np.mean(np.where(v, loss_val, 0.0)))    # :60-64
+    tot = 1.7 * float(np.sum(loss_elements))                         # :69-70
+    ours, _ = losses.pose_l2(logits_pose, labels_pose, labels_pose_valid, 1.7)
+    # tf.reduce_sum(mask) at :57 sums ones of shape [B, H, W]: the divisor is B*H*W, not H*W -- the restatement (and the
+    # kernel) must divide by it as well
+    assert abs(ours - tot) <= 1e-12, (ours, tot)
